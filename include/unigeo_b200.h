@@ -1,0 +1,144 @@
+/* unigeo_b200 -- C ABI of the B200-native hot path of SunYangtian/UniGeo.
+ *
+ * The reference has no FFI of its own: its hot path is the Python call
+ *     self.pipeline(frames, ...)            /root/reference/model/depthcrafter.py:80-90
+ * into [UPSTREAM] diffusers/DepthCrafter modules.  Each entry
+ * point below names the reference-side call it replaces; INTEGRATION.md shows the
+ * ctypes binding a maintainer adds to model/depthcrafter.py.
+ *
+ * Conventions: every function returns 0 (UG_OK) or a negative ug_status and never throws
+ * across the ABI; ug_last_error() gives the message (thread-local, valid until the next
+ * call on that thread).  The CALLER allocates all inputs/outputs (device pointers, e.g.
+ * torch.Tensor.data_ptr()); the library owns only its weight copies and its workspace.
+ * `stream` is a cudaStream_t passed as void* (torch.cuda.current_stream().cuda_stream).
+ * A ug_ctx is bound to one device and is not thread-safe; distinct contexts are
+ * independent (one per GPU rank).  Batch size is 1 clip per call, as in the reference
+ * (eval.py:33-39 feeds one clip at a time).
+ *
+ * Tensor layouts at the ABI are the upstream ones (fp32, NCHW per frame) so the parity
+ * tests read like upstream code; inside, activations are 16-bit channels-last.
+ */
+#ifndef UNIGEO_B200_H
+#define UNIGEO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UG_VERSION 100
+
+typedef struct ug_ctx ug_ctx;
+
+typedef enum ug_status {
+  UG_OK = 0,
+  UG_ERR_INVALID = -1,   /* bad argument / unsupported shape */
+  UG_ERR_CUDA = -2,      /* CUDA runtime or driver error */
+  UG_ERR_WEIGHT = -3,    /* missing / mis-shaped weight */
+  UG_ERR_WORKSPACE = -4, /* workspace arena exhausted */
+  UG_ERR_STATE = -5      /* call order (finalize / prepare / set_clip_context missing) */
+} ug_status;
+
+typedef enum ug_dtype { UG_F16 = 0, UG_BF16 = 1, UG_F32 = 2 } ug_dtype;
+
+/* Architecture description (mirrors unigeo_b200/config.py). */
+typedef struct ug_model_cfg {
+  int32_t dtype; /* storage/compute type of activations and matrices: UG_F16 or UG_BF16 */
+  /* spatio-temporal UNet */
+  int32_t unet_in_channels, unet_out_channels;
+  int32_t unet_num_blocks;
+  int32_t unet_block_out[4];
+  int32_t unet_heads[4];
+  int32_t unet_layers_per_block;
+  int32_t cross_attention_dim;
+  int32_t addition_time_embed_dim;
+  int32_t num_added_ids;
+  int32_t norm_groups;
+  float eps_cross_attn_block, eps_plain_block, eps_transformer_norm, eps_out_norm, ln_eps;
+  /* temporal-decoder VAE */
+  int32_t vae_in_channels, vae_latent_channels;
+  int32_t vae_num_blocks;
+  int32_t vae_block_out[4];
+  int32_t vae_layers_per_block;
+  int32_t vae_norm_groups;
+  float vae_eps, vae_temporal_eps, vae_scaling_factor;
+  /* Euler / Karras scheduler */
+  float sigma_min, sigma_max, rho;
+} ug_model_cfg;
+
+int ug_version(void);
+const char* ug_last_error(void);
+
+/* Replaces DepthCrafter.__init__'s from_pretrained + .to(cuda) (model/depthcrafter.py:18-31). */
+int ug_ctx_create(ug_ctx** out, int device, const ug_model_cfg* cfg);
+int ug_ctx_destroy(ug_ctx* ctx);
+/* One tensor of a diffusers state_dict ("unet." / "vae." + diffusers key), any of f16/bf16/f32,
+ * original diffusers shape.  Copied and re-laid-out into library storage. */
+int ug_ctx_load_weight(ug_ctx* ctx, const char* key, const void* dev_ptr, int dtype, const int64_t* shape,
+                       int rank, void* stream);
+/* Build fused matrices (QKV, GEGLU-interleaved FF, stacked time-embedding projections). */
+int ug_ctx_finalize(ug_ctx* ctx, void* stream);
+/* Size the workspace for clips of T frames with h x w latents (H = 8h, W = 8w) and precompute
+ * shape-only constants.  Must be called outside CUDA-graph capture. */
+int ug_ctx_prepare(ug_ctx* ctx, int T, int h, int w, void* stream);
+
+/* Per-clip constants of the single-token cross-attentions (SURVEY.md App. A.3 "exact
+ * simplification"): enc fp32 [T][cross_attention_dim], the CLIP image embeddings upstream
+ * passes as encoder_hidden_states (pipeline step 3). */
+int ug_set_clip_context(ug_ctx* ctx, const float* enc, void* stream);
+
+/* Replaces unet(x_in, t, encoder_hidden_states, added_time_ids)[0] (pipeline step 8):
+ * x fp32 [1][T][8][h][w]; added_time_ids HOST float[3]; out fp32 [1][T][4][h][w].
+ * Needs ug_set_clip_context for this clip. */
+int ug_unet_st_forward(ug_ctx* ctx, const float* x, float timestep, const float* added_time_ids_host,
+                       float* out, void* stream);
+
+/* Replaces the whole denoising loop (scheduler.set_timesteps / scale_model_input / unet / step,
+ * pipeline steps 7-8): cond_lat, init_noise, lat_out fp32 [T][4][h][w]; init_noise is the raw
+ * N(0,1) draw (scaled by init_noise_sigma inside). */
+int ug_denoise_clip(ug_ctx* ctx, const float* cond_lat, const float* init_noise,
+                    const float* added_time_ids_host, int steps, float* lat_out, void* stream);
+
+/* Replaces vae.encode(video).latent_dist.mode() (pipeline steps 4-5):
+ * img fp32 [N][3][H][W] in [-1,1]; noise (nullable) fp32 same shape, added * noise_strength;
+ * lat_mean fp32 [N][4][H/8][W/8] (not multiplied by the scaling factor). */
+int ug_vae_encode(ug_ctx* ctx, const float* img, const float* noise, float noise_strength, int N, int H,
+                  int W, float* lat_mean, void* stream);
+
+/* Replaces decode_latents (pipeline step 9): lat fp32 [T][4][h][w] -> img fp32 [T][3][8h][8w];
+ * divides by the scaling factor, decodes in chunks of `chunk` frames. */
+int ug_vae_decode_temporal(ug_ctx* ctx, const float* lat, int T, int h, int w, int chunk, float* img,
+                           void* stream);
+
+/* Kernels launched on behalf of this context since the last reset (bench "gpu_launches"). */
+long long ug_ctx_launch_count(ug_ctx* ctx, int reset);
+/* Bytes of workspace currently reserved. */
+long long ug_ctx_workspace_bytes(ug_ctx* ctx);
+
+/* ---- single-op entry points (kernel parity tests; same kernels the graphs above use) ----
+ * 16-bit tensors are in `dtype` (UG_F16 / UG_BF16), channels-last, dense. */
+/* y[M][N] = x[M][K] W[N][K]^T (+bias) (+res) ; geglu: N = 2*Nout, W rows already interleaved by 64 */
+int ug_op_linear(int dtype, const void* x, long long M, int K, const void* W, int N, const float* bias,
+                 const void* res, int geglu, int out_fp32, void* y, void* stream);
+/* x [Nf][H][W][C], Wt [9][Cout][C] -> y [Nf][H/stride][W/stride][Cout] */
+int ug_op_conv3x3(int dtype, const void* x, int Nf, int H, int W, int C, const void* Wt, int Cout, int stride,
+                  int asym_pad, const float* bias, const void* res, void* y, void* stream);
+/* x [T][P][C], Wt [3][Cout][C]; blend != NULL: y = alpha*blend + (1-alpha)*(conv + bias + res) */
+int ug_op_tconv3(int dtype, const void* x, int T, long long P, int C, const void* Wt, int Cout, int chunk,
+                 const float* bias, const void* res, const void* blend, float alpha, void* y, void* stream);
+/* GroupNorm(+SiLU) over [rows][C1+C2] (x2 nullable), sets of rows_per_set rows */
+int ug_op_groupnorm(int dtype, const void* x1, int C1, const void* x2, int C2, long long rows,
+                    long long rows_per_set, int groups, const float* gamma, const float* beta, float eps,
+                    int silu, void* y, void* stream);
+int ug_op_layernorm(int dtype, const void* x, long long rows, int C, const float* gamma, const float* beta,
+                    float eps, const float* add, int add_div, void* y, void* stream);
+/* qkv [F*N][3C] -> y [F*N][C]; softmax(q k^T / sqrt(dh)) v per frame and head (dh = 64 or C) */
+int ug_op_spatial_attention(int dtype, const void* qkv, int F, int N, int C, int dh, void* y, void* stream);
+/* qkv [T][P][3C] -> y [T][P][C]; attention over T per pixel and 64-wide head */
+int ug_op_temporal_attention(int dtype, const void* qkv, int T, long long P, int C, void* y, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIGEO_B200_H */

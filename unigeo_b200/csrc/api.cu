@@ -1,0 +1,358 @@
+// extern "C" boundary of libunigeo_b200.so (declared in include/unigeo_b200.h).
+#include <cmath>
+#include <cstring>
+#include <functional>
+
+#include "model.cuh"
+
+using namespace ug;
+
+struct ug_ctx {
+  Ctx c;
+  std::unordered_map<std::string, size_t> ws_need;   // call signature -> workspace bytes
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+int guard(const std::function<void()>& f) {
+  try {
+    f();
+    g_err.clear();
+    return UG_OK;
+  } catch (const UgError& e) {
+    g_err = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return UG_ERR_INVALID;
+  }
+}
+
+// Runs `body` twice: once dry to learn the workspace high-water mark (cached per signature),
+// then for real on `stream`.
+void run_sized(ug_ctx* u, const std::string& sig, void* stream, const std::function<void(Ctx&)>& body) {
+  Ctx& c = u->c;
+  UG_CUDA(cudaSetDevice(c.device));
+  auto it = u->ws_need.find(sig);
+  if (it == u->ws_need.end()) {
+    c.dry = true; c.ws.dry = true; c.ws.off = 0; c.ws.peak = 0;
+    try { body(c); } catch (...) { c.dry = false; c.ws.dry = false; throw; }
+    c.dry = false; c.ws.dry = false;
+    it = u->ws_need.emplace(sig, c.ws.peak + (1 << 20)).first;
+  }
+  c.ensure_workspace(it->second);
+  c.ws.off = 0;
+  c.stream = reinterpret_cast<cudaStream_t>(stream);
+  body(c);
+}
+
+std::vector<double> karras_sigmas(const ug_model_cfg& g, int steps) {
+  std::vector<double> s;
+  const double lo = std::pow((double)g.sigma_min, 1.0 / g.rho), hi = std::pow((double)g.sigma_max, 1.0 / g.rho);
+  for (int i = 0; i < steps; ++i) {
+    const double r = steps > 1 ? (double)i / (steps - 1) : 0.0;
+    s.push_back(std::pow(hi + r * (lo - hi), (double)g.rho));
+  }
+  s.push_back(0.0);
+  return s;
+}
+
+thread_local ug_ctx* g_scratch[2] = {nullptr, nullptr};
+ug_ctx* scratch_ctx(int dtype) {
+  UG_CHECK(dtype == UG_F16 || dtype == UG_BF16, UG_ERR_INVALID, "dtype must be UG_F16 or UG_BF16");
+  if (!g_scratch[dtype]) {
+    g_scratch[dtype] = new ug_ctx();
+    Ctx& c = g_scratch[dtype]->c;
+    c.fmt = dtype;
+    c.cfg.dtype = dtype;
+    c.cfg.norm_groups = 32;
+    UG_CUDA(cudaGetDevice(&c.device));
+  }
+  return g_scratch[dtype];
+}
+
+}  // namespace
+
+extern "C" {
+
+int ug_version(void) { return UG_VERSION; }
+const char* ug_last_error(void) { return g_err.c_str(); }
+
+int ug_ctx_create(ug_ctx** out, int device, const ug_model_cfg* cfg) {
+  return guard([&] {
+    UG_CHECK(out && cfg, UG_ERR_INVALID, "null argument");
+    UG_CHECK(cfg->dtype == UG_F16 || cfg->dtype == UG_BF16, UG_ERR_INVALID, "cfg.dtype must be UG_F16 or UG_BF16");
+    UG_CHECK(cfg->unet_num_blocks <= 4 && cfg->vae_num_blocks <= 4, UG_ERR_INVALID, "at most 4 blocks");
+    UG_CUDA(cudaSetDevice(device));
+    int major = 0;
+    UG_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device));
+    UG_CHECK(major == 10, UG_ERR_CUDA, "unigeo_b200 kernels are built for sm_100a only (B200)");
+    ug_ctx* u = new ug_ctx();
+    u->c.device = device;
+    u->c.cfg = *cfg;
+    u->c.fmt = cfg->dtype;
+    *out = u;
+  });
+}
+
+int ug_ctx_destroy(ug_ctx* u) {
+  return guard([&] {
+    if (!u) return;
+    cudaSetDevice(u->c.device);
+    cudaDeviceSynchronize();
+    for (void* p : u->c.owned) cudaFree(p);
+    if (u->c.ws.base) cudaFree(u->c.ws.base);
+    delete u->c.unet;
+    delete u->c.vae;
+    delete u;
+  });
+}
+
+int ug_ctx_load_weight(ug_ctx* u, const char* key, const void* dev_ptr, int dtype, const int64_t* shape, int rank,
+                       void* stream) {
+  return guard([&] {
+    UG_CHECK(u && key && dev_ptr && shape, UG_ERR_INVALID, "null argument");
+    UG_CHECK(rank >= 1 && rank <= 5, UG_ERR_WEIGHT, std::string("unsupported weight rank: ") + key);
+    UG_CHECK(dtype >= 0 && dtype <= 2, UG_ERR_INVALID, "bad dtype");
+    Ctx& c = u->c;
+    UG_CUDA(cudaSetDevice(c.device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Weight w;
+    long long n = 1;
+    for (int i = 0; i < rank; ++i) n *= shape[i];
+    w.numel = n;
+    if (rank == 1) {
+      w.is_f32 = 1;
+      w.cout = (int)shape[0];
+      w.p = c.dmalloc((size_t)n * 4);
+      UG_CUDA(launch_convert_f32(dev_ptr, dtype, reinterpret_cast<float*>(w.p), n, st));
+      if (n <= 16) {
+        w.host.resize(n);
+        UG_CUDA(cudaStreamSynchronize(st));
+        UG_CUDA(cudaMemcpy(w.host.data(), w.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+      }
+    } else {
+      w.cout = (int)shape[0];
+      w.cin = (int)shape[1];
+      w.taps = 1;
+      for (int i = 2; i < rank; ++i) w.taps *= (int)shape[i];
+      UG_CHECK(w.taps == 1 || w.taps == 3 || w.taps == 9, UG_ERR_WEIGHT, std::string("unsupported kernel size: ") + key);
+      w.cin_pad = (w.cin + 7) & ~7;
+      const size_t bytes = (size_t)w.taps * w.cout * w.cin_pad * 2;
+      w.p = c.dmalloc(bytes);
+      if (w.cin_pad != w.cin) UG_CUDA(cudaMemsetAsync(w.p, 0, bytes, st));
+      UG_CUDA(launch_convert_weight(dev_ptr, dtype, w.p, w.cout, w.cin, w.cin_pad, w.taps, c.fmt, st));
+      w.cin = w.cin_pad;
+    }
+    c.weights[key] = w;
+    c.finalized = false;
+  });
+}
+
+int ug_ctx_finalize(ug_ctx* u, void* stream) {
+  return guard([&] {
+    UG_CHECK(u, UG_ERR_INVALID, "null ctx");
+    Ctx& c = u->c;
+    UG_CUDA(cudaSetDevice(c.device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unet_finalize(c, st);
+    vae_finalize(c, st);
+    UG_CUDA(cudaStreamSynchronize(st));
+    c.finalized = true;
+  });
+}
+
+int ug_ctx_prepare(ug_ctx* u, int T, int h, int w, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_ctx_prepare");
+    UG_CHECK(T >= 1 && T <= 64 && h >= 1 && w >= 1, UG_ERR_INVALID, "need 1 <= T <= 64 frames");
+    Ctx& c = u->c;
+    UG_CUDA(cudaSetDevice(c.device));
+    if (c.T != T || c.h != h || c.w != w) u->ws_need.clear();
+    c.T = T; c.h = h; c.w = w;
+    c.stream = reinterpret_cast<cudaStream_t>(stream);
+    unet_prepare(c, T, c.stream);
+    UG_CUDA(cudaStreamSynchronize(c.stream));
+  });
+}
+
+int ug_set_clip_context(ug_ctx* u, const float* enc, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && enc, UG_ERR_INVALID, "null argument");
+    run_sized(u, "clipctx", stream, [&](Ctx& c) {
+      if (c.dry) { c.allocf((long long)c.T * 4096); return; }
+      unet_set_clip_context(c, enc, c.stream);
+    });
+  });
+}
+
+int ug_unet_st_forward(ug_ctx* u, const float* x, float timestep, const float* ids, float* out, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && x && ids && out, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.T > 0, UG_ERR_STATE, "ug_ctx_prepare must precede ug_unet_st_forward");
+    run_sized(u, "unet", stream, [&](Ctx& c) {
+      const long long hw = (long long)c.h * c.w, tok = hw * c.T;
+      const int Ci = c.cfg.unet_in_channels, Co = c.cfg.unet_out_channels;
+      UG_CHECK(Ci == 8 && Co == 4, UG_ERR_INVALID, "UNet I/O must be 8 -> 4 channels");
+      void* x16 = c.alloc16(tok * Ci);
+      float* v = c.allocf(tok * Co);
+      if (!c.dry)
+        op_check(c, launch_nchw_to_nhwc(x, nullptr, 0.f, 1.f, 0.f, c.T, Ci, c.h, c.w, Ci, x16, c.fmt, c.stream),
+                 "nchw_to_nhwc");
+      unet_forward(c, x16, timestep, ids, v);
+      if (!c.dry) op_check(c, launch_f32_nhwc_to_nchw(v, c.T, hw, Co, 1.f, out, c.stream), "f32 swap");
+    });
+  });
+}
+
+int ug_denoise_clip(ug_ctx* u, const float* cond_lat, const float* init_noise, const float* ids, int steps,
+                    float* lat_out, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && cond_lat && init_noise && ids && lat_out, UG_ERR_INVALID, "null argument");
+    UG_CHECK(steps >= 1 && steps <= 1000, UG_ERR_INVALID, "steps out of range");
+    UG_CHECK(u->c.T > 0, UG_ERR_STATE, "ug_ctx_prepare must precede ug_denoise_clip");
+    const std::vector<double> sig = karras_sigmas(u->c.cfg, steps);
+    run_sized(u, "denoise", stream, [&](Ctx& c) {
+      const long long hw = (long long)c.h * c.w, tok = hw * c.T;
+      void* cond16 = c.alloc16(tok * 4);
+      float* lat = c.allocf(tok * 4);
+      void* x16 = c.alloc16(tok * 8);
+      float* v = c.allocf(tok * 4);
+      const size_t mk = c.ws.mark();
+      if (!c.dry) {
+        op_check(c, launch_nchw_to_nhwc(cond_lat, nullptr, 0.f, 1.f, 0.f, c.T, 4, c.h, c.w, 4, cond16, c.fmt,
+                                        c.stream), "cond latents");
+        const float s0 = (float)std::sqrt(sig[0] * sig[0] + 1.0);   // init_noise_sigma ("leading" spacing)
+        op_check(c, launch_f32_nchw_to_nhwc(init_noise, c.T, hw, 4, s0, lat, c.stream), "init latents");
+      }
+      const int n_iter = c.dry ? 1 : steps;
+      for (int i = 0; i < n_iter; ++i) {
+        c.ws.release(mk);
+        const float sg = (float)sig[i], sn = (float)sig[i + 1];
+        if (!c.dry) op_check(c, launch_build_unet_input(lat, cond16, sg, tok, x16, c.fmt, c.stream), "unet input");
+        unet_forward(c, x16, (float)(0.25 * std::log(sig[i])), ids, v);
+        if (!c.dry) op_check(c, launch_euler_step(lat, v, sg, sn, tok * 4, c.stream), "euler step");
+      }
+      if (!c.dry) op_check(c, launch_f32_nhwc_to_nchw(lat, c.T, hw, 4, 1.f, lat_out, c.stream), "latents out");
+    });
+  });
+}
+
+int ug_vae_encode(ug_ctx* u, const float* img, const float* noise, float noise_strength, int N, int H, int W,
+                  float* lat_mean, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && img && lat_mean, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_vae_encode");
+    UG_CHECK(N >= 1 && H % 8 == 0 && W % 8 == 0, UG_ERR_INVALID, "H and W must be multiples of 8");
+    const std::string sig = "enc:" + std::to_string(N) + "x" + std::to_string(H) + "x" + std::to_string(W);
+    run_sized(u, sig, stream, [&](Ctx& c) {
+      void* img16 = c.alloc16((long long)N * H * W * 8);
+      if (!c.dry)
+        op_check(c, launch_nchw_to_nhwc(img, noise, noise_strength, 1.f, 0.f, N, c.cfg.vae_in_channels, H, W, 8,
+                                        img16, c.fmt, c.stream), "image in");
+      vae_encode(c, img16, N, H, W, lat_mean);
+    });
+  });
+}
+
+int ug_vae_decode_temporal(ug_ctx* u, const float* lat, int T, int h, int w, int chunk, float* img, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && lat && img, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_vae_decode_temporal");
+    UG_CHECK(T >= 1 && chunk >= 1, UG_ERR_INVALID, "T and chunk must be positive");
+    const std::string sig = "dec:" + std::to_string(T) + "x" + std::to_string(h) + "x" + std::to_string(w) + "/" +
+                            std::to_string(chunk);
+    run_sized(u, sig, stream, [&](Ctx& c) {
+      void* z16 = c.alloc16((long long)T * h * w * 8);
+      if (!c.dry)
+        op_check(c, launch_nchw_to_nhwc(lat, nullptr, 0.f, 1.0f / c.cfg.vae_scaling_factor, 0.f, T,
+                                        c.cfg.vae_latent_channels, h, w, 8, z16, c.fmt, c.stream), "latents in");
+      vae_decode(c, z16, T, h, w, chunk, img);
+    });
+  });
+}
+
+long long ug_ctx_launch_count(ug_ctx* u, int reset) {
+  if (!u) return -1;
+  const long long n = u->c.launches;
+  if (reset) u->c.launches = 0;
+  return n;
+}
+long long ug_ctx_workspace_bytes(ug_ctx* u) { return u ? (long long)u->c.ws.cap : -1; }
+
+// ------------------------------------------------------------------ single ops
+int ug_op_linear(int dtype, const void* x, long long M, int K, const void* W, int N, const float* bias,
+                 const void* res, int geglu, int out_fp32, void* y, void* stream) {
+  return guard([&] {
+    ug_ctx* u = scratch_ctx(dtype);
+    u->c.stream = reinterpret_cast<cudaStream_t>(stream);
+    Epi e;
+    const int nout = geglu ? N / 2 : N;
+    e.out = y; e.ldc = nout; e.out_fp32 = out_fp32; e.bias = bias; e.res = res; e.ldr = nout; e.geglu = geglu;
+    op_linear(u->c, x, M, K, K, W, N, e);
+  });
+}
+
+int ug_op_conv3x3(int dtype, const void* x, int Nf, int H, int W, int C, const void* Wt, int Cout, int stride,
+                  int asym_pad, const float* bias, const void* res, void* y, void* stream) {
+  return guard([&] {
+    ug_ctx* u = scratch_ctx(dtype);
+    u->c.stream = reinterpret_cast<cudaStream_t>(stream);
+    Epi e;
+    e.out = y; e.ldc = Cout; e.bias = bias; e.res = res; e.ldr = Cout;
+    op_conv3x3(u->c, x, Nf, H, W, C, Wt, Cout, stride, asym_pad, e);
+  });
+}
+
+int ug_op_tconv3(int dtype, const void* x, int T, long long P, int C, const void* Wt, int Cout, int chunk,
+                 const float* bias, const void* res, const void* blend, float alpha, void* y, void* stream) {
+  return guard([&] {
+    ug_ctx* u = scratch_ctx(dtype);
+    u->c.stream = reinterpret_cast<cudaStream_t>(stream);
+    Epi e;
+    e.out = y; e.ldc = Cout; e.bias = bias; e.res = res; e.ldr = Cout; e.blend = blend; e.ldb = Cout; e.alpha = alpha;
+    op_tconv3(u->c, x, T, P, C, Wt, Cout, chunk, e);
+  });
+}
+
+int ug_op_groupnorm(int dtype, const void* x1, int C1, const void* x2, int C2, long long rows,
+                    long long rows_per_set, int groups, const float* gamma, const float* beta, float eps, int silu,
+                    void* y, void* stream) {
+  return guard([&] {
+    ug_ctx* u = scratch_ctx(dtype);
+    u->c.cfg.norm_groups = groups;
+    run_sized(u, "gn:" + std::to_string(rows / rows_per_set) + ":" + std::to_string(groups), stream, [&](Ctx& c) {
+      op_gn(c, x1, C1, x2, C2, rows, rows_per_set, gamma, beta, eps, silu, y);
+    });
+  });
+}
+
+int ug_op_layernorm(int dtype, const void* x, long long rows, int C, const float* gamma, const float* beta,
+                    float eps, const float* add, int add_div, void* y, void* stream) {
+  return guard([&] {
+    ug_ctx* u = scratch_ctx(dtype);
+    u->c.stream = reinterpret_cast<cudaStream_t>(stream);
+    op_layernorm(u->c, x, rows, C, gamma, beta, eps, add, add_div, y);
+  });
+}
+
+int ug_op_spatial_attention(int dtype, const void* qkv, int F, int N, int C, int dh, void* y, void* stream) {
+  return guard([&] {
+    ug_ctx* u = scratch_ctx(dtype);
+    const std::string sig = "attn:" + std::to_string(F) + ":" + std::to_string(N) + ":" + std::to_string(C) + ":" +
+                            std::to_string(dh);
+    run_sized(u, sig, stream, [&](Ctx& c) { op_spatial_attention(c, qkv, F, N, C, dh, y); });
+  });
+}
+
+int ug_op_temporal_attention(int dtype, const void* qkv, int T, long long P, int C, void* y, void* stream) {
+  return guard([&] {
+    ug_ctx* u = scratch_ctx(dtype);
+    u->c.stream = reinterpret_cast<cudaStream_t>(stream);
+    op_temporal_attention(u->c, qkv, y, T, P, C);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,132 @@
+// Library context: device, element format, weight store, bump-arena workspace and the
+// op wrappers that the model graphs (unet.cu / vae.cu) are written in.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/unigeo_b200.h"
+#include "kernels.cuh"
+#include "tapgemm.cuh"
+
+namespace ug {
+
+struct UgError : std::runtime_error {
+  int code;
+  UgError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define UG_CUDA(expr)                                                                            \
+  do {                                                                                           \
+    int _e = (int)(expr);                                                                        \
+    if (_e != 0)                                                                                 \
+      throw ::ug::UgError(UG_ERR_CUDA, std::string(#expr) + " failed: " +                        \
+                                           cudaGetErrorString((cudaError_t)_e) + " (" +          \
+                                           std::to_string(_e) + ")");                            \
+  } while (0)
+
+#define UG_CHECK(cond, code, msg)                                        \
+  do {                                                                   \
+    if (!(cond)) throw ::ug::UgError((code), std::string(msg));          \
+  } while (0)
+
+// Bump allocator over one cudaMalloc'd slab.  In dry mode nothing is backed: addresses
+// are offsets from a fake base and only the high-water mark matters.
+struct Arena {
+  char* base = nullptr;
+  size_t cap = 0, off = 0, peak = 0;
+  bool dry = false;
+  void* alloc(size_t bytes) {
+    size_t a = (off + 255) & ~size_t(255);
+    off = a + bytes;
+    if (off > peak) peak = off;
+    if (!dry && off > cap)
+      throw UgError(UG_ERR_WORKSPACE, "workspace arena exhausted (" + std::to_string(off) + " > " +
+                                          std::to_string(cap) + " bytes)");
+    return (dry ? reinterpret_cast<char*>(uintptr_t(4096)) : base) + a;
+  }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }
+};
+
+struct Weight {
+  void* p = nullptr;             // device storage (library-owned)
+  int is_f32 = 0;                // 1: fp32 vector/scalars; 0: 16-bit matrix in ctx fmt
+  int taps = 1, cout = 0, cin = 0, cin_pad = 0;   // matrix: [taps][cout][cin_pad]
+  long long numel = 0;
+  std::vector<float> host;       // small tensors (mix_factor) mirrored on the host
+};
+
+struct Epi {                     // epilogue description for tapgemm-backed ops
+  void* out = nullptr;
+  long long ldc = 0;
+  int out_fp32 = 0;
+  const float* bias = nullptr;
+  const float* fbias = nullptr;
+  int fbias_ld = 0, fbias_div = 1;
+  const void* res = nullptr;
+  long long ldr = 0;
+  const void* blend = nullptr;
+  long long ldb = 0;
+  float alpha = 0.f;
+  float scale = 1.f;
+  int geglu = 0;
+};
+
+struct UNetModel;
+struct VaeModel;
+
+struct Ctx {
+  int device = 0;
+  int fmt = 1;                   // 0 fp16, 1 bf16
+  ug_model_cfg cfg{};
+  std::unordered_map<std::string, Weight> weights;
+  Arena ws;                      // activations / temporaries
+  bool dry = false;              // size-only pass: no launches
+  cudaStream_t stream = nullptr; // stream of the current API call
+  long long launches = 0;        // kernels launched since the last reset (bench "gpu_launches")
+  UNetModel* unet = nullptr;
+  VaeModel* vae = nullptr;
+  bool finalized = false;
+  // prepared clip shape
+  int T = 0, h = 0, w = 0;
+  std::vector<void*> owned;      // cudaMalloc'd blocks to free at destroy
+
+  void* dmalloc(size_t bytes);
+  const Weight& W(const std::string& key) const;
+  bool has(const std::string& key) const { return weights.count(key) != 0; }
+  const float* F(const std::string& key) const;     // fp32 vector
+  const void* M(const std::string& key) const;      // 16-bit matrix
+  void* alloc16(long long elems) { return ws.alloc((size_t)elems * 2); }
+  float* allocf(long long elems) { return reinterpret_cast<float*>(ws.alloc((size_t)elems * 4)); }
+  void ensure_workspace(size_t bytes);
+};
+
+// ---- op wrappers (all enqueue on ctx.stream; no-ops in dry mode) ----------------------
+void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const void* Wm, int N, const Epi& e);
+// x: [Nf][H][W][C] dense.  stride 1: pad 1.  stride 2: pad 1 (asym=0) or pad (0,1,0,1) (asym=1).
+void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* Wm, int Cout, int stride,
+                int asym, const Epi& e);
+// x: [T][P][C]; (3,1,1) conv over T with zero padding inside each chunk of `chunk` frames.
+void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm, int Cout, int chunk,
+               const Epi& e);
+// self-attention over N tokens per frame from a fused [F*N][3C] q|k|v buffer, head_dim dh -> out [F*N][C]
+void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, void* out);
+
+void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
+           const float* gamma, const float* beta, float eps, int silu, void* y);
+void op_layernorm(Ctx& c, const void* x, long long rows, int C, const float* g, const float* b, float eps,
+                  const float* add, int add_div, void* y);
+void op_temporal_attention(Ctx& c, const void* qkv, void* out, int T, long long P, int C);
+void op_upsample2x(Ctx& c, const void* x, void* y, int N, int H, int W, int C);
+void op_concat(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long rows, void* y);
+void op_gemv(Ctx& c, const void* Wm, const float* b, const float* addend, const float* x, float* out, int M,
+             int N, int K, int silu_in, int silu_out);
+void op_check(Ctx& c, int err, const char* what);
+
+}  // namespace ug

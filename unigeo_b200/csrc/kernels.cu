@@ -1,0 +1,692 @@
+// HBM-bound kernels (see kernels.cuh).  128-bit accesses, fp32 math, 16-bit storage.
+#include "kernels.cuh"
+#include "ptx.cuh"
+
+namespace ug {
+namespace {
+
+#define UG_DISPATCH_FMT(fmt, ...)                         \
+  do {                                                    \
+    if ((fmt) == 1) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { using T = __half; __VA_ARGS__; }               \
+  } while (0)
+
+template <typename T> __device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  float2 a = Elem<T>::unpack2(u.x), b = Elem<T>::unpack2(u.y), c = Elem<T>::unpack2(u.z), d = Elem<T>::unpack2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+template <typename T> __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 u;
+  u.x = Elem<T>::pack2(f[0], f[1]); u.y = Elem<T>::pack2(f[2], f[3]);
+  u.z = Elem<T>::pack2(f[4], f[5]); u.w = Elem<T>::pack2(f[6], f[7]);
+  return u;
+}
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// vector c8 of the (virtually concatenated) row
+__device__ __forceinline__ const uint4* cat_ptr(const void* x1, int nv1, const void* x2, int nv2, long long row,
+                                                int c8) {
+  return c8 < nv1 ? reinterpret_cast<const uint4*>(x1) + row * nv1 + c8
+                  : reinterpret_cast<const uint4*>(x2) + row * nv2 + (c8 - nv1);
+}
+
+// ------------------------------------------------------------------ GroupNorm statistics
+template <typename T>
+__global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
+                                long long rows_per_set, long long chunk_rows, int G, int cs,
+                                float* __restrict__ stats) {
+  __shared__ float s_sum[64], s_sq[64];
+  const int nvec = nv1 + nv2;
+  const int rpb = blockDim.x / nvec;
+  const int c8 = threadIdx.x % nvec;
+  const int rr = threadIdx.x / nvec;
+  const long long set = blockIdx.y;
+  const long long r_begin = (long long)blockIdx.x * chunk_rows;
+  long long r_end = r_begin + chunk_rows;
+  if (r_end > rows_per_set) r_end = rows_per_set;
+  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
+  __syncthreads();
+  float a[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
+  if (rr < rpb) {
+    for (long long r = r_begin + rr; r < r_end; r += rpb) {
+      uint4 u = __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r, c8));
+      float f[8];
+      unpack8<T>(u, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] += f[j] * f[j]; }
+    }
+    // fold the 8 channels into their groups (runs of equal group index are merged first)
+    int g_prev = (c8 * 8) / cs;
+    float sa = 0.f, sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int g = (c8 * 8 + j) / cs;
+      if (g != g_prev) {
+        atomicAdd(&s_sum[g_prev], sa); atomicAdd(&s_sq[g_prev], sq);
+        sa = 0.f; sq = 0.f; g_prev = g;
+      }
+      sa += a[j]; sq += q[j];
+    }
+    atomicAdd(&s_sum[g_prev], sa); atomicAdd(&s_sq[g_prev], sq);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    atomicAdd(&stats[(set * G + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
+    atomicAdd(&stats[(set * G + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+  }
+}
+
+// ------------------------------------------------------------------ GroupNorm apply (+SiLU)
+template <typename T>
+__global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
+                                long long rows_per_set, long long chunk_rows, int G, int cs,
+                                const float* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float eps, int silu, void* __restrict__ y) {
+  extern __shared__ float s_ab[];   // [C] scale, [C] shift
+  const int nvec = nv1 + nv2;
+  const int C = nvec * 8;
+  float* s_a = s_ab;
+  float* s_b = s_ab + C;
+  const long long set = blockIdx.y;
+  const float inv_cnt = 1.0f / ((float)rows_per_set * (float)cs);
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cs;
+    const float mean = stats[(set * G + g) * 2 + 0] * inv_cnt;
+    float var = stats[(set * G + g) * 2 + 1] * inv_cnt - mean * mean;
+    var = fmaxf(var, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    const float ga = gamma[c] * rstd;
+    s_a[c] = ga;
+    s_b[c] = beta[c] - mean * ga;
+  }
+  __syncthreads();
+  const long long r_begin = (long long)blockIdx.x * chunk_rows;
+  long long r_end = r_begin + chunk_rows;
+  if (r_end > rows_per_set) r_end = rows_per_set;
+  const long long n_items = (r_end - r_begin) * nvec;
+  uint4* yo = reinterpret_cast<uint4*>(y);
+  for (long long i = threadIdx.x; i < n_items; i += blockDim.x) {
+    const long long r = set * rows_per_set + r_begin + i / nvec;
+    const int c8 = (int)(i % nvec);
+    uint4 u = __ldg(cat_ptr(x1, nv1, x2, nv2, r, c8));
+    float f[8];
+    unpack8<T>(u, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float v = f[j] * s_a[c8 * 8 + j] + s_b[c8 * 8 + j];
+      f[j] = silu ? silu_f(v) : v;
+    }
+    yo[r * nvec + c8] = pack8<T>(f);
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (warp per row)
+template <typename T>
+__global__ void layernorm_kernel(const void* __restrict__ x, long long rows, int C,
+                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                 const float* __restrict__ add, int add_div, void* __restrict__ y) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = C >> 3;
+  const uint4* xr = reinterpret_cast<const uint4*>(x) + row * nvec;
+  const float* addr = add ? add + (row / add_div) * C : nullptr;
+  float f[8][8];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nvec) {
+      uint4 u = __ldg(xr + i);
+      unpack8<T>(u, f[k]);
+      if (addr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[k][j] += __ldg(addr + i * 8 + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += f[k][j];
+    }
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[k][j] - mean; v += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
+  uint4* yr = reinterpret_cast<uint4*>(y) + row * nvec;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = lane + 32 * k;
+    if (i < nvec) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        o[j] = (f[k][j] - mean) * rstd * __ldg(gamma + i * 8 + j) + __ldg(beta + i * 8 + j);
+      yr[i] = pack8<T>(o);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ row softmax (block per row)
+template <typename T, int VPT>
+__global__ void softmax_rows_kernel(void* __restrict__ s, long long rows, int n, float scale_log2e) {
+  __shared__ float red[32];
+  const long long row = blockIdx.x;
+  const int nvec = n >> 3;
+  uint4* p = reinterpret_cast<uint4*>(s) + row * nvec;
+  float f[VPT][8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int i = threadIdx.x + k * blockDim.x;
+    if (i < nvec) {
+      unpack8<T>(p[i], f[k]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { f[k][j] *= scale_log2e; m = fmaxf(m, f[k][j]); }
+    }
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < nw; ++w) m = fmaxf(m, red[w]);
+  __syncthreads();
+  float sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int i = threadIdx.x + k * blockDim.x;
+    if (i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { f[k][j] = exp2f(f[k][j] - m); sum += f[k][j]; }
+    }
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = 0.f;
+  for (int w = 0; w < nw; ++w) sum += red[w];
+  const float inv = 1.0f / sum;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int i = threadIdx.x + k * blockDim.x;
+    if (i < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[k][j] *= inv;
+      p[i] = pack8<T>(f[k]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ temporal attention
+// one warp per (pixel, head); lane j owns query frame j (and j+32 when T > 32)
+template <typename T, int TMAX>
+__global__ void temporal_attn_kernel(const void* __restrict__ qkv, void* __restrict__ out, int Tn, long long P,
+                                     int C, float scale_log2e) {
+  extern __shared__ uint32_t sm_kv[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int heads = C >> 6;
+  const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
+  if (item >= P * heads) return;
+  const long long p = item / heads;
+  const int h = (int)(item % heads);
+  uint32_t* Ks = sm_kv + (size_t)warp * Tn * 64;       // [T][32] packed pairs
+  uint32_t* Vs = Ks + (size_t)Tn * 32;
+  const uint32_t* base = reinterpret_cast<const uint32_t*>(qkv);
+  const long long row_words = (long long)3 * C / 2;
+  for (int i = 0; i < Tn; ++i) {
+    const long long tok = (long long)i * P + p;
+    Ks[i * 32 + lane] = __ldg(base + tok * row_words + (C + h * 64) / 2 + lane);
+    Vs[i * 32 + lane] = __ldg(base + tok * row_words + (2 * C + h * 64) / 2 + lane);
+  }
+  __syncwarp();
+  for (int j = lane; j < Tn; j += 32) {
+    const long long tok = (long long)j * P + p;
+    const uint4* qp = reinterpret_cast<const uint4*>(base + tok * row_words + (h * 64) / 2);
+    float q[64];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float f[8];
+      unpack8<T>(__ldg(qp + k), f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) q[k * 8 + e] = f[e] * scale_log2e;
+    }
+    float sc[TMAX];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+      if (i < Tn) {
+        float acc = 0.f;
+#pragma unroll
+        for (int d2 = 0; d2 < 32; ++d2) {
+          float2 kk = Elem<T>::unpack2(Ks[i * 32 + d2]);
+          acc = fmaf(q[2 * d2], kk.x, acc);
+          acc = fmaf(q[2 * d2 + 1], kk.y, acc);
+        }
+        sc[i] = acc;
+        m = fmaxf(m, acc);
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+      if (i < Tn) { sc[i] = exp2f(sc[i] - m); sum += sc[i]; }
+    }
+    const float inv = 1.0f / sum;
+    float o[64];
+#pragma unroll
+    for (int d = 0; d < 64; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int i = 0; i < TMAX; ++i) {
+      if (i < Tn) {
+        // probabilities are rounded to the storage type before P*V, like the 16-bit reference path
+        const float pw = Elem<T>::to_f(Elem<T>::from_f(sc[i] * inv));
+#pragma unroll
+        for (int d2 = 0; d2 < 32; ++d2) {
+          float2 vv = Elem<T>::unpack2(Vs[i * 32 + d2]);
+          o[2 * d2] = fmaf(pw, vv.x, o[2 * d2]);
+          o[2 * d2 + 1] = fmaf(pw, vv.y, o[2 * d2 + 1]);
+        }
+      }
+    }
+    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + tok * C + h * 64);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = o[k * 8 + e];
+      op[k] = pack8<T>(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ layout kernels
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int N, int H, int W,
+                                  int nvec) {
+  const long long total = (long long)N * 2 * H * 2 * W * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % nvec);
+    long long r = i / nvec;
+    const int ox = (int)(r % (2 * W)); r /= (2 * W);
+    const int oy = (int)(r % (2 * H));
+    const long long n = r / (2 * H);
+    y[i] = __ldg(x + ((n * H + (oy >> 1)) * W + (ox >> 1)) * nvec + c8);
+  }
+}
+__global__ void concat_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
+                              long long rows, uint4* __restrict__ y) {
+  const int nvec = nv1 + nv2;
+  const long long total = rows * nvec;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x)
+    y[i] = __ldg(cat_ptr(x1, nv1, x2, nv2, i / nvec, (int)(i % nvec)));
+}
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ noise, float ns,
+                                    float scale, float shift, int N, int Cs, long long HW, int Cd,
+                                    T* __restrict__ y) {
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i % HW;
+    for (int c = 0; c < Cd; ++c) {
+      float v = 0.f;
+      if (c < Cs) {
+        const long long idx = (n * Cs + c) * HW + p;
+        v = x[idx] * scale + shift;
+        if (noise) v += ns * noise[idx];
+      }
+      y[i * Cd + c] = Elem<T>::from_f(v);
+    }
+  }
+}
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ x, int N, long long HW, int Cs, int Cd, float scale,
+                                    float shift, int clamp01, float* __restrict__ y) {
+  const long long total = (long long)N * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long n = i / HW, p = i % HW;
+    for (int c = 0; c < Cd; ++c) {
+      float v = Elem<T>::to_f(x[i * Cs + c]) * scale + shift;
+      if (clamp01) v = fminf(fmaxf(v, 0.f), 1.f);
+      y[(n * Cd + c) * HW + p] = v;
+    }
+  }
+}
+
+__global__ void f32_swap_kernel(const float* __restrict__ x, int N, long long HW, int C, float scale,
+                                float* __restrict__ y, int to_nhwc) {
+  const long long total = (long long)N * HW * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    // i indexes the NHWC tensor
+    const int c = (int)(i % C);
+    const long long p = (i / C) % HW;
+    const long long n = i / (C * HW);
+    const long long j = (n * C + c) * HW + p;
+    if (to_nhwc) y[i] = x[j] * scale;
+    else y[j] = x[i] * scale;
+  }
+}
+
+// ------------------------------------------------------------------ small dense helpers
+template <typename T>
+__global__ void gemv_kernel(const void* __restrict__ W, const float* __restrict__ b,
+                            const float* __restrict__ addend, const float* __restrict__ x,
+                            float* __restrict__ out, int N, int K, int silu_in, int silu_out) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int m = blockIdx.y;
+  if (n >= N) return;
+  const uint4* w = reinterpret_cast<const uint4*>(W) + (long long)n * (K >> 3);
+  const float* xr = x + (long long)m * K;
+  float acc = 0.f;
+  for (int i = lane; i < (K >> 3); i += 32) {
+    float f[8];
+    unpack8<T>(__ldg(w + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float xv = xr[i * 8 + j];
+      if (silu_in) xv = silu_f(xv);
+      acc = fmaf(f[j], xv, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = acc + (b ? b[n] : 0.f) + (addend ? addend[n] : 0.f);
+    out[(long long)m * N + n] = silu_out ? silu_f(v) : v;
+  }
+}
+__global__ void sinusoid_vals_kernel(float4 vals, int n, int dim, float* __restrict__ out) {
+  const int half = dim >> 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int r = i / half, j = i % half;
+  const float v = r == 0 ? vals.x : r == 1 ? vals.y : r == 2 ? vals.z : vals.w;
+  const float freq = expf(-9.210340371976184f * (float)j / (float)half);
+  const float ang = v * freq;
+  out[(long long)r * dim + j] = cosf(ang);
+  out[(long long)r * dim + half + j] = sinf(ang);
+}
+__global__ void iota_kernel(float* out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)i;
+}
+__global__ void sinusoid_kernel(const float* __restrict__ vals, int n, int dim, float* __restrict__ out) {
+  const int half = dim >> 1;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * half) return;
+  const int r = i / half, j = i % half;
+  const float freq = expf(-9.210340371976184f * (float)j / (float)half);   // ln(10000)
+  const float ang = vals[r] * freq;
+  out[(long long)r * dim + j] = cosf(ang);
+  out[(long long)r * dim + half + j] = sinf(ang);
+}
+template <typename T>
+__global__ void build_unet_input_kernel(const float4* __restrict__ lat, const uint2* __restrict__ cond,
+                                        float inv, long long tokens, uint4* __restrict__ y) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= tokens) return;
+  const float4 l = lat[i];
+  const uint2 c = cond[i];
+  uint4 u;
+  u.x = Elem<T>::pack2(l.x * inv, l.y * inv);
+  u.y = Elem<T>::pack2(l.z * inv, l.w * inv);
+  u.z = c.x;
+  u.w = c.y;
+  y[i] = u;
+}
+__global__ void euler_step_kernel(float* __restrict__ lat, const float* __restrict__ v, float c_v, float c_x,
+                                  float inv_sigma, float dsigma, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = lat[i];
+  const float x0 = v[i] * c_v + x * c_x;
+  const float d = (x - x0) * inv_sigma;
+  lat[i] = x + d * dsigma;
+}
+template <typename T>
+__global__ void convert_weight_kernel(const void* __restrict__ src, int sd, T* __restrict__ dst, int Cout,
+                                      int Cin, int CinPad, int taps) {
+  const long long total = (long long)Cout * Cin * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ci = (int)(i % Cin);
+    long long r = i / Cin;
+    const int co = (int)(r % Cout);
+    const int tap = (int)(r / Cout);
+    const long long s = ((long long)co * Cin + ci) * taps + tap;
+    float v = sd == 2 ? reinterpret_cast<const float*>(src)[s]
+            : sd == 1 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[s])
+                      : __half2float(reinterpret_cast<const __half*>(src)[s]);
+    dst[((long long)tap * Cout + co) * CinPad + ci] = Elem<T>::from_f(v);
+  }
+}
+__global__ void convert_f32_kernel(const void* __restrict__ src, int sd, float* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = sd == 2 ? reinterpret_cast<const float*>(src)[i]
+           : sd == 1 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[i])
+                     : __half2float(reinterpret_cast<const __half*>(src)[i]);
+}
+
+inline int grid_for(long long total, int block, int cap = 148 * 16) {
+  long long g = (total + block - 1) / block;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+inline int last_err() { return (int)cudaGetLastError(); }
+
+struct GnGeom { int threads; int chunks; long long chunk_rows; };
+inline GnGeom gn_geom(int nvec, long long rows_per_set, long long sets) {
+  GnGeom g;
+  int rpb = 256 / nvec;
+  if (rpb < 1) rpb = 1;
+  g.threads = nvec * rpb;
+  if (g.threads < 64) g.threads = 64;
+  long long want = (148LL * 4 + sets - 1) / sets;
+  long long maxc = (rows_per_set + rpb * 4 - 1) / (rpb * 4);
+  if (want > maxc) want = maxc;
+  if (want < 1) want = 1;
+  g.chunk_rows = (rows_per_set + want - 1) / want;
+  g.chunks = (int)((rows_per_set + g.chunk_rows - 1) / g.chunk_rows);
+  return g;
+}
+
+}  // namespace
+
+int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
+                    int G, float* stats, int fmt, cudaStream_t st) {
+  const int C = C1 + C2;
+  if ((C1 & 7) || (C2 & 7) || C % G || G > 64 || C / 8 > 512) return (int)cudaErrorInvalidValue;
+  const long long sets = rows / rows_per_set;
+  GnGeom g = gn_geom(C / 8, rows_per_set, sets);
+  dim3 grid(g.chunks, (unsigned)sets);
+  UG_DISPATCH_FMT(fmt, (gn_stats_kernel<T><<<grid, g.threads, 0, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
+                                                                         g.chunk_rows, G, C / G, stats)));
+  return last_err();
+}
+
+int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
+                    int G, const float* stats, const float* gamma, const float* beta, float eps, int silu,
+                    void* y, int fmt, cudaStream_t st) {
+  const int C = C1 + C2;
+  if ((C1 & 7) || (C2 & 7) || C % G) return (int)cudaErrorInvalidValue;
+  const long long sets = rows / rows_per_set;
+  GnGeom g = gn_geom(C / 8, rows_per_set, sets);
+  dim3 grid(g.chunks, (unsigned)sets);
+  const size_t smem = (size_t)C * 2 * sizeof(float);
+  UG_DISPATCH_FMT(fmt, (gn_apply_kernel<T><<<grid, 256, smem, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
+                                                                      g.chunk_rows, G, C / G, stats, gamma, beta,
+                                                                      eps, silu, y)));
+  return last_err();
+}
+
+int launch_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
+                     const float* add, int add_div, void* y, int fmt, cudaStream_t st) {
+  if ((C & 7) || C > 2048) return (int)cudaErrorInvalidValue;
+  const int wpb = 8;
+  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
+  UG_DISPATCH_FMT(fmt, (layernorm_kernel<T><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, add,
+                                                                         add_div > 0 ? add_div : 1, y)));
+  return last_err();
+}
+
+int launch_softmax_rows(void* s, long long rows, int n, float scale, int fmt, cudaStream_t st) {
+  if (n & 7) return (int)cudaErrorInvalidValue;
+  const float sl = scale * 1.4426950408889634f;
+  const int nvec = n / 8;
+  if (nvec <= 32) {
+    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 1><<<(unsigned)rows, 32, 0, st>>>(s, rows, n, sl)));
+  } else if (nvec <= 128) {
+    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 1><<<(unsigned)rows, 128, 0, st>>>(s, rows, n, sl)));
+  } else if (nvec <= 512) {
+    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 2><<<(unsigned)rows, 256, 0, st>>>(s, rows, n, sl)));
+  } else if (nvec <= 2048) {
+    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 8><<<(unsigned)rows, 256, 0, st>>>(s, rows, n, sl)));
+  } else {
+    return (int)cudaErrorInvalidValue;
+  }
+  return last_err();
+}
+
+int launch_temporal_attention(const void* qkv, void* out, int Tn, long long P, int C, float scale, int fmt,
+                              cudaStream_t st) {
+  if ((C & 63) || Tn > 64 || Tn < 1) return (int)cudaErrorInvalidValue;
+  const int wpb = 4;
+  const long long items = P * (C / 64);
+  const unsigned grid = (unsigned)((items + wpb - 1) / wpb);
+  const size_t smem = (size_t)wpb * Tn * 64 * sizeof(uint32_t);
+  const float sl = scale * 1.4426950408889634f;
+  if (Tn <= 32) {
+    UG_DISPATCH_FMT(fmt, {
+      cudaFuncSetAttribute(temporal_attn_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      temporal_attn_kernel<T, 32><<<grid, wpb * 32, smem, st>>>(qkv, out, Tn, P, C, sl);
+    });
+  } else {
+    UG_DISPATCH_FMT(fmt, {
+      cudaFuncSetAttribute(temporal_attn_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      temporal_attn_kernel<T, 64><<<grid, wpb * 32, smem, st>>>(qkv, out, Tn, P, C, sl);
+    });
+  }
+  return last_err();
+}
+
+int launch_upsample2x(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st) {
+  if (C & 7) return (int)cudaErrorInvalidValue;
+  const long long total = (long long)N * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(x),
+                                                           reinterpret_cast<uint4*>(y), N, H, W, C / 8);
+  return last_err();
+}
+
+int launch_concat(const void* x1, int C1, const void* x2, int C2, long long rows, void* y, cudaStream_t st) {
+  if ((C1 & 7) || (C2 & 7)) return (int)cudaErrorInvalidValue;
+  const long long total = rows * ((C1 + C2) / 8);
+  concat_kernel<<<grid_for(total, 256), 256, 0, st>>>(x1, C1 / 8, x2, C2 / 8, rows, reinterpret_cast<uint4*>(y));
+  return last_err();
+}
+
+int launch_nchw_to_nhwc(const float* x, const float* noise, float noise_scale, float scale, float shift, int N,
+                        int Csrc, int H, int W, int Cdst, void* y, int fmt, cudaStream_t st) {
+  const long long total = (long long)N * H * W;
+  UG_DISPATCH_FMT(fmt, (nchw_to_nhwc_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+                           x, noise, noise_scale, scale, shift, N, Csrc, (long long)H * W, Cdst,
+                           reinterpret_cast<T*>(y))));
+  return last_err();
+}
+
+int launch_nhwc_to_nchw(const void* x, int N, int H, int W, int Csrc, int Cdst, float scale, float shift,
+                        int clamp01, float* y, int fmt, cudaStream_t st) {
+  const long long total = (long long)N * H * W;
+  UG_DISPATCH_FMT(fmt, (nhwc_to_nchw_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+                           reinterpret_cast<const T*>(x), N, (long long)H * W, Csrc, Cdst, scale, shift, clamp01,
+                           y)));
+  return last_err();
+}
+
+int launch_f32_nchw_to_nhwc(const float* x, int N, long long HW, int C, float scale, float* y, cudaStream_t st) {
+  f32_swap_kernel<<<grid_for((long long)N * HW * C, 256), 256, 0, st>>>(x, N, HW, C, scale, y, 1);
+  return last_err();
+}
+int launch_f32_nhwc_to_nchw(const float* x, int N, long long HW, int C, float scale, float* y, cudaStream_t st) {
+  f32_swap_kernel<<<grid_for((long long)N * HW * C, 256), 256, 0, st>>>(x, N, HW, C, scale, y, 0);
+  return last_err();
+}
+
+int launch_gemv(const void* W, const float* b, const float* addend, const float* x, float* out, int M, int N,
+                int K, int silu_in, int silu_out, int fmt, cudaStream_t st) {
+  if (K & 7) return (int)cudaErrorInvalidValue;
+  const int wpb = 4;
+  dim3 grid((N + wpb - 1) / wpb, M);
+  UG_DISPATCH_FMT(fmt, (gemv_kernel<T><<<grid, wpb * 32, 0, st>>>(W, b, addend, x, out, N, K, silu_in, silu_out)));
+  return last_err();
+}
+
+int launch_sinusoid(const float* vals, int n, int dim, float* out, cudaStream_t st) {
+  const int total = n * (dim / 2);
+  sinusoid_kernel<<<(total + 127) / 128, 128, 0, st>>>(vals, n, dim, out);
+  return last_err();
+}
+
+int launch_sinusoid_vals(float v0, float v1, float v2, float v3, int n, int dim, float* out, cudaStream_t st) {
+  const int total = n * (dim / 2);
+  sinusoid_vals_kernel<<<(total + 127) / 128, 128, 0, st>>>(make_float4(v0, v1, v2, v3), n, dim, out);
+  return last_err();
+}
+int launch_iota(float* out, int n, cudaStream_t st) {
+  iota_kernel<<<(n + 127) / 128, 128, 0, st>>>(out, n);
+  return last_err();
+}
+
+int launch_build_unet_input(const float* latents, const void* cond, float sigma, long long tokens, void* y,
+                            int fmt, cudaStream_t st) {
+  const float inv = 1.0f / sqrtf(sigma * sigma + 1.0f);
+  UG_DISPATCH_FMT(fmt, (build_unet_input_kernel<T><<<(unsigned)((tokens + 255) / 256), 256, 0, st>>>(
+                           reinterpret_cast<const float4*>(latents), reinterpret_cast<const uint2*>(cond), inv,
+                           tokens, reinterpret_cast<uint4*>(y))));
+  return last_err();
+}
+
+int launch_euler_step(float* latents, const float* v, float sigma, float sigma_next, long long n,
+                      cudaStream_t st) {
+  const float c_v = -sigma / sqrtf(sigma * sigma + 1.0f);
+  const float c_x = 1.0f / (sigma * sigma + 1.0f);
+  euler_step_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(latents, v, c_v, c_x, 1.0f / sigma,
+                                                                  sigma_next - sigma, n);
+  return last_err();
+}
+
+int launch_convert_weight(const void* src, int src_dtype, void* dst, int Cout, int Cin, int CinPad, int taps,
+                          int fmt, cudaStream_t st) {
+  const long long total = (long long)Cout * Cin * taps;
+  UG_DISPATCH_FMT(fmt, (convert_weight_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
+                           src, src_dtype, reinterpret_cast<T*>(dst), Cout, Cin, CinPad, taps)));
+  return last_err();
+}
+
+int launch_convert_f32(const void* src, int src_dtype, float* dst, long long n, cudaStream_t st) {
+  convert_f32_kernel<<<grid_for(n, 256), 256, 0, st>>>(src, src_dtype, dst, n);
+  return last_err();
+}
+
+}  // namespace ug

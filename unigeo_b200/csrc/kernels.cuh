@@ -1,0 +1,71 @@
+// HBM-bound kernels of the hot path (CUDA cores, 128-bit coalesced accesses).
+// All activations are 16-bit channels-last: [frames][pixels][C] ("token-major").
+// fmt: 0 = fp16, 1 = bf16.  Every launcher returns a cudaError_t as int.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ug {
+
+// ---- GroupNorm over channels-last tokens ------------------------------------------
+// Statistics set s covers rows [s*rows_per_set, (s+1)*rows_per_set): one frame for a
+// spatial GroupNorm, the whole clip for the temporal-resnet GroupNorm.  The input may be
+// the channel concatenation [x1 (C1) | x2 (C2)] (UNet skip connections); C = C1 + C2.
+// stats: [sets][G][2] fp32 (sum, sumsq) -- must be zero on entry.
+int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
+                    int G, float* stats, int fmt, cudaStream_t st);
+// y = act((x - mean) * rstd * gamma + beta), act = SiLU when silu != 0; y is [rows][C] dense.
+int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
+                    int G, const float* stats, const float* gamma, const float* beta, float eps, int silu,
+                    void* y, int fmt, cudaStream_t st);
+
+// ---- LayerNorm over C, optional per-frame vector added first: LN(x + add[row / add_div]) ----
+int launch_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
+                     const float* add, int add_div, void* y, int fmt, cudaStream_t st);
+
+// ---- row softmax in place over [rows][n] 16-bit (scores pre-scaled) ------------------
+int launch_softmax_rows(void* s, long long rows, int n, float scale, int fmt, cudaStream_t st);
+
+// ---- temporal self-attention: sequences of T tokens per (pixel, head), head_dim 64 ----
+// qkv: [T][P][3C] (q | k | v), out: [T][P][C]; heads = C / 64.
+int launch_temporal_attention(const void* qkv, void* out, int T, long long P, int C, float scale, int fmt,
+                              cudaStream_t st);
+
+// ---- layout / elementwise -------------------------------------------------------------
+int launch_upsample2x(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st);   // nearest
+int launch_concat(const void* x1, int C1, const void* x2, int C2, long long rows, void* y, cudaStream_t st);
+// fp32 NCHW [N][Csrc][H][W] -> 16-bit NHWC [N][H][W][Cdst] (Cdst >= Csrc, zero padded), v*scale+shift (+noise*ns)
+int launch_nchw_to_nhwc(const float* x, const float* noise, float noise_scale, float scale, float shift, int N,
+                        int Csrc, int H, int W, int Cdst, void* y, int fmt, cudaStream_t st);
+// uint8/float HWC frames handled on the host side of the ABI; this one: 16-bit NHWC -> fp32 NCHW, first Cdst ch.
+int launch_nhwc_to_nchw(const void* x, int N, int H, int W, int Csrc, int Cdst, float scale, float shift,
+                        int clamp01, float* y, int fmt, cudaStream_t st);
+// fp32 layout swaps for the (small) latent tensors: y = x * scale
+int launch_f32_nchw_to_nhwc(const float* x, int N, long long HW, int C, float scale, float* y, cudaStream_t st);
+int launch_f32_nhwc_to_nchw(const float* x, int N, long long HW, int C, float scale, float* y, cudaStream_t st);
+// out[n] = act(sum_k W[n][k] * in_act(x[k]) + b[n]); W 16-bit [N][K]; x,b,out fp32.  M rows of x/out.
+// addend (nullable, [N]) is added before the output activation.
+int launch_gemv(const void* W, const float* b, const float* addend, const float* x, float* out, int M, int N,
+                int K, int silu_in, int silu_out, int fmt, cudaStream_t st);
+// sinusoid embedding rows: out[i][0:dim/2] = cos(v_i * f_j), out[i][dim/2:] = sin(v_i * f_j)
+int launch_sinusoid(const float* vals, int n, int dim, float* out, cudaStream_t st);
+// same, values passed by value (n <= 4): timestep / added time ids known on the host
+int launch_sinusoid_vals(float v0, float v1, float v2, float v3, int n, int dim, float* out, cudaStream_t st);
+// vals[i] = i
+int launch_iota(float* out, int n, cudaStream_t st);
+
+// ---- scheduler glue (K10) -------------------------------------------------------------
+// UNet input [T][P][8] 16-bit  <-  [ latents/sqrt(sigma^2+1) (4 ch) | cond latents (4 ch) ]
+// latents fp32 [T][P][4] (channels-last), cond 16-bit [T][P][4].
+int launch_build_unet_input(const float* latents, const void* cond, float sigma, long long tokens, void* y,
+                            int fmt, cudaStream_t st);
+// Euler v-prediction step in place on fp32 latents; v fp32 [tokens][4].
+int launch_euler_step(float* latents, const float* v, float sigma, float sigma_next, long long n,
+                      cudaStream_t st);
+
+// weights: src fp32/16-bit [Cout][Cin][taps] -> dst 16-bit [taps][Cout][CinPad] (dst pre-zeroed when padded)
+int launch_convert_weight(const void* src, int src_dtype /*0 f16,1 bf16,2 f32*/, void* dst, int Cout, int Cin,
+                          int CinPad, int taps, int fmt, cudaStream_t st);
+int launch_convert_f32(const void* src, int src_dtype, float* dst, long long n, cudaStream_t st);
+
+}  // namespace ug

@@ -1,0 +1,354 @@
+// Op wrappers: turn layer-level calls into tensor maps + tapgemm launches / kernel launches.
+#include "ctx.cuh"
+
+#include <cmath>
+#include <cstring>
+
+namespace ug {
+
+// ------------------------------------------------------------------ Ctx
+void* Ctx::dmalloc(size_t bytes) {
+  void* p = nullptr;
+  UG_CUDA(cudaMalloc(&p, bytes < 256 ? 256 : bytes));
+  owned.push_back(p);
+  return p;
+}
+const Weight& Ctx::W(const std::string& key) const {
+  auto it = weights.find(key);
+  if (it == weights.end()) throw UgError(UG_ERR_WEIGHT, "missing weight: " + key);
+  return it->second;
+}
+const float* Ctx::F(const std::string& key) const {
+  const Weight& w = W(key);
+  UG_CHECK(w.is_f32, UG_ERR_WEIGHT, "weight is not an fp32 vector: " + key);
+  return reinterpret_cast<const float*>(w.p);
+}
+const void* Ctx::M(const std::string& key) const {
+  const Weight& w = W(key);
+  UG_CHECK(!w.is_f32, UG_ERR_WEIGHT, "weight is not a 16-bit matrix: " + key);
+  return w.p;
+}
+void Ctx::ensure_workspace(size_t bytes) {
+  if (bytes <= ws.cap) return;
+  if (ws.base) {
+    UG_CUDA(cudaDeviceSynchronize());
+    UG_CUDA(cudaFree(ws.base));
+    ws.base = nullptr;
+    ws.cap = 0;
+  }
+  void* p = nullptr;
+  UG_CUDA(cudaMalloc(&p, bytes));
+  ws.base = reinterpret_cast<char*>(p);
+  ws.cap = bytes;
+}
+
+void op_check(Ctx& c, int err, const char* what) {
+  if (err != 0)
+    throw UgError(UG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString((cudaError_t)err) + " (" +
+                                   std::to_string(err) + ")");
+  c.launches++;
+}
+
+// ------------------------------------------------------------------ tapgemm plumbing
+namespace {
+
+void fill_epi(TapGemmArgs& a, const Epi& e, int fmt) {
+  a.fmt = fmt;
+  a.out = e.out;
+  a.ldc = e.ldc;
+  a.out_fp32 = e.out_fp32;
+  a.bias = e.bias;
+  a.fbias = e.fbias;
+  a.fbias_ld = e.fbias_ld;
+  a.fbias_div = e.fbias_div > 0 ? e.fbias_div : 1;
+  a.res = e.res;
+  a.ldr = e.ldr;
+  a.blend = e.blend;
+  a.ldb = e.ldb;
+  a.alpha = e.alpha;
+  a.scale = e.scale;
+  a.geglu = e.geglu;
+}
+
+void base_args(TapGemmArgs& a) {
+  std::memset(&a, 0, sizeof(a));
+  a.dim_x = a.dim_y = a.dim_n = a.dim_z0 = a.dim_z1 = 5;
+  a.zdiv = 1;
+  a.tiles_x = a.tiles_y = a.tiles_n = 1;
+  a.bw = a.bh = a.bn = 1;
+  a.W = a.H = a.N = 1;
+  a.num_taps = 1;
+  a.kchunks = 1;
+  a.scale = 1.f;
+  a.fbias_div = 1;
+}
+
+// A: rank-5 map (unused dims = 1).  dims[0] = channels.
+void make_a_map(CUtensorMap* m, const void* p, int fmt, const unsigned long long dims[5],
+                const unsigned long long strides_bytes[4], int box1, int box2, int box3, int box4) {
+  TmapDesc d;
+  d.ptr = p;
+  d.elem_fmt = fmt;
+  d.rank = 5;
+  for (int i = 0; i < 5; ++i) d.dims[i] = dims[i];
+  for (int i = 0; i < 4; ++i) d.strides[i] = strides_bytes[i];
+  d.box[0] = 64;
+  d.box[1] = box1; d.box[2] = box2; d.box[3] = box3; d.box[4] = box4;
+  int r = encode_tmap(m, d);
+  if (r != 0) throw UgError(UG_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string(r));
+}
+// B: rank-2 map [rows][cols], box (64 cols, box_rows)
+void make_b_map(CUtensorMap* m, const void* p, int fmt, unsigned long long cols, unsigned long long rows,
+                unsigned long long row_stride_bytes, int box_rows) {
+  TmapDesc d;
+  d.ptr = p;
+  d.elem_fmt = fmt;
+  d.rank = 2;
+  d.dims[0] = cols; d.dims[1] = rows;
+  d.strides[0] = row_stride_bytes;
+  d.box[0] = 64; d.box[1] = box_rows;
+  int r = encode_tmap(m, d);
+  if (r != 0) throw UgError(UG_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string(r));
+}
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline int imin(int a, int b) { return a < b ? a : b; }
+
+void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmArgs& a, int batch,
+            const char* what) {
+  op_check(c, launch_tapgemm(ma, mb, a, batch, c.stream), what);
+}
+
+}  // namespace
+
+void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const void* Wm, int N, const Epi& e) {
+  if (c.dry) return;
+  UG_CHECK((K % 8) == 0 && (ldx % 8) == 0, UG_ERR_INVALID, "linear: K and ldx must be multiples of 8");
+  TapGemmArgs a;
+  base_args(a);
+  a.dim_x = 1;
+  a.bw = 128;
+  a.W = (int)M;
+  a.tiles_x = cdiv(M, 128);
+  a.kchunks = cdiv(K, 64);
+  a.n_total = N;
+  fill_epi(a, e, c.fmt);
+  const int bn = tapgemm_pick_bn(N, e.geglu);
+  CUtensorMap ma, mb;
+  unsigned long long dims[5] = {(unsigned long long)K, (unsigned long long)M, 1, 1, 1};
+  unsigned long long st[4] = {(unsigned long long)ldx * 2, (unsigned long long)ldx * 2 * M,
+                              (unsigned long long)ldx * 2 * M, (unsigned long long)ldx * 2 * M};
+  make_a_map(&ma, x, c.fmt, dims, st, 128, 1, 1, 1);
+  make_b_map(&mb, Wm, c.fmt, K, N, (unsigned long long)K * 2, bn);
+  launch(c, ma, mb, a, 1, "linear");
+}
+
+void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* Wm, int Cout, int stride,
+                int asym, const Epi& e) {
+  if (c.dry) return;
+  UG_CHECK((C % 8) == 0, UG_ERR_INVALID, "conv3x3: C must be a multiple of 8");
+  TapGemmArgs a;
+  base_args(a);
+  const int Ho = H / stride, Wo = W / stride;
+  a.W = Wo; a.H = Ho; a.N = Nf;
+  a.bw = imin(Wo, 128);
+  a.bh = imin(Ho, 128 / a.bw);
+  a.bn = imin(Nf, 128 / (a.bw * a.bh));
+  a.tiles_x = cdiv(Wo, a.bw);
+  a.tiles_y = cdiv(Ho, a.bh);
+  a.tiles_n = cdiv(Nf, a.bn);
+  a.num_taps = 9;
+  a.kchunks = cdiv(C, 64);
+  a.b_tap_rows = Cout;
+  a.n_total = Cout;
+  fill_epi(a, e, c.fmt);
+  const int bn = tapgemm_pick_bn(Cout, e.geglu);
+  CUtensorMap ma, mb;
+  const unsigned long long rowb = (unsigned long long)C * 2;
+  if (stride == 1) {
+    a.dim_x = 1; a.dim_y = 2; a.dim_n = 3;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        int* o = a.tap_off[ky * 3 + kx];
+        o[1] = kx - 1;
+        o[2] = ky - 1;
+      }
+    unsigned long long dims[5] = {(unsigned long long)C, (unsigned long long)W, (unsigned long long)H,
+                                  (unsigned long long)Nf, 1};
+    unsigned long long st[4] = {rowb, rowb * W, rowb * W * H, rowb * W * H * Nf};
+    make_a_map(&ma, x, c.fmt, dims, st, a.bw, a.bh, a.bn, 1);
+  } else {
+    UG_CHECK(stride == 2 && (H % 2) == 0 && (W % 2) == 0, UG_ERR_INVALID, "conv3x3: stride 2 needs even H, W");
+    // space-to-depth VIEW of x (no copy): dims (2C [px,c], W/2, py, H/2, N)
+    a.dim_x = 1; a.dim_y = 3; a.dim_n = 4;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        int* o = a.tap_off[ky * 3 + kx];
+        const int dy = asym ? ky : ky - 1;       // input row = 2*oy + dy
+        const int dx = asym ? kx : kx - 1;
+        const int py = ((dy % 2) + 2) % 2, px = ((dx % 2) + 2) % 2;
+        o[0] = px * C;
+        o[1] = (dx - px) / 2;
+        o[2] = py;
+        o[3] = (dy - py) / 2;
+      }
+    unsigned long long dims[5] = {(unsigned long long)2 * C, (unsigned long long)W / 2, 2,
+                                  (unsigned long long)H / 2, (unsigned long long)Nf};
+    unsigned long long st[4] = {rowb * 2, rowb * W, rowb * W * 2, rowb * W * H};
+    make_a_map(&ma, x, c.fmt, dims, st, a.bw, 1, a.bh, a.bn);
+  }
+  make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)9 * Cout, rowb, bn);
+  launch(c, ma, mb, a, 1, "conv3x3");
+}
+
+void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm, int Cout, int chunk,
+               const Epi& e) {
+  if (c.dry) return;
+  UG_CHECK((C % 8) == 0, UG_ERR_INVALID, "tconv3: C must be a multiple of 8");
+  const unsigned long long rowb = (unsigned long long)C * 2;
+  // chunks are independent zero-padded clips (VAE decode): run one launch per chunk so that
+  // the TMA bounds ARE the chunk bounds.
+  for (int t0 = 0; t0 < T; t0 += chunk) {
+    const int Tc = imin(chunk, T - t0);
+    TapGemmArgs a;
+    base_args(a);
+    a.dim_x = 1; a.dim_y = 2;
+    a.W = (int)P; a.H = Tc;
+    a.bw = (int)(P < 128 ? P : 128);
+    a.bh = imin(Tc, 128 / a.bw);
+    a.tiles_x = cdiv(P, a.bw);
+    a.tiles_y = cdiv(Tc, a.bh);
+    a.num_taps = 3;
+    a.kchunks = cdiv(C, 64);
+    a.b_tap_rows = Cout;
+    a.n_total = Cout;
+    for (int kt = 0; kt < 3; ++kt) a.tap_off[kt][2] = kt - 1;
+    Epi ec = e;
+    const long long tok0 = (long long)t0 * P;
+    const int osz = e.out_fp32 ? 4 : 2;
+    ec.out = reinterpret_cast<char*>(e.out) + tok0 * e.ldc * osz;
+    if (e.res) ec.res = reinterpret_cast<const char*>(e.res) + tok0 * e.ldr * 2;
+    if (e.blend) ec.blend = reinterpret_cast<const char*>(e.blend) + tok0 * e.ldb * 2;
+    if (e.fbias) ec.fbias = e.fbias + (tok0 / ec.fbias_div) * e.fbias_ld;
+    fill_epi(a, ec, c.fmt);
+    const int bn = tapgemm_pick_bn(Cout, e.geglu);
+    CUtensorMap ma, mb;
+    unsigned long long dims[5] = {(unsigned long long)C, (unsigned long long)P, (unsigned long long)Tc, 1, 1};
+    unsigned long long st[4] = {rowb, rowb * P, rowb * P * Tc, rowb * P * Tc};
+    make_a_map(&ma, reinterpret_cast<const char*>(x) + tok0 * rowb, c.fmt, dims, st, a.bw, a.bh, 1, 1);
+    make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)3 * Cout, rowb, bn);
+    launch(c, ma, mb, a, 1, "tconv3");
+  }
+}
+
+// v1 attention: S = Q K^T (tapgemm, batched over frame x head) -> row softmax -> O = P V
+// (tapgemm with the MN-major B path reading V in place).  Scores live in the workspace.
+void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, void* out) {
+  UG_CHECK(dh == 64 || dh == C, UG_ERR_INVALID, "attention: head_dim must be 64 or C");
+  UG_CHECK((N % 8) == 0 && (dh % 64) == 0, UG_ERR_INVALID, "attention: N % 8 and head_dim % 64");
+  const int heads = C / dh;
+  const size_t m = c.ws.mark();
+  void* S = c.alloc16((long long)F * heads * N * N);
+  if (!c.dry) {
+    const unsigned long long rowb = (unsigned long long)3 * C * 2;
+    {  // S[z][N][N] = Q K^T
+      TapGemmArgs a;
+      base_args(a);
+      a.dim_x = 1;
+      a.bw = imin(N, 128);
+      a.W = N;
+      a.tiles_x = cdiv(N, a.bw);
+      a.kchunks = dh / 64;
+      a.zdiv = heads;
+      a.dim_z1 = 1; a.a_z1step = N;       // frame -> token rows
+      a.dim_z0 = 0; a.a_z0step = dh;      // head  -> q columns
+      a.b_c0 = C; a.b_z0_cstep = dh; a.b_z1_rowstep = N;
+      a.n_total = N;
+      Epi e;
+      e.out = S; e.ldc = N;
+      fill_epi(a, e, c.fmt);
+      a.out_z1stride = (long long)heads * N * N;
+      a.out_z0stride = (long long)N * N;
+      CUtensorMap ma, mb;
+      unsigned long long dims[5] = {(unsigned long long)3 * C, (unsigned long long)F * N, 1, 1, 1};
+      unsigned long long st[4] = {rowb, rowb * F * N, rowb * F * N, rowb * F * N};
+      make_a_map(&ma, qkv, c.fmt, dims, st, a.bw, 1, 1, 1);
+      make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb,
+                 tapgemm_pick_bn(N, 0));
+      launch(c, ma, mb, a, F * heads, "attention QK^T");
+    }
+    op_check(c, launch_softmax_rows(S, (long long)F * heads * N, N, 1.0f / sqrtf((float)dh), c.fmt, c.stream),
+             "softmax");
+    {  // O[z] = P[z] V[z]
+      TapGemmArgs a;
+      base_args(a);
+      a.dim_x = 1;
+      a.bw = imin(N, 128);
+      a.W = N;
+      a.tiles_x = cdiv(N, a.bw);
+      a.kchunks = cdiv(N, 64);
+      a.zdiv = heads;
+      a.dim_z0 = 2; a.a_z0step = 1;
+      a.dim_z1 = 3; a.a_z1step = 1;
+      a.b_mn_major = 1;
+      a.b_c0 = 2 * C; a.b_z0_cstep = dh; a.b_z1_rowstep = N;
+      a.n_total = dh;
+      Epi e;
+      e.out = out; e.ldc = C;
+      fill_epi(a, e, c.fmt);
+      a.out_z1stride = (long long)N * C;
+      a.out_z0stride = dh;
+      CUtensorMap ma, mb;
+      const unsigned long long srow = (unsigned long long)N * 2;
+      unsigned long long dims[5] = {(unsigned long long)N, (unsigned long long)N, (unsigned long long)heads,
+                                    (unsigned long long)F, 1};
+      unsigned long long st[4] = {srow, srow * N, srow * N * heads, srow * N * heads * F};
+      make_a_map(&ma, S, c.fmt, dims, st, a.bw, 1, 1, 1);
+      make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb, 64);
+      // the MN-major path is built for 64-wide N tiles
+      op_check(c, launch_tapgemm(ma, mb, a, F * heads, c.stream), "attention PV");
+    }
+  }
+  c.ws.release(m);
+}
+
+// ------------------------------------------------------------------ simple wrappers
+void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
+           const float* gamma, const float* beta, float eps, int silu, void* y) {
+  const int G = c.cfg.norm_groups;
+  const long long sets = rows / rows_per_set;
+  const size_t m = c.ws.mark();
+  float* stats = c.allocf(sets * G * 2);
+  if (!c.dry) {
+    UG_CUDA(cudaMemsetAsync(stats, 0, (size_t)sets * G * 2 * sizeof(float), c.stream));
+    op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, stats, c.fmt, c.stream), "gn_stats");
+    op_check(c, launch_gn_apply(x1, C1, x2, C2, rows, rows_per_set, G, stats, gamma, beta, eps, silu, y, c.fmt,
+                                c.stream),
+             "gn_apply");
+  }
+  c.ws.release(m);
+}
+void op_layernorm(Ctx& c, const void* x, long long rows, int C, const float* g, const float* b, float eps,
+                  const float* add, int add_div, void* y) {
+  if (c.dry) return;
+  op_check(c, launch_layernorm(x, rows, C, g, b, eps, add, add_div, y, c.fmt, c.stream), "layernorm");
+}
+void op_temporal_attention(Ctx& c, const void* qkv, void* out, int T, long long P, int C) {
+  if (c.dry) return;
+  op_check(c, launch_temporal_attention(qkv, out, T, P, C, 0.125f, c.fmt, c.stream), "temporal_attention");
+}
+void op_upsample2x(Ctx& c, const void* x, void* y, int N, int H, int W, int C) {
+  if (c.dry) return;
+  op_check(c, launch_upsample2x(x, y, N, H, W, C, c.stream), "upsample2x");
+}
+void op_concat(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long rows, void* y) {
+  if (c.dry) return;
+  op_check(c, launch_concat(x1, C1, x2, C2, rows, y, c.stream), "concat");
+}
+void op_gemv(Ctx& c, const void* Wm, const float* b, const float* addend, const float* x, float* out, int M,
+             int N, int K, int silu_in, int silu_out) {
+  if (c.dry) return;
+  op_check(c, launch_gemv(Wm, b, addend, x, out, M, N, K, silu_in, silu_out, c.fmt, c.stream), "gemv");
+}
+
+}  // namespace ug

@@ -1,0 +1,391 @@
+// tapgemm kernel + launcher (see tapgemm.cuh for what it computes and replaces).
+//
+// CTA = 192 threads, one 128 x BN output tile:
+//   warp 0      TMA producer   (one elected lane; A box + B box per stage, mbarrier tx-count)
+//   warp 1      TMEM owner + UMMA issuer (one elected lane; tcgen05.mma 128xBNx16, commit -> mbarrier)
+//   warps 2..5  epilogue       (tcgen05.ld 32x32b: thread = output row, registers = columns)
+// smem: STAGES x (A 128x64 + B BNx64) 16-bit tiles in the TMA/UMMA SWIZZLE_128B layout.
+#include "tapgemm.cuh"
+#include "ptx.cuh"
+
+#include <cstdio>
+#include <mutex>
+
+namespace ug {
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int kThreads = 192;
+constexpr int kATileBytes = BM * BK * 2;
+
+template <int BN> struct Cfg {
+  static constexpr int b_tile_bytes = BN * BK * 2;
+  static constexpr int stage_bytes = kATileBytes + (b_tile_bytes < 1024 ? 1024 : b_tile_bytes);
+  // 3 stages for the wide tiles (<= 96 KB: two CTAs co-reside, one's epilogue hides under the
+  // other's main loop); deeper ring for the narrow ones.
+  static constexpr int stages = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
+  static constexpr int tmem_cols = BN < 32 ? 32 : BN;
+  static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ float2 unpack16x2(uint32_t u, int fmt) {
+  return fmt ? Elem<__nv_bfloat16>::unpack2(u) : Elem<__half>::unpack2(u);
+}
+__device__ __forceinline__ uint32_t pack16x2(float a, float b, int fmt) {
+  return fmt ? Elem<__nv_bfloat16>::pack2(a, b) : Elem<__half>::pack2(a, b);
+}
+__device__ __forceinline__ float load16(const void* base, long long idx, int fmt) {
+  return fmt ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx])
+             : __half2float(reinterpret_cast<const __half*>(base)[idx]);
+}
+__device__ __forceinline__ void store16(void* base, long long idx, float v, int fmt) {
+  if (fmt) reinterpret_cast<__nv_bfloat16*>(base)[idx] = __float2bfloat16_rn(v);
+  else reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
+}
+
+// Finishes NC (16 or 32) consecutive output columns of one row and stores them.
+//   f[]    accumulator values (already scaled / gated)
+//   col0   first column in OUTPUT column space; ncols_valid = how many of the NC exist
+template <int NC>
+__device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmArgs& a, long long pix,
+                                                 long long zoff, int col0, int bias_col0, int ncols_valid,
+                                                 bool row_ok) {
+  if (!row_ok || ncols_valid <= 0) return;
+  const int fmt = a.fmt;
+  const bool full = ncols_valid >= NC;
+  if (a.bias != nullptr && !a.geglu) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (full || j < ncols_valid) f[j] += __ldg(a.bias + bias_col0 + j);
+  }
+  if (a.fbias != nullptr) {
+    const float* fb = a.fbias + (long long)(pix / a.fbias_div) * a.fbias_ld + col0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (full || j < ncols_valid) f[j] += __ldg(fb + j);
+  }
+  const bool vec_ok = full && ((col0 & 7) == 0);
+  if (a.res != nullptr) {
+    const long long off = pix * a.ldr + col0;
+    if (vec_ok && ((a.ldr & 7) == 0)) {
+      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.res) + off);
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) {
+        uint4 u = __ldg(p + j);
+        float2 t0 = unpack16x2(u.x, fmt), t1 = unpack16x2(u.y, fmt), t2 = unpack16x2(u.z, fmt),
+               t3 = unpack16x2(u.w, fmt);
+        f[8 * j + 0] += t0.x; f[8 * j + 1] += t0.y; f[8 * j + 2] += t1.x; f[8 * j + 3] += t1.y;
+        f[8 * j + 4] += t2.x; f[8 * j + 5] += t2.y; f[8 * j + 6] += t3.x; f[8 * j + 7] += t3.y;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (full || j < ncols_valid) f[j] += load16(a.res, off + j, fmt);
+    }
+  }
+  if (a.blend != nullptr) {
+    const long long off = pix * a.ldb + col0;
+    const float al = a.alpha, be = 1.0f - a.alpha;
+    if (vec_ok && ((a.ldb & 7) == 0)) {
+      const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.blend) + off);
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) {
+        uint4 u = __ldg(p + j);
+        float2 t0 = unpack16x2(u.x, fmt), t1 = unpack16x2(u.y, fmt), t2 = unpack16x2(u.z, fmt),
+               t3 = unpack16x2(u.w, fmt);
+        f[8 * j + 0] = al * t0.x + be * f[8 * j + 0]; f[8 * j + 1] = al * t0.y + be * f[8 * j + 1];
+        f[8 * j + 2] = al * t1.x + be * f[8 * j + 2]; f[8 * j + 3] = al * t1.y + be * f[8 * j + 3];
+        f[8 * j + 4] = al * t2.x + be * f[8 * j + 4]; f[8 * j + 5] = al * t2.y + be * f[8 * j + 5];
+        f[8 * j + 6] = al * t3.x + be * f[8 * j + 6]; f[8 * j + 7] = al * t3.y + be * f[8 * j + 7];
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (full || j < ncols_valid) f[j] = al * load16(a.blend, off + j, fmt) + be * f[j];
+    }
+  }
+  const long long ooff = zoff + pix * a.ldc + col0;
+  if (a.out_fp32) {
+    float* o = reinterpret_cast<float*>(a.out) + ooff;
+    if (full && ((a.ldc & 3) == 0) && ((col0 & 3) == 0)) {
+#pragma unroll
+      for (int j = 0; j < NC / 4; ++j)
+        reinterpret_cast<float4*>(o)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (full || j < ncols_valid) o[j] = f[j];
+    }
+  } else {
+    if (vec_ok && ((a.ldc & 7) == 0)) {
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) + ooff);
+#pragma unroll
+      for (int j = 0; j < NC / 8; ++j) {
+        uint4 u;
+        u.x = pack16x2(f[8 * j + 0], f[8 * j + 1], fmt);
+        u.y = pack16x2(f[8 * j + 2], f[8 * j + 3], fmt);
+        u.z = pack16x2(f[8 * j + 4], f[8 * j + 5], fmt);
+        u.w = pack16x2(f[8 * j + 6], f[8 * j + 7], fmt);
+        o[j] = u;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (full || j < ncols_valid) store16(a.out, ooff + j, f[j], fmt);
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads)
+tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TapGemmArgs a) {
+  using C = Cfg<BN>;
+  constexpr int STAGES = C::stages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::stage_bytes);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  int m_tile = blockIdx.x;
+  const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
+  const int ty = m_tile % a.tiles_y;
+  const int tn = m_tile / a.tiles_y;
+  const int x0 = tx * a.bw, y0 = ty * a.bh, nn0 = tn * a.bn;
+  const int n0 = blockIdx.y * BN;
+  const int z1 = blockIdx.z / a.zdiv;
+  const int z0 = blockIdx.z - z1 * a.zdiv;
+  const int num_iters = a.num_taps * a.kchunks;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(&full_bar[s], 1);
+        mbar_init(&empty_bar[s], 1);
+      }
+      mbar_init(tmem_full_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr_smem, C::tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int base[6] = {0, 0, 0, 0, 0, 0};   // slot 5 swallows unused roles
+      base[a.dim_x] += x0;
+      base[a.dim_y] += y0;
+      base[a.dim_n] += nn0;
+      base[a.dim_z1] += z1 * a.a_z1step;
+      base[a.dim_z0] += z0 * a.a_z0step;
+      const uint32_t tx_bytes = (uint32_t)(a.bw * a.bh * a.bn) * (BK * 2) +
+                                (uint32_t)(a.b_mn_major ? BK : BN) * (BK * 2);
+      const int bcol0 = a.b_c0 + z0 * a.b_z0_cstep;
+      const int brow0 = z1 * a.b_z1_rowstep + (a.b_mn_major ? 0 : n0);
+      for (int it = 0; it < num_iters; ++it) {
+        const int s = it % STAGES;
+        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+        const int tap = it / a.kchunks;
+        const int kc = it - tap * a.kchunks;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+        uint8_t* sa = smem + s * C::stage_bytes;
+        uint8_t* sb = sa + kATileBytes;
+        tma_load_5d(sa, &tmA, &full_bar[s], base[0] + a.tap_off[tap][0] + kc * BK, base[1] + a.tap_off[tap][1],
+                    base[2] + a.tap_off[tap][2], base[3] + a.tap_off[tap][3], base[4] + a.tap_off[tap][4]);
+        if (a.b_mn_major)  // [64 K rows][64 N elements] box of a row-major [K, N] matrix
+          tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + n0, brow0 + kc * BK);
+        else
+          tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + kc * BK, brow0 + tap * a.b_tap_rows);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== UMMA issuer =====================
+    const uint32_t idesc = make_idesc_f16(BM, BN, a.fmt, a.b_mn_major);
+    for (int it = 0; it < num_iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(&full_bar[s], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + s * C::stage_bytes);
+        const uint64_t da = make_desc_kmajor_sw128(sa);
+        // K-major: +32 B per K=16 slice inside the 128-byte swizzle row (start field += 2).
+        // MN-major: a K=16 slice is 16 rows of 128 B (start field += 128).
+        const uint64_t db = a.b_mn_major ? make_desc_mnmajor_sw128(sa + kATileBytes, 8192)
+                                         : make_desc_kmajor_sw128(sa + kATileBytes);
+        const uint32_t bstep = a.b_mn_major ? 128u : 2u;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          umma_f16(tmem_base, da + 2 * k, db + bstep * k, idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+        if (it == num_iters - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;             // TMEM lane quarter this warp may read
+    const int r = q * 32 + lane;        // output row inside the tile
+    const int xi = r % a.bw;
+    const int yi = (r / a.bw) % a.bh;
+    const int ni = r / (a.bw * a.bh);
+    const bool row_ok = (ni < a.bn) && (x0 + xi < a.W) && (y0 + yi < a.H) && (nn0 + ni < a.N);
+    const long long pix = ((long long)(nn0 + ni) * a.H + (y0 + yi)) * a.W + (x0 + xi);
+    const long long zoff = (long long)z1 * a.out_z1stride + (long long)z0 * a.out_z0stride;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    if constexpr (BN >= 32) {
+      if (a.geglu) {
+        if constexpr (BN == 128) {
+          const int ocol_tile = blockIdx.y * 64;
+#pragma unroll 1
+          for (int c = 0; c < 64; c += 32) {
+            uint32_t v[32], g[32];
+            tmem_ld_32x32(trow + c, v);
+            tmem_ld_32x32(trow + 64 + c, g);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int vc = n0 + c + j, gc = n0 + 64 + c + j;
+              float val = __uint_as_float(v[j]) * a.scale;
+              float gate = __uint_as_float(g[j]) * a.scale;
+              if (a.bias != nullptr) {
+                if (vc < a.n_total) val += __ldg(a.bias + vc);
+                if (gc < a.n_total) gate += __ldg(a.bias + gc);
+              }
+              f[j] = val * gelu_erf(gate);
+            }
+            finish_and_store<32>(f, a, pix, zoff, ocol_tile + c, 0, a.n_total / 2 - (ocol_tile + c), row_ok);
+          }
+        }
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + c, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
+          finish_and_store<32>(f, a, pix, zoff, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
+        }
+      }
+    } else {
+      uint32_t v[16];
+      tmem_ld_32x16(trow, v);
+      tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
+      finish_and_store<16>(f, a, pix, zoff, n0, n0, a.n_total - n0, row_ok);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  });
+  return fn;
+}
+
+template <int BN>
+int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args, int batch,
+              cudaStream_t stream) {
+  using C = Cfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         C::smem_bytes);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int m_tiles = args.tiles_x * args.tiles_y * args.tiles_n;
+  const int n_tiles = (args.n_total + BN - 1) / BN;
+  dim3 grid(m_tiles, n_tiles, batch);
+  tapgemm_kernel<BN><<<grid, kThreads, C::smem_bytes, stream>>>(tmA, tmB, args);
+  return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int encode_tmap(CUtensorMap* out, const TmapDesc& d) {
+  PFN_encodeTiled fn = get_encode_fn();
+  if (fn == nullptr) return -1;
+  cuuint64_t dims[5];
+  cuuint64_t strides[4];
+  cuuint32_t box[5], estr[5];
+  for (int i = 0; i < d.rank; ++i) {
+    dims[i] = d.dims[i];
+    box[i] = d.box[i];
+    estr[i] = 1;
+  }
+  for (int i = 0; i + 1 < d.rank; ++i) strides[i] = d.strides[i];
+  CUresult r = fn(out, d.elem_fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                  (cuuint32_t)d.rank, const_cast<void*>(d.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return (int)r;
+}
+
+int tapgemm_pick_bn(int n_total, int geglu) {
+  if (geglu) return 128;
+  if (n_total <= 16) return 16;
+  if (n_total <= 32) return 32;
+  if (n_total <= 64) return 64;
+  return 128;
+}
+
+int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args, int batch,
+                   cudaStream_t stream) {
+  // the MN-major B path stages [64 K][64 N] boxes: 64-wide N tiles only
+  switch (args.b_mn_major ? 64 : tapgemm_pick_bn(args.n_total, args.geglu)) {
+    case 16: return launch_bn<16>(tmA, tmB, args, batch, stream);
+    case 32: return launch_bn<32>(tmA, tmB, args, batch, stream);
+    case 64: return launch_bn<64>(tmA, tmB, args, batch, stream);
+    default: return launch_bn<128>(tmA, tmB, args, batch, stream);
+  }
+}
+
+}  // namespace ug

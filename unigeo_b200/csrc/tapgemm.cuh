@@ -1,0 +1,81 @@
+// tapgemm: the one tensor-core workhorse of the hot path.
+//
+//   D[pixel, cout] = sum_{tap} sum_{cin} A[pixel shifted by tap, cin] * W[tap][cout][cin]
+//
+// A is a 16-bit channels-last activation tensor described by a <=5-D TMA tensor map;
+// every (tap, 64-channel chunk) is ONE box load whose out-of-bounds elements TMA
+// zero-fills, which is exactly the zero padding of a 3x3 conv, of the (3,1,1)
+// temporal conv at clip edges, and of the K tail.  With one tap it is a plain
+// (batched) GEMM  D = A * W^T.  Accumulation runs on tcgen05 (UMMA 128 x BN x 16,
+// fp32 in TMEM); the epilogue reads TMEM with tcgen05.ld and fuses bias,
+// per-frame bias (time embedding / collapsed cross-attention), residual add,
+// AlphaBlender mixing and GEGLU gating before the store.
+//
+// Replaces (reference -> [UPSTREAM] diffusers): cuDNN Conv2d/Conv3d
+// implicit GEMMs and cuBLASLt linear layers of the SVD UNet / temporal VAE.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace ug {
+
+constexpr int kMaxTaps = 9;
+
+struct TapGemmArgs {
+  // ---- M tiling over the OUTPUT pixel grid (n, y, x); pixel = (n*H + y)*W + x
+  int tiles_x, tiles_y, tiles_n;
+  int bw, bh, bn;          // box extent: rows per tile = bw*bh*bn <= 128
+  int W, H, N;
+  int dim_x, dim_y, dim_n; // which A-map coordinate (1..4) carries x / y / n (5 = unused)
+  // batch index z = blockIdx.z splits as z1 = z / zdiv, z0 = z % zdiv (e.g. frame, head):
+  //   A coordinate[dim_z1] += z1 * a_z1step ; A coordinate[dim_z0] += z0 * a_z0step
+  // (coordinate 0 is the channel coordinate; use dim 5 for "none")
+  int zdiv, dim_z1, a_z1step, dim_z0, a_z0step;
+  // ---- K loop
+  int num_taps, kchunks;   // iterations = num_taps * kchunks, 64 channels each
+  int tap_off[kMaxTaps][5];
+  int b_tap_rows;          // B row offset per tap
+  int b_z1_rowstep;        // B row offset per z1
+  int b_z0_cstep;          // B column (dim-0) offset per z0
+  int b_c0;                // B column (dim-0) base offset
+  int b_mn_major;          // B tile is [K rows][64 N elements] (e.g. V of attention): needs BN == 64
+  // ---- epilogue
+  int n_total;             // valid output columns (before GEGLU halving)
+  int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
+  int out_fp32;
+  int geglu;               // columns [0,64) of each 128-wide tile gate-multiplied by gelu([64,128))
+  void* out;
+  long long ldc;
+  long long out_z1stride, out_z0stride;   // element offsets per z1 / z0
+  const float* bias;       // [n_total]
+  const float* fbias;      // [frames][fbias_ld], frame = pixel / fbias_div
+  int fbias_ld, fbias_div;
+  const void* res;         // 16-bit residual, same pixel indexing
+  long long ldr;
+  const void* blend;       // out = alpha * blend + (1 - alpha) * value
+  long long ldb;
+  float alpha;
+  float scale;             // value = acc * scale + ...
+};
+
+// Host-side helpers -----------------------------------------------------------------
+struct TmapDesc {
+  const void* ptr;
+  int elem_fmt;                 // 0 fp16, 1 bf16
+  int rank;                     // 2..5
+  unsigned long long dims[5];
+  unsigned long long strides[4];   // bytes, dims 1..rank-1
+  unsigned int box[5];
+};
+
+// Encodes a SWIZZLE_128B tiled tensor map; returns cudaSuccess-like 0 or non-zero.
+int encode_tmap(CUtensorMap* out, const TmapDesc& d);
+
+// Launch; BN is chosen from n_total.  Returns cudaError_t as int.
+int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args, int batch,
+                   cudaStream_t stream);
+
+int tapgemm_pick_bn(int n_total, int geglu);
+
+}  // namespace ug
