@@ -1,0 +1,159 @@
+"""Host-side owner of one ``ug_ctx``: weights in, tensors through the C ABI, tensors out.
+
+PyTorch is used for device memory and streams only; every FLOP of the UNet / VAE runs in
+libunigeo_b200.so.  Tensors at this level are fp32 CUDA tensors in the upstream layouts
+(see include/unigeo_b200.h), so callers read like the [UPSTREAM] pipeline they replace
+(reference call site: /root/reference/model/depthcrafter.py:80-90).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Iterable, Tuple
+
+import torch
+
+from . import _lib
+from .config import PipelineConfig
+
+_DTYPES = {"fp16": _lib.UG_F16, "float16": _lib.UG_F16, "bf16": _lib.UG_BF16, "bfloat16": _lib.UG_BF16}
+_TORCH_TO_UG = {torch.float16: _lib.UG_F16, torch.bfloat16: _lib.UG_BF16, torch.float32: _lib.UG_F32}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t: torch.Tensor, device) -> torch.Tensor:
+    return t.to(device=device, dtype=torch.float32).contiguous()
+
+
+class Engine:
+    """One context = one GPU = one model replica (clip-sharded data parallelism above it)."""
+
+    def __init__(self, cfg: PipelineConfig, dtype: str = "fp16", device: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("unigeo_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
+        if dtype not in _DTYPES:
+            raise ValueError(f"dtype must be one of {sorted(_DTYPES)}")
+        self.lib = _lib.load()
+        self.cfg = cfg
+        self.dtype = dtype
+        self.device = torch.device("cuda", device)
+        self._cfg_struct = _lib.cfg_struct(cfg, _DTYPES[dtype])
+        self._ctx = C.c_void_p()
+        _lib.check(self.lib.ug_ctx_create(C.byref(self._ctx), device, C.byref(self._cfg_struct)))
+        self._shape: Tuple[int, int, int] | None = None
+        self._finalized = False
+
+    # ------------------------------------------------------------------ weights
+    def load_state_dict(self, prefix: str, sd: Dict[str, torch.Tensor]) -> None:
+        """``prefix`` is "unet" or "vae"; ``sd`` maps diffusers keys to tensors (any device/dtype)."""
+        with torch.cuda.device(self.device):
+            for key, t in sd.items():
+                if t.dtype not in _TORCH_TO_UG:
+                    t = t.float()
+                t = t.to(self.device).contiguous()
+                shape = (C.c_int64 * t.dim())(*t.shape)
+                _lib.check(self.lib.ug_ctx_load_weight(self._ctx, f"{prefix}.{key}".encode(), t.data_ptr(),
+                                                       _TORCH_TO_UG[t.dtype], shape, t.dim(), _stream()))
+            torch.cuda.current_stream().synchronize()
+        self._finalized = False
+
+    def finalize(self) -> None:
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_ctx_finalize(self._ctx, _stream()))
+        self._finalized = True
+
+    def prepare(self, T: int, h: int, w: int) -> None:
+        if not self._finalized:
+            self.finalize()
+        if self._shape != (T, h, w):
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.ug_ctx_prepare(self._ctx, T, h, w, _stream()))
+            self._shape = (T, h, w)
+
+    # ------------------------------------------------------------------ UNet / denoising
+    def set_clip_context(self, enc: torch.Tensor) -> None:
+        """enc: [T, cross_attention_dim] CLIP image embeddings of the clip's frames."""
+        enc = _f32(enc, self.device)
+        assert self._shape is not None and enc.shape == (self._shape[0], self.cfg.unet.cross_attention_dim)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_set_clip_context(self._ctx, enc.data_ptr(), _stream()))
+
+    def unet_forward(self, x: torch.Tensor, timestep: float, added_time_ids: Iterable[float]) -> torch.Tensor:
+        """x [1,T,8,h,w] -> v [1,T,4,h,w] (needs prepare + set_clip_context)."""
+        x = _f32(x, self.device)
+        _, T, _, h, w = x.shape
+        assert self._shape == (T, h, w), "call prepare(T, h, w) first"
+        ids = (C.c_float * 3)(*[float(v) for v in added_time_ids])
+        out = torch.empty((1, T, self.cfg.unet.out_channels, h, w), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_unet_st_forward(self._ctx, x.data_ptr(), float(timestep), ids, out.data_ptr(),
+                                                   _stream()))
+        return out
+
+    def denoise(self, cond_latents: torch.Tensor, init_noise: torch.Tensor, added_time_ids, steps: int,
+                out: torch.Tensor | None = None) -> torch.Tensor:
+        """Whole Euler/Karras loop. cond_latents, init_noise: [T,4,h,w] fp32 -> latents [T,4,h,w]."""
+        cond = _f32(cond_latents, self.device)
+        noise = _f32(init_noise, self.device)
+        T, _, h, w = cond.shape
+        assert self._shape == (T, h, w), "call prepare(T, h, w) first"
+        ids = (C.c_float * 3)(*[float(v) for v in added_time_ids])
+        if out is None:
+            out = torch.empty_like(cond)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_denoise_clip(self._ctx, cond.data_ptr(), noise.data_ptr(), ids, int(steps),
+                                                out.data_ptr(), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ VAE
+    def vae_encode(self, img: torch.Tensor, noise: torch.Tensor | None = None, noise_strength: float = 0.0,
+                   out: torch.Tensor | None = None) -> torch.Tensor:
+        """img [N,3,H,W] in [-1,1] (+ noise * strength) -> latent mean [N,4,H/8,W/8]."""
+        if not self._finalized:
+            self.finalize()
+        img = _f32(img, self.device)
+        N, _, H, W = img.shape
+        nptr = None
+        if noise is not None:
+            noise = _f32(noise, self.device)
+            nptr = noise.data_ptr()
+        if out is None:
+            out = torch.empty((N, self.cfg.vae.latent_channels, H // 8, W // 8), dtype=torch.float32,
+                              device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_vae_encode(self._ctx, img.data_ptr(), nptr, float(noise_strength), N, H, W,
+                                              out.data_ptr(), _stream()))
+        return out
+
+    def vae_decode(self, latents: torch.Tensor, chunk: int = 8, out: torch.Tensor | None = None) -> torch.Tensor:
+        """latents [T,4,h,w] (scaled) -> frames [T,3,8h,8w]."""
+        if not self._finalized:
+            self.finalize()
+        lat = _f32(latents, self.device)
+        T, _, h, w = lat.shape
+        if out is None:
+            out = torch.empty((T, self.cfg.vae.in_channels, 8 * h, 8 * w), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_vae_decode_temporal(self._ctx, lat.data_ptr(), T, h, w, int(chunk),
+                                                       out.data_ptr(), _stream()))
+        return out
+
+    # ------------------------------------------------------------------ bookkeeping
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self.lib.ug_ctx_launch_count(self._ctx, 1 if reset else 0))
+
+    def workspace_bytes(self) -> int:
+        return int(self.lib.ug_ctx_workspace_bytes(self._ctx))
+
+    def close(self) -> None:
+        if self._ctx:
+            self.lib.ug_ctx_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
