@@ -46,9 +46,9 @@ def surface_normal(xyz: torch.Tensor, patch_size: int = 5) -> torch.Tensor:
     """utils/geometry_utils.py:9-70 on xyz [H,W,3] float32 -> unit normals [H,W,3].
 
     Per-pixel 3x3 systems (A^T A + 1e-6 I) n = A^T 1 over an un-normalised 5x5 box,
-    solved with torch.linalg.lstsq like the reference; each system is independent, so
-    solving all pixels at once equals the reference's 4x4-tile sweep whenever H and W
-    are divisible by 4 (App. B.7).  Normals are flipped to face the camera (n.p <= 0).
+    solved with torch.linalg.lstsq in the reference's 4x4-tile sweep; H and W must be
+    divisible by 4 (App. B.7: otherwise the reference leaves random values behind).
+    Normals are flipped to face the camera (n.p <= 0).
     """
     p = xyz.permute(2, 0, 1)[None].float()                    # [1,3,H,W]
     x, y, z = p[:, 0:1], p[:, 1:2], p[:, 2:3]
@@ -62,7 +62,24 @@ def surface_normal(xyz: torch.Tensor, patch_size: int = 5) -> torch.Tensor:
     ata = torch.stack([xx, xy, xz, xy, yy, yz, xz, yz, zz], dim=-1).reshape(*xx.shape, 3, 3)
     ata = ata + 1e-6 * torch.eye(3)
     at1 = torch.stack([box(x), box(y), box(z)], dim=-1)[..., None]
-    n = torch.linalg.lstsq(ata, at1).solution[..., 0]          # [H,W,3]
+    # :42-62 -- the reference sweeps a 4x4 grid of tiles (each grown by patch//2+1 pixels towards its
+    # neighbours) and keeps the tile interiors; LAPACK's batched driver is sensitive to the batch
+    # it is handed, so the sweep is restated as is to stay bit-identical.
+    H, W = xx.shape
+    tiles = 4
+    th, tw = H // tiles, W // tiles
+    grow = patch_size // 2 + 1
+    n = torch.empty((H, W, 3))
+    for ty in range(tiles):
+        for tx in range(tiles):
+            gy0 = grow if ty > 0 else 0
+            gx0 = grow if tx > 0 else 0
+            gy1 = grow if ty < tiles - 1 else 0
+            gx1 = grow if tx < tiles - 1 else 0
+            ys = slice(ty * th - gy0, (ty + 1) * th + gy1)
+            xs = slice(tx * tw - gx0, (tx + 1) * tw + gx1)
+            sol = torch.linalg.lstsq(ata[ys, xs], at1[ys, xs]).solution[..., 0]
+            n[ty * th:(ty + 1) * th, tx * tw:(tx + 1) * tw] = sol[gy0:gy0 + th, gx0:gx0 + tw]
     n = n / torch.sqrt(torch.sum(n ** 2, dim=2, keepdim=True))
     flip = torch.sum(n * xyz.float(), dim=2) > 0
     n[flip] *= -1

@@ -1,0 +1,125 @@
+"""Generates the committed golden fixtures by running the UNMODIFIED reference code
+(/root/reference, dev container only):
+
+  metrics_kat.npz      metrics/eval_depth.py::depth_evaluation(align_with_lstsq=True, custom_mask)
+                       metrics/eval_normal.py::normal_evaluation           (as eval.py:49,54 call them)
+  depthcrafter_post.npz  model/depthcrafter.py::DepthCrafter.forward with the upstream pipeline replaced
+                       by a stub returning fixed frames -> pins prepare_input (:39-45), the
+                       disparity->depth lines (:92-97) and prepare_output (:48-69, incl.
+                       utils/geometry_utils.py::backproject_to_cv_position / get_surface_normal)
+  stablenormal_post.npz  model/stablenormal.py::StableNormal.forward with a stub predictor (:30-52)
+  oracle_tiny.npz      output of oracle.pipeline on the tiny config (regression pin of the restatement
+                       itself; there is no upstream code here to pin it against -- "parity unpinned")
+
+Run:  python tests/golden/make_golden.py
+"""
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+from harness import refload  # noqa: E402
+from harness.synthetic import gt_label, make_clip  # noqa: E402
+
+
+def metrics_kat():
+    ed, en = refload.metrics_eval_depth(), refload.metrics_eval_normal()
+    g = torch.Generator().manual_seed(42)
+    Nf, H, W = 3, 32, 48
+    gt = torch.rand(Nf, H, W, generator=g) * 9 + 0.5
+    gt[0, :4, :5] = 0.0            # invalid (gt == 0)
+    gt[1, 10:12, :] = 100.0        # beyond max_depth
+    pred = 0.37 * gt + 0.8 + 0.3 * torch.randn(Nf, H, W, generator=g)
+    mask = torch.rand(Nf, H, W, generator=g) > 0.1
+    res = ed.depth_evaluation(pred.clone(), gt.clone(), custom_mask=mask.clone(), align_with_lstsq=True)[0]
+    pn = torch.nn.functional.normalize(torch.randn(Nf, H, W, 3, generator=g), dim=-1)
+    gn = torch.nn.functional.normalize(pn + 0.4 * torch.randn(Nf, H, W, 3, generator=g), dim=-1)
+    nres = en.normal_evaluation(pn.clone(), gn.clone(), custom_mask=mask.clone())
+    np.savez_compressed(os.path.join(OUT, "metrics_kat.npz"), pred=pred.numpy(), gt=gt.numpy(), mask=mask.numpy(),
+                        pn=pn.numpy(), gn=gn.numpy(),
+                        depth_keys=np.array(list(res)), depth_vals=np.array([float(v) for v in res.values()]),
+                        normal_keys=np.array(list(nres)), normal_vals=np.array([float(v) for v in nres.values()]))
+    print("metrics_kat", res, nres)
+
+
+def depthcrafter_post():
+    sys.path.insert(0, refload.REF)                      # reference adapter does `from utils.geometry_utils import ...`
+    mod = refload._load("model", "depthcrafter")
+    data = make_clip(3, 32, 48, seed=7)
+    # fractional pixel values exercise the uint8 truncation of prepare_input (:43)
+    data["images"] = [np.clip(x + 0.7, 0, 255) for x in data["images"]]
+    g = torch.Generator().manual_seed(3)
+    jj, ii = np.meshgrid(np.arange(32), np.arange(48), indexing="ij")
+    smooth = 0.5 + 0.3 * np.sin(ii / 9.0)[None, :, :, None] * np.cos(jj / 7.0)[None, :, :, None]
+    frames = (smooth + 0.02 * torch.rand(3, 32, 48, 3, generator=g).numpy()).astype(np.float32)
+    frames = np.clip(frames + np.arange(3).reshape(3, 1, 1, 1) * 0.03, 0, 1).astype(np.float32)
+    seen = {}
+
+    def stub_pipeline(fr, **kw):
+        seen["frames_in"] = np.array(fr)
+        seen["kwargs"] = {k: v for k, v in kw.items()}
+        return types.SimpleNamespace(frames=[frames.copy()])
+
+    obj = object.__new__(mod.DepthCrafter)
+    obj.pipeline = stub_pipeline
+    torch.manual_seed(0)
+    out = obj.forward(data)
+    np.savez_compressed(
+        os.path.join(OUT, "depthcrafter_post.npz"),
+        images=np.stack(data["images"]), intrinsics=np.stack(data["intrinsics"]), frames=frames,
+        prepared_input=seen["frames_in"], pred_depths=out["pred_depths"].numpy(),
+        pred_normals=out["pred_normals"].numpy(),
+        call_steps=np.array(seen["kwargs"]["num_inference_steps"]), call_guidance=np.array(seen["kwargs"]["guidance_scale"]),
+        call_window=np.array(seen["kwargs"]["window_size"]), call_overlap=np.array(seen["kwargs"]["overlap"]))
+    print("depthcrafter_post", out["pred_depths"].shape, out["pred_normals"].shape, seen["kwargs"])
+
+
+def stablenormal_post():
+    from PIL import Image
+    mod = refload._load("model", "stablenormal")
+    data = make_clip(2, 16, 24, seed=9)
+    rng = np.random.default_rng(5)
+    preds = [rng.integers(0, 256, (16, 24, 3), dtype=np.uint8) for _ in range(2)]
+    preds[0][0, :4, 0] = [0, 1, 200, 255]                # the wraparound cases of App. B.10
+    it = iter(preds)
+    obj = object.__new__(mod.StableNormal)
+    obj.predictor = lambda im: Image.fromarray(next(it))
+    out = obj.forward(data)
+    np.savez_compressed(os.path.join(OUT, "stablenormal_post.npz"), preds=np.stack(preds),
+                        pred_normals=out["pred_normals"].numpy(), pred_depths=out["pred_depths"].numpy())
+    print("stablenormal_post", out["pred_normals"].shape)
+
+
+def oracle_tiny():
+    from oracle.pipeline import depthcrafter_pipeline
+    from unigeo_b200.config import tiny_config
+    from unigeo_b200.weights import synthetic_state_dict, unet_param_shapes, vae_param_shapes
+    cfg = tiny_config()
+    usd = synthetic_state_dict(unet_param_shapes(cfg.unet), 11)
+    vsd = synthetic_state_dict(vae_param_shapes(cfg.vae), 12)
+    g = torch.Generator().manual_seed(99)
+    T, H, W = 2, 64, 64
+    frames = torch.rand(T, H, W, 3, generator=g)
+    enc = torch.randn(1, T, cfg.clip_embed_dim, generator=g)
+    aug = torch.randn(T, 3, H, W, generator=g)
+    init = torch.randn(1, T, 4, H // 8, W // 8, generator=g)
+    with torch.no_grad():
+        out = depthcrafter_pipeline(usd, vsd, cfg, frames, enc, aug, init, 2)
+    np.savez_compressed(os.path.join(OUT, "oracle_tiny.npz"), out=out.numpy().astype(np.float16),
+                        mean=np.array(out.mean().item()), std=np.array(out.std().item()))
+    print("oracle_tiny", out.shape, out.mean().item(), out.std().item())
+
+
+if __name__ == "__main__":
+    if not refload.available():
+        raise SystemExit("needs /root/reference (dev container)")
+    metrics_kat()
+    depthcrafter_post()
+    stablenormal_post()
+    oracle_tiny()

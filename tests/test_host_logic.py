@@ -1,0 +1,150 @@
+"""Host-side logic that needs no GPU: configs, weight inventory, scheduler, sharding maths,
+synthetic harness data, C-ABI surface."""
+import math
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_param_inventory_matches_svd_sizes():
+    from unigeo_b200.config import full_config
+    from unigeo_b200.weights import count_params, unet_param_shapes, vae_param_shapes
+    cfg = full_config()
+    nu = count_params(unet_param_shapes(cfg.unet))
+    nv = count_params(vae_param_shapes(cfg.vae))
+    assert abs(nu - 1.5246e9) < 1e6          # SVD-XT UNet ~1.52 B
+    assert abs(nv - 97.7e6) < 1e5            # temporal-decoder VAE ~98 M
+    us = unet_param_shapes(cfg.unet)
+    assert us["up_blocks.1.resnets.2.spatial_res_block.conv1.weight"] == (1280, 1920, 3, 3)
+    assert us["down_blocks.0.attentions.0.transformer_blocks.0.attn2.to_k.weight"] == (320, 1024)
+    assert us["down_blocks.2.resnets.0.temporal_res_block.conv1.weight"] == (1280, 1280, 3, 1, 1)
+
+
+def test_synthetic_weights_are_deterministic_and_nonzero():
+    from unigeo_b200.config import tiny_config
+    from unigeo_b200.weights import synthetic_state_dict, vae_param_shapes
+    s = vae_param_shapes(tiny_config().vae)
+    a, b = synthetic_state_dict(s, 5), synthetic_state_dict(s, 5)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert all(t.abs().sum() > 0 for t in a.values())
+    assert abs(a["decoder.conv_norm_out.weight"].mean().item() - 1.0) < 0.05
+
+
+def test_scheduler_matches_oracle_and_closed_form():
+    from oracle import scheduler as O
+    from unigeo_b200 import scheduler as S
+    for n in (1, 5, 25):
+        a, b = S.karras_sigmas(n), O.karras_sigmas(n)
+        assert a == b and len(a) == n + 1 and a[-1] == 0.0
+        assert abs(a[0] - 700.0) < 1e-9
+        if n > 1:
+            assert abs(a[n - 1] - 0.002) < 1e-12
+        assert S.unet_timesteps(a) == O.timesteps_from_sigmas(b)
+        assert abs(S.init_noise_sigma(a) - math.sqrt(700.0 ** 2 + 1)) < 1e-9
+    # Euler step towards sigma_next = 0 returns the x0 prediction
+    x, v = torch.randn(7), torch.randn(7)
+    s = 3.0
+    x0 = v * (-s / math.sqrt(s * s + 1)) + x / (s * s + 1)
+    assert torch.allclose(O.euler_step(v, x, s, 0.0), x0, atol=1e-6)
+
+
+def test_geglu_interleave_layout():
+    from unigeo_b200.ops import geglu_interleave
+    H, K = 128, 8
+    W = torch.arange(2 * H * K, dtype=torch.float32).view(2 * H, K)
+    b = torch.arange(2 * H, dtype=torch.float32)
+    Wi, bi = geglu_interleave(W, b)
+    assert torch.equal(Wi[0:64], W[0:64]) and torch.equal(Wi[64:128], W[H:H + 64])
+    assert torch.equal(Wi[128:192], W[64:128]) and torch.equal(Wi[192:256], W[H + 64:H + 128])
+    assert torch.equal(bi[64:128], b[H:H + 64])
+
+
+def test_adapter_prepare_input_truncates():
+    from unigeo_b200.model.depthcrafter import DepthCrafter
+    data = {"images": [np.full((3, 4, 4), 17.9, np.float32), np.full((3, 4, 4), 255.0, np.float32)]}
+    out = DepthCrafter.prepare_input(None, data)
+    assert out.shape == (2, 4, 4, 3) and out.dtype == np.float32
+    assert out[0, 0, 0, 0] == np.float32(17) / np.float32(255) and out[1].max() == 1.0
+
+
+def test_stablenormal_requires_predictor():
+    from unigeo_b200.model import StableNormal
+    with pytest.raises(RuntimeError):
+        StableNormal()
+
+
+def test_synthetic_clip_unified_format():
+    from harness.synthetic import gt_label, make_clip
+    d = make_clip(3, 32, 48)
+    assert len(d["images"]) == 3 and d["images"][0].shape == (3, 32, 48) and d["images"][0].dtype == np.float32
+    assert d["intrinsics"][0].shape == (3, 3) and d["cam_normal"][0].shape == (3, 32, 48)
+    g = gt_label(d)
+    assert g["gt_depths"].min() >= 0.5 and g["gt_depths"].max() <= 8.0
+    assert torch.allclose(g["gt_normals"].norm(dim=-1), torch.ones(3, 32, 48), atol=1e-4)
+
+
+def test_sharding_assignment_and_stitch_single_process():
+    from unigeo_b200 import sharding as sh
+    assert sh.clips_of_rank(8, 1, 4) == [1, 5]
+    assert sh.clip_starts(165, 25, 5)[:3] == [0, 20, 40]
+    # a scene with a global depth ramp, cut into clips that are each affinely distorted
+    T, ov, n = 10, 3, 4
+    starts = [k * (T - ov) for k in range(n)]
+    N = starts[-1] + T
+    scene = torch.linspace(1, 5, N).view(N, 1, 1) + torch.rand(N, 6, 8) * 0.5
+    clips = [scene[s:s + T] * (1.0 + 0.3 * k) - 0.2 * k for k, s in enumerate(starts)]
+    st = sh.stitch_scene(clips, list(range(n)), n, ov)
+    video = sh.assemble_scene(st, starts, N, ov)
+    assert video.shape == scene.shape
+    assert torch.allclose(video, scene, atol=1e-4)
+
+
+def test_fit_scale_shift_exact():
+    from unigeo_b200.sharding import fit_scale_shift
+    x = torch.rand(100, dtype=torch.float64)
+    s, t = fit_scale_shift(x, 2.5 * x - 0.75)
+    assert abs(s.item() - 2.5) < 1e-9 and abs(t.item() + 0.75) < 1e-9
+
+
+def test_abi_header_and_library_agree():
+    """The shared library loads without a GPU and exports every function include/*.h declares."""
+    from unigeo_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "unigeo_b200.h")).read()
+    declared = set(re.findall(r"\b(ug_[a-z0-9_]+)\s*\(", hdr))
+    lib = _lib.load()
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.ug_version() == 100
+
+
+def test_abi_fails_cleanly_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import ctypes as C
+    from unigeo_b200 import _lib
+    from unigeo_b200.config import tiny_config
+    lib = _lib.load()
+    ctx = C.c_void_p()
+    cfg = _lib.cfg_struct(tiny_config(), _lib.UG_F16)
+    rc = lib.ug_ctx_create(C.byref(ctx), 0, C.byref(cfg))
+    assert rc != 0 and not ctx.value
+    assert len(lib.ug_last_error()) > 0
+    from unigeo_b200.engine import Engine
+    with pytest.raises(RuntimeError):
+        Engine(tiny_config())
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "unigeo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "harness" not in src or f == "__init__.py", f

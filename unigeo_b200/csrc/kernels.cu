@@ -40,12 +40,16 @@ __device__ __forceinline__ const uint4* cat_ptr(const void* x1, int nv1, const v
 }
 
 // ------------------------------------------------------------------ GroupNorm statistics
+// Deterministic two-level reduction (no atomics): every CTA reduces its row chunk in a fixed
+// order and writes one (sum, sumsq) pair per group to part[set][chunk][G][2]; the apply
+// kernel adds the chunks in index order.  Reruns are bit-identical.
 template <typename T>
 __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
                                 long long rows_per_set, long long chunk_rows, int G, int cs,
-                                float* __restrict__ stats) {
-  __shared__ float s_sum[64], s_sq[64];
+                                float* __restrict__ part) {
+  extern __shared__ float s_part[];   // [rpb][C] sums, then [rpb][C] sumsq
   const int nvec = nv1 + nv2;
+  const int C = nvec * 8;
   const int rpb = blockDim.x / nvec;
   const int c8 = threadIdx.x % nvec;
   const int rr = threadIdx.x / nvec;
@@ -53,8 +57,6 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void
   const long long r_begin = (long long)blockIdx.x * chunk_rows;
   long long r_end = r_begin + chunk_rows;
   if (r_end > rows_per_set) r_end = rows_per_set;
-  if (threadIdx.x < 64) { s_sum[threadIdx.x] = 0.f; s_sq[threadIdx.x] = 0.f; }
-  __syncthreads();
   float a[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
@@ -66,24 +68,23 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void
 #pragma unroll
       for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] += f[j] * f[j]; }
     }
-    // fold the 8 channels into their groups (runs of equal group index are merged first)
-    int g_prev = (c8 * 8) / cs;
-    float sa = 0.f, sq = 0.f;
+    float* ps = s_part + (size_t)rr * C + c8 * 8;
+    float* pq = s_part + (size_t)(rpb + rr) * C + c8 * 8;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int g = (c8 * 8 + j) / cs;
-      if (g != g_prev) {
-        atomicAdd(&s_sum[g_prev], sa); atomicAdd(&s_sq[g_prev], sq);
-        sa = 0.f; sq = 0.f; g_prev = g;
-      }
-      sa += a[j]; sq += q[j];
-    }
-    atomicAdd(&s_sum[g_prev], sa); atomicAdd(&s_sq[g_prev], sq);
+    for (int j = 0; j < 8; ++j) { ps[j] = a[j]; pq[j] = q[j]; }
   }
   __syncthreads();
   if (threadIdx.x < G) {
-    atomicAdd(&stats[(set * G + threadIdx.x) * 2 + 0], s_sum[threadIdx.x]);
-    atomicAdd(&stats[(set * G + threadIdx.x) * 2 + 1], s_sq[threadIdx.x]);
+    const int g = threadIdx.x;
+    float sa = 0.f, sq = 0.f;
+    for (int r = 0; r < rpb; ++r)
+      for (int cc = g * cs; cc < (g + 1) * cs; ++cc) {
+        sa += s_part[(size_t)r * C + cc];
+        sq += s_part[(size_t)(rpb + r) * C + cc];
+      }
+    float* o = part + ((set * gridDim.x + blockIdx.x) * G + g) * 2;
+    o[0] = sa;
+    o[1] = sq;
   }
 }
 
@@ -91,24 +92,36 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void
 template <typename T>
 __global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
                                 long long rows_per_set, long long chunk_rows, int G, int cs,
-                                const float* __restrict__ stats, const float* __restrict__ gamma,
+                                const float* __restrict__ part, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, float eps, int silu, void* __restrict__ y) {
-  extern __shared__ float s_ab[];   // [C] scale, [C] shift
+  extern __shared__ float s_ab[];   // [C] scale, [C] shift, [G] mean, [G] rstd
   const int nvec = nv1 + nv2;
   const int C = nvec * 8;
   float* s_a = s_ab;
   float* s_b = s_ab + C;
+  float* s_mean = s_b + C;
+  float* s_rstd = s_mean + G;
   const long long set = blockIdx.y;
   const float inv_cnt = 1.0f / ((float)rows_per_set * (float)cs);
+  if (threadIdx.x < G) {
+    const int g = threadIdx.x;
+    float sa = 0.f, sq = 0.f;
+    for (int ch = 0; ch < (int)gridDim.x; ++ch) {
+      const float* o = part + ((set * gridDim.x + ch) * G + g) * 2;
+      sa += o[0];
+      sq += o[1];
+    }
+    const float mean = sa * inv_cnt;
+    const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cs;
-    const float mean = stats[(set * G + g) * 2 + 0] * inv_cnt;
-    float var = stats[(set * G + g) * 2 + 1] * inv_cnt - mean * mean;
-    var = fmaxf(var, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float ga = gamma[c] * rstd;
+    const float ga = gamma[c] * s_rstd[g];
     s_a[c] = ga;
-    s_b[c] = beta[c] - mean * ga;
+    s_b[c] = beta[c] - s_mean[g] * ga;
   }
   __syncthreads();
   const long long r_begin = (long long)blockIdx.x * chunk_rows;
@@ -501,7 +514,7 @@ inline GnGeom gn_geom(int nvec, long long rows_per_set, long long sets) {
   GnGeom g;
   int rpb = 256 / nvec;
   if (rpb < 1) rpb = 1;
-  g.threads = nvec * rpb;
+  g.threads = nvec * rpb;   // >= 64 whenever C >= 64 * 8 / rpb ... padded below for tiny C
   if (g.threads < 64) g.threads = 64;
   long long want = (148LL * 4 + sets - 1) / sets;
   long long maxc = (rows_per_set + rpb * 4 - 1) / (rpb * 4);
@@ -514,6 +527,12 @@ inline GnGeom gn_geom(int nvec, long long rows_per_set, long long sets) {
 
 }  // namespace
 
+long long gn_partial_floats(int C, long long rows, long long rows_per_set, int G) {
+  const long long sets = rows / rows_per_set;
+  GnGeom g = gn_geom(C / 8, rows_per_set, sets);
+  return sets * g.chunks * G * 2;
+}
+
 int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
                     int G, float* stats, int fmt, cudaStream_t st) {
   const int C = C1 + C2;
@@ -521,8 +540,10 @@ int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long ro
   const long long sets = rows / rows_per_set;
   GnGeom g = gn_geom(C / 8, rows_per_set, sets);
   dim3 grid(g.chunks, (unsigned)sets);
-  UG_DISPATCH_FMT(fmt, (gn_stats_kernel<T><<<grid, g.threads, 0, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
-                                                                         g.chunk_rows, G, C / G, stats)));
+  const int rpb = g.threads / (C / 8);
+  const size_t smem = (size_t)2 * rpb * C * sizeof(float);
+  UG_DISPATCH_FMT(fmt, (gn_stats_kernel<T><<<grid, g.threads, smem, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
+                                                                           g.chunk_rows, G, C / G, stats)));
   return last_err();
 }
 
@@ -534,7 +555,7 @@ int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long ro
   const long long sets = rows / rows_per_set;
   GnGeom g = gn_geom(C / 8, rows_per_set, sets);
   dim3 grid(g.chunks, (unsigned)sets);
-  const size_t smem = (size_t)C * 2 * sizeof(float);
+  const size_t smem = (size_t)(C * 2 + G * 2) * sizeof(float);
   UG_DISPATCH_FMT(fmt, (gn_apply_kernel<T><<<grid, 256, smem, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
                                                                       g.chunk_rows, G, C / G, stats, gamma, beta,
                                                                       eps, silu, y)));

@@ -11,7 +11,9 @@ namespace ug {
 // Statistics set s covers rows [s*rows_per_set, (s+1)*rows_per_set): one frame for a
 // spatial GroupNorm, the whole clip for the temporal-resnet GroupNorm.  The input may be
 // the channel concatenation [x1 (C1) | x2 (C2)] (UNet skip connections); C = C1 + C2.
-// stats: [sets][G][2] fp32 (sum, sumsq) -- must be zero on entry.
+// stats: per-CTA partial (sum, sumsq) pairs, gn_partial_floats(...) floats; no zeroing needed,
+// no atomics: the result is bit-identical from run to run.
+long long gn_partial_floats(int C, long long rows, long long rows_per_set, int G);
 int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
                     int G, float* stats, int fmt, cudaStream_t st);
 // y = act((x - mean) * rstd * gamma + beta), act = SiLU when silu != 0; y is [rows][C] dense.

@@ -318,9 +318,9 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
   const int G = c.cfg.norm_groups;
   const long long sets = rows / rows_per_set;
   const size_t m = c.ws.mark();
-  float* stats = c.allocf(sets * G * 2);
+  (void)sets;
+  float* stats = c.allocf(gn_partial_floats(C1 + C2, rows, rows_per_set, G));
   if (!c.dry) {
-    UG_CUDA(cudaMemsetAsync(stats, 0, (size_t)sets * G * 2 * sizeof(float), c.stream));
     op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, stats, c.fmt, c.stream), "gn_stats");
     op_check(c, launch_gn_apply(x1, C1, x2, C2, rows, rows_per_set, G, stats, gamma, beta, eps, silu, y, c.fmt,
                                 c.stream),

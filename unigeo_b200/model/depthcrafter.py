@@ -1,0 +1,78 @@
+"""``DepthCrafter`` plugin adapter on the B200 engine.
+
+Same contract as the reference adapter (/root/reference/model/depthcrafter.py):
+  ctor   DepthCrafter(model_dir, unet_path, pre_train_path, **kwargs)     :8
+  call   forward(data) -> {'pred_depths' [Nf,H,W], 'pred_normals' [Nf,H,W,3]} CPU float32  :73-99
+  input  data['images'] list of [3,H,W] float 0..255 (uint8-truncated, /255)      :39-45
+         data['intrinsics'] list of [3,3]                                          :49
+Extra, optional ``model_params`` (ride in **kwargs like the reference tolerates):
+  config="full"|"tiny", dtype="fp16"|"bf16", num_inference_steps=5, seed=None,
+  weights="synthetic"|"pretrained", device=0, clip="random"|"none".
+There is no CPU path: constructing this class without a B200 raises.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import numpy as np
+import torch
+
+from ..clip_embed import ClipEmbedder
+from ..config import get_config
+from ..engine import Engine
+from ..pipeline import DepthCrafterPipelineB200
+from ..postprocess import depth_and_normals
+from ..weights import load_diffusers_dir, synthetic_state_dict, unet_param_shapes, vae_param_shapes
+
+
+class DepthCrafter:
+    def __init__(self, model_dir: Optional[str] = None, unet_path: Optional[str] = None,
+                 pre_train_path: Optional[str] = None, **kwargs):
+        self.device = torch.device("cuda", int(kwargs.get("device", 0)))
+        self.cfg = get_config(kwargs.get("config", "full"))
+        self.dtype = kwargs.get("dtype", "fp16")                 # reference: torch_dtype=float16 (:21,:27)
+        self.num_inference_steps = int(kwargs.get("num_inference_steps", 5))   # reference hard-codes 5 (:86)
+        self.seed = kwargs.get("seed")
+        weights = kwargs.get("weights")
+        if weights is None:
+            weights = "pretrained" if unet_path and os.path.isdir(unet_path) else "synthetic"
+        self.engine = Engine(self.cfg, dtype=self.dtype, device=self.device.index)
+        clip_dir = None
+        if weights == "pretrained":
+            self.engine.load_state_dict("unet", load_diffusers_dir(unet_path))
+            self.engine.load_state_dict("vae", load_diffusers_dir(os.path.join(pre_train_path, "vae")))
+            clip_dir = os.path.join(pre_train_path, "image_encoder")
+        else:
+            s = int(kwargs.get("weight_seed", 0))
+            self.engine.load_state_dict("unet", synthetic_state_dict(unet_param_shapes(self.cfg.unet), 1000 + s))
+            self.engine.load_state_dict("vae", synthetic_state_dict(vae_param_shapes(self.cfg.vae), 2000 + s))
+        self.engine.finalize()
+        clip = None
+        if kwargs.get("clip", "random") != "none":
+            clip = ClipEmbedder(self.cfg.clip_embed_dim, self.device,
+                                torch.float16 if self.dtype == "fp16" else torch.bfloat16,
+                                pretrained=clip_dir if clip_dir and os.path.isdir(clip_dir) else None)
+        self.pipeline = DepthCrafterPipelineB200(self.cfg, self.engine, clip)
+        print(f"Using device: {self.device}")
+
+    def prepare_input(self, data):
+        """reference :39-45 -- uint8 TRUNCATION (astype), then /255."""
+        frames = [np.asarray(x).transpose(1, 2, 0).astype(np.uint8) for x in data["images"]]
+        return np.stack(frames, axis=0).astype(np.float32) / 255.0
+
+    def prepare_output(self, frames: torch.Tensor, data):
+        """reference :92-97 + :48-69 on the device; returns CPU float32 tensors."""
+        K = torch.from_numpy(np.stack([np.asarray(k, dtype=np.float32) for k in data["intrinsics"]], 0))
+        depth, normals = depth_and_normals(frames, K.to(frames.device))
+        return {"pred_depths": depth.float().cpu(), "pred_normals": normals.float().cpu()}
+
+    def forward(self, data, **debug_inputs):
+        """``debug_inputs``: enc / aug_noise / init_noise tensors to pin the random draws (parity tests)."""
+        frames = self.prepare_input(data)
+        gen = None
+        if self.seed is not None:
+            gen = torch.Generator().manual_seed(int(self.seed))
+        out = self.pipeline(frames, num_inference_steps=self.num_inference_steps, generator=gen,
+                            output_type="pt", **debug_inputs)
+        return self.prepare_output(out, data)

@@ -237,3 +237,21 @@ def count_params(shapes: Shapes) -> int:
             p *= x
         n += p
     return n
+
+
+def load_diffusers_dir(path: str) -> Dict[str, torch.Tensor]:
+    """Read every ``*.safetensors`` in a diffusers model directory into one {key: tensor} dict
+    (the files ``from_pretrained`` reads at /root/reference/model/depthcrafter.py:18-29)."""
+    import glob
+    import os
+
+    from safetensors.torch import load_file
+    files = sorted(glob.glob(os.path.join(path, "*.safetensors")))
+    if not files:
+        raise FileNotFoundError(f"no .safetensors files under {path}")
+    # prefer the fp16 variant when both exist, like variant="fp16" upstream
+    fp16 = [f for f in files if ".fp16." in os.path.basename(f)]
+    sd: Dict[str, torch.Tensor] = {}
+    for f in (fp16 or files):
+        sd.update(load_file(f))
+    return sd
