@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""Headline benchmark: denoising-steps/sec on 25x384x512 clips (BASELINE.json `metric`).
+
+    python bench.py --gpus N --steps K --warmup W             our arm (libunigeo_b200.so on B200)
+    python bench.py --impl reference --steps K --warmup W     CPU arm (oracle restatement, host cores)
+
+A "step" is one denoising step of the hot path on one clip: scale_model_input + concat of the
+conditioning latents, one full SVD-XT spatio-temporal UNet forward (1.52 B params, 23.16 TFLOP at
+25x384x512) and the Euler update -- exactly what ug_denoise_clip runs per step.  Weights are seeded
+random-init of the real architecture, inputs synthetic (no datasets/checkpoints offline).
+
+Timing: W untimed steps, then K steps bracketed by barrier + cuda.synchronize, CUDA events on the
+launching stream, max over ranks.  One step streams ~3 GB of weights and >10 GB of activations, far
+beyond the 126 MB L2, so no extra flush is needed between steps ("inputs larger than L2").
+`e2e` is the same metric through the plugin call DepthCrafter.forward(data) with HOST buffers
+(H2D of the frames, CLIP, VAE encode, the denoising loop, VAE decode, post-processing, D2H).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UNET_TFLOP_PER_STEP = {(25, 384, 512): 23.16}       # SURVEY.md §8(d) algorithmic count
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="full", choices=["full", "tiny"])
+    ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--frames", type=int, default=25)
+    ap.add_argument("--height", type=int, default=384)
+    ap.add_argument("--width", type=int, default=512)
+    ap.add_argument("--e2e-steps", type=int, default=25, help="num_inference_steps of the e2e plugin call (cfg2: 25)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-frames", type=int, default=2)
+    ap.add_argument("--profile-out", default=None, help="write the per-kernel launch table (json) here")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return f"DepthCrafter {a.frames}x{a.height}x{a.width} clip, SVD-XT UNet denoising step ({a.config} config)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        busy = [c for c in sm if c > 0]
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_unet_sample(a, steps, warmup):
+    """Times the oracle restatement of ONE denoising step on the host cores, on a bounded sample:
+    `cpu_sample_frames` of the clip's frames at full resolution, full SVD-XT config, fp32.  Cost is
+    linear in T for every layer except temporal attention (0.1 % of the FLOPs), so steps/s for the
+    whole clip = measured / (T / sample_frames)."""
+    import torch
+    from oracle import scheduler as S
+    from oracle.pipeline import added_time_ids
+    from oracle.unet_st import unet_forward
+    from unigeo_b200.config import get_config
+    from unigeo_b200.weights import synthetic_state_dict, unet_param_shapes
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = get_config(a.config)
+    Ts = max(1, min(a.cpu_sample_frames, a.frames))
+    h, w = a.height // 8, a.width // 8
+    sd = synthetic_state_dict(unet_param_shapes(cfg.unet), 1000)
+    g = torch.Generator().manual_seed(1234)
+    lat = torch.randn(1, Ts, 4, h, w, generator=g)
+    cond = torch.randn(1, Ts, 4, h, w, generator=g)
+    enc = torch.randn(1, Ts, cfg.clip_embed_dim, generator=g)
+    sig = S.karras_sigmas(25, cfg.sigma_min, cfg.sigma_max, cfg.rho)
+    ids = added_time_ids(cfg)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            x = torch.cat([S.scale_model_input(lat, sig[i % 24]), cond], dim=2)
+            v = unet_forward(sd, cfg.unet, x, 0.25 * math.log(sig[i % 24]), enc, ids)
+            lat = S.euler_step(v, lat, sig[i % 24], sig[i % 24 + 1])
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    per_step_clip = (sum(times) / len(times)) * (a.frames / Ts)
+    sample = (f"oracle (torch fp32, {cores} threads) full denoising step on {Ts} of {a.frames} frames at "
+              f"{a.height}x{a.width}, x{a.frames / Ts:g} (cost linear in T), mean of {len(times)} steps")
+    return 1.0 / per_step_clip, per_step_clip * 1e3, cores, sample
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    val, ms, cores, sample = cpu_unet_sample(a, max(1, a.steps), max(0, a.warmup))
+    print(json.dumps({
+        "impl": "reference", "metric": "denoising-steps/sec", "value": val, "unit": "steps/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(a), "frames": a.frames, "height": a.height, "width": a.width},
+        "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "the reference's own diffusers path is not installable offline (no diffusers/weights); "
+                "this is the oracle port of the same algorithm (parity unpinned, see DESIGN.md)",
+    }))
+
+
+# ----------------------------------------------------------------------------- B200 arm
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+
+    from unigeo_b200.config import get_config
+    from unigeo_b200.engine import Engine
+    from unigeo_b200.weights import synthetic_state_dict, unet_param_shapes, vae_param_shapes
+    cfg = get_config(a.config)
+    T, h, w = a.frames, a.height // 8, a.width // 8
+    eng = Engine(cfg, dtype=a.dtype, device=local)
+    # weights are generated in 16 bit chunk by chunk to keep host memory flat
+    eng.load_state_dict("unet", synthetic_state_dict(unet_param_shapes(cfg.unet), 1000, torch.float16))
+    eng.load_state_dict("vae", synthetic_state_dict(vae_param_shapes(cfg.vae), 2000, torch.float16))
+    eng.finalize()
+    eng.prepare(T, h, w)
+    dev = eng.device
+    g = torch.Generator().manual_seed(1234 + rank)
+    cond = torch.randn(T, 4, h, w, generator=g).to(dev)
+    noise = torch.randn(T, 4, h, w, generator=g).to(dev)
+    enc = torch.randn(T, cfg.clip_embed_dim, generator=g).to(dev)
+    ids = [cfg.fps_id, cfg.motion_bucket_id, cfg.noise_aug_strength]
+    eng.set_clip_context(enc)
+    out = torch.empty_like(cond)
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    eng.denoise(cond, noise, ids, max(a.warmup, 1), out=out)         # warm-up steps (untimed)
+    sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    eng.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    e0.record()
+    eng.denoise(cond, noise, ids, a.steps, out=out)                  # EXACTLY K timed steps
+    e1.record()
+    sync()
+    launches = eng.launch_count()
+    ms_total = e0.elapsed_time(e1)
+    t = torch.tensor([ms_total], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = t.item()
+    clocks = sampler.stop() if rank == 0 else None
+    assert torch.isfinite(out).all(), "non-finite latents"
+    ms_per_step = ms_total / a.steps
+    value = world * a.steps / (ms_total / 1e3)
+
+    # ---- roofline of the dominant kernel: one extra instrumented step (events after every launch)
+    roof, table = None, None
+    if rank == 0:
+        eng.profile(True)
+        eng.denoise(cond, noise, ids, 1, out=out)
+        table = eng.profile_read()
+        eng.profile(False)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)      # kernel timed inside a long step
+        peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback (B200_PROFILING.md ~1.4 PF sustained)"
+        tg = [r for r in table if r["name"].startswith("tapgemm")]
+        tot_ms = sum(r["ms"] for r in table)
+        tg_ms, tg_fl, tg_n = sum(r["ms"] for r in tg), sum(r["flops"] for r in tg), sum(r["launches"] for r in tg)
+        ach = tg_fl / (tg_ms * 1e-3) / 1e12 if tg_ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "tapgemm_kernel<BN> (tcgen05 implicit GEMM: conv3x3 / temporal conv / linear / attention GEMMs)",
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "peak_source": peak_src, "launches_per_step": tg_n, "flops_per_launch_avg": tg_fl / max(tg_n, 1),
+                "avg_launch_us": 1e3 * tg_ms / max(tg_n, 1), "share_of_step": tg_ms / tot_ms if tot_ms else None,
+                "step_tflops_algorithmic": UNET_TFLOP_PER_STEP.get((a.frames, a.height, a.width)),
+                "how": "CUDA events after every launch of one extra step on the launching stream (ug_ctx_profile)"}
+        if a.profile_out:
+            with open(a.profile_out, "w") as f:
+                json.dump({"ms_per_step_timed": ms_per_step, "instrumented_step_ms": tot_ms, "kernels": sorted(table, key=lambda r: -r["ms"])}, f, indent=1)
+
+    # ---- e2e through the plugin call with host buffers
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, eng, cfg, world, rank, dev)
+
+    cpu = None
+    if rank == 0 and not a.no_cpu_baseline:
+        del eng
+        torch.cuda.empty_cache()
+        v, ms, cores, sample = cpu_unet_sample(a, 1, 0)
+        cpu = {"value": v, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample}
+
+    if rank == 0:
+        line = {
+            "metric": "denoising-steps/sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": a.dtype, "data": "synthetic",
+            "config": {"workload": workload_name(a), "frames": T, "height": a.height, "width": a.width,
+                       "clips_per_gpu": 1, "l2": "inputs larger than L2 (3 GB weights + >10 GB activations per step)",
+                       "weights": "seeded random-init, SVD-XT architecture (1.52 B params)"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(a, eng, cfg, world, rank, dev):
+    """steps/s through the reference-facing plugin call with HOST buffers, every rank one clip."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from harness.synthetic import make_clip
+    from unigeo_b200.clip_embed import ClipEmbedder
+    from unigeo_b200.model.depthcrafter import DepthCrafter
+    from unigeo_b200.pipeline import DepthCrafterPipelineB200
+    plug = object.__new__(DepthCrafter)                       # reuse the already-loaded engine (one copy of weights)
+    plug.device, plug.cfg, plug.dtype, plug.engine = dev, cfg, a.dtype, eng
+    plug.num_inference_steps, plug.seed = a.e2e_steps, 1234 + rank
+    clip = ClipEmbedder(cfg.clip_embed_dim, dev, torch.float16 if a.dtype == "fp16" else torch.bfloat16)
+    plug.pipeline = DepthCrafterPipelineB200(cfg, eng, clip)
+    data = make_clip(a.frames, a.height, a.width, seed=1234 + rank)
+    plug.forward(data)                                         # warm-up (CLIP autotune, workspace sizing)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    out = plug.forward(data)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = t.item()
+    h2d = a.frames * a.height * a.width * 3 * 4
+    d2h = out["pred_depths"].numel() * 4 + out["pred_normals"].numel() * 4
+    return {"value": world * a.e2e_steps / dt, "unit": "steps/s", "h2d_bytes_per_step": h2d / a.e2e_steps,
+            "d2h_bytes_per_step": d2h / a.e2e_steps, "clip_seconds": dt, "num_inference_steps": a.e2e_steps,
+            "call": "unigeo_b200.model.DepthCrafter.forward(data) (CLIP + VAE encode + denoise + VAE decode + post-processing)"}
+
+
+if __name__ == "__main__":
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)

@@ -115,6 +115,12 @@ int ug_vae_decode_temporal(ug_ctx* ctx, const float* lat, int T, int h, int w, i
 long long ug_ctx_launch_count(ug_ctx* ctx, int reset);
 /* Bytes of workspace currently reserved. */
 long long ug_ctx_workspace_bytes(ug_ctx* ctx);
+/* Per-launch profiling for bench.py's roofline: while enabled, one CUDA event is recorded on the
+ * call's stream after every kernel launch; ug_ctx_profile_read synchronises and aggregates by kernel
+ * name (returns the number of rows written, or a negative ug_status).  Off by default. */
+int ug_ctx_profile(ug_ctx* ctx, int enable);
+int ug_ctx_profile_read(ug_ctx* ctx, int cap, char* names /* [cap][64] */, long long* launches, double* ms,
+                        double* flops, double* bytes);
 
 /* ---- single-op entry points (kernel parity tests; same kernels the graphs above use) ----
  * 16-bit tensors are in `dtype` (UG_F16 / UG_BF16), channels-last, dense. */

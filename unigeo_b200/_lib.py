@@ -61,6 +61,9 @@ _SIGNATURES = {
     "ug_vae_decode_temporal": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "ug_ctx_launch_count": ([_P, _I], C.c_longlong),
     "ug_ctx_workspace_bytes": ([_P], C.c_longlong),
+    "ug_ctx_profile": ([_P, _I], C.c_int),
+    "ug_ctx_profile_read": ([_P, _I, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
+                             C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),
     "ug_op_linear": ([_I, _P, _L, _I, _P, _I, _P, _P, _I, _I, _P, _P], C.c_int),
     "ug_op_conv3x3": ([_I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P], C.c_int),
     "ug_op_tconv3": ([_I, _P, _I, _L, _I, _P, _I, _I, _P, _P, _P, _F, _P, _P], C.c_int),

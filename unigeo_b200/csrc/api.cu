@@ -45,6 +45,7 @@ void run_sized(ug_ctx* u, const std::string& sig, void* stream, const std::funct
   c.ensure_workspace(it->second);
   c.ws.off = 0;
   c.stream = reinterpret_cast<cudaStream_t>(stream);
+  if (c.profile) c.prof_mark("(start)", 0.0, 0.0);
   body(c);
 }
 
@@ -281,6 +282,53 @@ long long ug_ctx_launch_count(ug_ctx* u, int reset) {
   return n;
 }
 long long ug_ctx_workspace_bytes(ug_ctx* u) { return u ? (long long)u->c.ws.cap : -1; }
+
+int ug_ctx_profile(ug_ctx* u, int enable) {
+  return guard([&] {
+    UG_CHECK(u, UG_ERR_INVALID, "null ctx");
+    u->c.profile = enable != 0;
+    u->c.prof.clear();
+  });
+}
+
+// Aggregates the launches recorded since ug_ctx_profile(ctx, 1) by kernel name.  Writes up to `cap`
+// rows: names (64 bytes each, NUL padded), launches, milliseconds, algorithmic flops, algorithmic bytes.
+int ug_ctx_profile_read(ug_ctx* u, int cap, char* names, long long* counts, double* ms, double* flops,
+                        double* bytes) {
+  try {
+    if (!u) return UG_ERR_INVALID;
+    Ctx& c = u->c;
+    UG_CUDA(cudaSetDevice(c.device));
+    UG_CUDA(cudaDeviceSynchronize());
+    std::vector<std::string> order;
+    std::unordered_map<std::string, int> idx;
+    int n = 0;
+    for (size_t i = 1; i < c.prof.size(); ++i) {      // record 0 is the opening marker
+      const Ctx::ProfRec& r = c.prof[i];
+      if (std::strcmp(r.name, "(start)") == 0) continue;   // time origin of an API call
+      float t = 0.f;
+      UG_CUDA(cudaEventElapsedTime(&t, c.prof[i - 1].ev, r.ev));
+      auto it = idx.find(r.name);
+      int k;
+      if (it == idx.end()) {
+        if (n >= cap) continue;
+        k = n++;
+        idx[r.name] = k;
+        std::memset(names + 64 * k, 0, 64);
+        std::strncpy(names + 64 * k, r.name, 63);
+        counts[k] = 0; ms[k] = 0; flops[k] = 0; bytes[k] = 0;
+      } else {
+        k = it->second;
+      }
+      counts[k] += 1; ms[k] += t; flops[k] += r.flops; bytes[k] += r.bytes;
+    }
+    g_err.clear();
+    return n;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return UG_ERR_CUDA;
+  }
+}
 
 // ------------------------------------------------------------------ single ops
 int ug_op_linear(int dtype, const void* x, long long M, int K, const void* W, int N, const float* bias,

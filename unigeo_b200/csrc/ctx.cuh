@@ -96,6 +96,13 @@ struct Ctx {
   // prepared clip shape
   int T = 0, h = 0, w = 0;
   std::vector<void*> owned;      // cudaMalloc'd blocks to free at destroy
+  // ---- per-launch profiling (ug_ctx_profile): one event after every launch; a launch's time
+  // is the gap to the previous event on the (single) stream
+  struct ProfRec { const char* name; double flops, bytes; cudaEvent_t ev; };
+  bool profile = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  void prof_mark(const char* name, double flops, double bytes);
 
   void* dmalloc(size_t bytes);
   const Weight& W(const std::string& key) const;
@@ -127,6 +134,6 @@ void op_upsample2x(Ctx& c, const void* x, void* y, int N, int H, int W, int C);
 void op_concat(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long rows, void* y);
 void op_gemv(Ctx& c, const void* Wm, const float* b, const float* addend, const float* x, float* out, int M,
              int N, int K, int silu_in, int silu_out);
-void op_check(Ctx& c, int err, const char* what);
+void op_check(Ctx& c, int err, const char* what, double flops = 0.0, double bytes = 0.0);
 
 }  // namespace ug

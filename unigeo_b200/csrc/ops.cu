@@ -42,11 +42,24 @@ void Ctx::ensure_workspace(size_t bytes) {
   ws.cap = bytes;
 }
 
-void op_check(Ctx& c, int err, const char* what) {
+void Ctx::prof_mark(const char* name, double flops, double bytes) {
+  cudaEvent_t ev;
+  if (ev_pool.size() > prof.size()) {
+    ev = ev_pool[prof.size()];
+  } else {
+    UG_CUDA(cudaEventCreate(&ev));
+    ev_pool.push_back(ev);
+  }
+  UG_CUDA(cudaEventRecord(ev, stream));
+  prof.push_back({name, flops, bytes, ev});
+}
+
+void op_check(Ctx& c, int err, const char* what, double flops, double bytes) {
   if (err != 0)
     throw UgError(UG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString((cudaError_t)err) + " (" +
                                    std::to_string(err) + ")");
   c.launches++;
+  if (c.profile) c.prof_mark(what, flops, bytes);
 }
 
 // ------------------------------------------------------------------ tapgemm plumbing
@@ -114,9 +127,14 @@ void make_b_map(CUtensorMap* m, const void* p, int fmt, unsigned long long cols,
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline int imin(int a, int b) { return a < b ? a : b; }
 
+// algorithmic work of one tapgemm launch: 2*M*N*K flops over the REAL (unpadded) extents;
+// bytes = A read once + output written once (16-bit), weights ignored (SURVEY.md §8 convention)
 void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmArgs& a, int batch,
-            const char* what) {
-  op_check(c, launch_tapgemm(ma, mb, a, batch, c.stream), what);
+            const char* what, long long k_real) {
+  const double M = (double)a.W * a.H * a.N * batch;
+  const double flops = 2.0 * M * a.n_total * (double)k_real * a.num_taps;
+  const double bytes = M * ((double)k_real + (a.geglu ? a.n_total / 2 : a.n_total)) * 2.0;
+  op_check(c, launch_tapgemm(ma, mb, a, batch, c.stream), what, flops, bytes);
 }
 
 }  // namespace
@@ -140,7 +158,7 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
                               (unsigned long long)ldx * 2 * M, (unsigned long long)ldx * 2 * M};
   make_a_map(&ma, x, c.fmt, dims, st, 128, 1, 1, 1);
   make_b_map(&mb, Wm, c.fmt, K, N, (unsigned long long)K * 2, bn);
-  launch(c, ma, mb, a, 1, "linear");
+  launch(c, ma, mb, a, 1, e.geglu ? "tapgemm.linear_geglu" : "tapgemm.linear", K);
 }
 
 void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* Wm, int Cout, int stride,
@@ -198,7 +216,7 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
     make_a_map(&ma, x, c.fmt, dims, st, a.bw, 1, a.bh, a.bn);
   }
   make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)9 * Cout, rowb, bn);
-  launch(c, ma, mb, a, 1, "conv3x3");
+  launch(c, ma, mb, a, 1, "tapgemm.conv3x3", C);
 }
 
 void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm, int Cout, int chunk,
@@ -237,7 +255,7 @@ void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm,
     unsigned long long st[4] = {rowb, rowb * P, rowb * P * Tc, rowb * P * Tc};
     make_a_map(&ma, reinterpret_cast<const char*>(x) + tok0 * rowb, c.fmt, dims, st, a.bw, a.bh, 1, 1);
     make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)3 * Cout, rowb, bn);
-    launch(c, ma, mb, a, 1, "tconv3");
+    launch(c, ma, mb, a, 1, "tapgemm.tconv3", C);
   }
 }
 
@@ -275,10 +293,10 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
       make_a_map(&ma, qkv, c.fmt, dims, st, a.bw, 1, 1, 1);
       make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb,
                  tapgemm_pick_bn(N, 0));
-      launch(c, ma, mb, a, F * heads, "attention QK^T");
+      launch(c, ma, mb, a, F * heads, "tapgemm.attn_qk", dh);
     }
     op_check(c, launch_softmax_rows(S, (long long)F * heads * N, N, 1.0f / sqrtf((float)dh), c.fmt, c.stream),
-             "softmax");
+             "softmax_rows", 0.0, 4.0 * F * heads * (double)N * N);
     {  // O[z] = P[z] V[z]
       TapGemmArgs a;
       base_args(a);
@@ -306,7 +324,7 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
       make_a_map(&ma, S, c.fmt, dims, st, a.bw, 1, 1, 1);
       make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb, 64);
       // the MN-major path is built for 64-wide N tiles
-      op_check(c, launch_tapgemm(ma, mb, a, F * heads, c.stream), "attention PV");
+      launch(c, ma, mb, a, F * heads, "tapgemm.attn_pv", N);
     }
   }
   c.ws.release(m);
@@ -321,29 +339,32 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
   (void)sets;
   float* stats = c.allocf(gn_partial_floats(C1 + C2, rows, rows_per_set, G));
   if (!c.dry) {
-    op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, stats, c.fmt, c.stream), "gn_stats");
+    op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, stats, c.fmt, c.stream), "gn_stats", 0.0,
+             2.0 * rows * (C1 + C2));
     op_check(c, launch_gn_apply(x1, C1, x2, C2, rows, rows_per_set, G, stats, gamma, beta, eps, silu, y, c.fmt,
                                 c.stream),
-             "gn_apply");
+             "gn_apply", 0.0, 4.0 * rows * (C1 + C2));
   }
   c.ws.release(m);
 }
 void op_layernorm(Ctx& c, const void* x, long long rows, int C, const float* g, const float* b, float eps,
                   const float* add, int add_div, void* y) {
   if (c.dry) return;
-  op_check(c, launch_layernorm(x, rows, C, g, b, eps, add, add_div, y, c.fmt, c.stream), "layernorm");
+  op_check(c, launch_layernorm(x, rows, C, g, b, eps, add, add_div, y, c.fmt, c.stream), "layernorm", 0.0,
+           4.0 * rows * C);
 }
 void op_temporal_attention(Ctx& c, const void* qkv, void* out, int T, long long P, int C) {
   if (c.dry) return;
-  op_check(c, launch_temporal_attention(qkv, out, T, P, C, 0.125f, c.fmt, c.stream), "temporal_attention");
+  op_check(c, launch_temporal_attention(qkv, out, T, P, C, 0.125f, c.fmt, c.stream), "temporal_attention",
+           4.0 * T * T * 64.0 * P * (C / 64), 8.0 * T * P * C);
 }
 void op_upsample2x(Ctx& c, const void* x, void* y, int N, int H, int W, int C) {
   if (c.dry) return;
-  op_check(c, launch_upsample2x(x, y, N, H, W, C, c.stream), "upsample2x");
+  op_check(c, launch_upsample2x(x, y, N, H, W, C, c.stream), "upsample2x", 0.0, 10.0 * N * H * W * C);
 }
 void op_concat(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long rows, void* y) {
   if (c.dry) return;
-  op_check(c, launch_concat(x1, C1, x2, C2, rows, y, c.stream), "concat");
+  op_check(c, launch_concat(x1, C1, x2, C2, rows, y, c.stream), "concat", 0.0, 4.0 * rows * (C1 + C2));
 }
 void op_gemv(Ctx& c, const void* Wm, const float* b, const float* addend, const float* x, float* out, int M,
              int N, int K, int silu_in, int silu_out) {

@@ -144,6 +144,23 @@ class Engine:
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.ug_ctx_launch_count(self._ctx, 1 if reset else 0))
 
+    def profile(self, enable: bool) -> None:
+        _lib.check(self.lib.ug_ctx_profile(self._ctx, 1 if enable else 0))
+
+    def profile_read(self, cap: int = 64):
+        """[{name, launches, ms, flops, bytes}] aggregated over the launches since profile(True)."""
+        names = C.create_string_buffer(64 * cap)
+        cnt = (C.c_longlong * cap)()
+        ms, fl, by = (C.c_double * cap)(), (C.c_double * cap)(), (C.c_double * cap)()
+        n = self.lib.ug_ctx_profile_read(self._ctx, cap, names, cnt, ms, fl, by)
+        if n < 0:
+            _lib.check(n)
+        rows = []
+        for i in range(n):
+            nm = names.raw[64 * i:64 * i + 64].split(b"\0", 1)[0].decode()
+            rows.append(dict(name=nm, launches=int(cnt[i]), ms=float(ms[i]), flops=float(fl[i]), bytes=float(by[i])))
+        return rows
+
     def workspace_bytes(self) -> int:
         return int(self.lib.ug_ctx_workspace_bytes(self._ctx))
 
