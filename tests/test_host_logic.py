@@ -55,13 +55,13 @@ def test_scheduler_matches_oracle_and_closed_form():
 
 def test_geglu_interleave_layout():
     from unigeo_b200.ops import geglu_interleave
-    H, K = 128, 8
+    H, K = 256, 8
     W = torch.arange(2 * H * K, dtype=torch.float32).view(2 * H, K)
     b = torch.arange(2 * H, dtype=torch.float32)
     Wi, bi = geglu_interleave(W, b)
-    assert torch.equal(Wi[0:64], W[0:64]) and torch.equal(Wi[64:128], W[H:H + 64])
-    assert torch.equal(Wi[128:192], W[64:128]) and torch.equal(Wi[192:256], W[H + 64:H + 128])
-    assert torch.equal(bi[64:128], b[H:H + 64])
+    assert torch.equal(Wi[0:128], W[0:128]) and torch.equal(Wi[128:256], W[H:H + 128])
+    assert torch.equal(Wi[256:384], W[128:256]) and torch.equal(Wi[384:512], W[H + 128:H + 256])
+    assert torch.equal(bi[128:256], b[H:H + 128])
 
 
 def test_adapter_prepare_input_truncates():

@@ -151,7 +151,7 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   a.kchunks = cdiv(K, 64);
   a.n_total = N;
   fill_epi(a, e, c.fmt);
-  const int bn = tapgemm_pick_bn(N, e.geglu);
+  const int bn = a.bn_tile = tapgemm_pick_bn(a, 1);
   CUtensorMap ma, mb;
   unsigned long long dims[5] = {(unsigned long long)K, (unsigned long long)M, 1, 1, 1};
   unsigned long long st[4] = {(unsigned long long)ldx * 2, (unsigned long long)ldx * 2 * M,
@@ -180,7 +180,7 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
   a.b_tap_rows = Cout;
   a.n_total = Cout;
   fill_epi(a, e, c.fmt);
-  const int bn = tapgemm_pick_bn(Cout, e.geglu);
+  const int bn = a.bn_tile = tapgemm_pick_bn(a, 1);
   CUtensorMap ma, mb;
   const unsigned long long rowb = (unsigned long long)C * 2;
   if (stride == 1) {
@@ -249,7 +249,7 @@ void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm,
     if (e.blend) ec.blend = reinterpret_cast<const char*>(e.blend) + tok0 * e.ldb * 2;
     if (e.fbias) ec.fbias = e.fbias + (tok0 / ec.fbias_div) * e.fbias_ld;
     fill_epi(a, ec, c.fmt);
-    const int bn = tapgemm_pick_bn(Cout, e.geglu);
+    const int bn = a.bn_tile = tapgemm_pick_bn(a, 1);
     CUtensorMap ma, mb;
     unsigned long long dims[5] = {(unsigned long long)C, (unsigned long long)P, (unsigned long long)Tc, 1, 1};
     unsigned long long st[4] = {rowb, rowb * P, rowb * P * Tc, rowb * P * Tc};
@@ -291,8 +291,8 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
       unsigned long long dims[5] = {(unsigned long long)3 * C, (unsigned long long)F * N, 1, 1, 1};
       unsigned long long st[4] = {rowb, rowb * F * N, rowb * F * N, rowb * F * N};
       make_a_map(&ma, qkv, c.fmt, dims, st, a.bw, 1, 1, 1);
-      make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb,
-                 tapgemm_pick_bn(N, 0));
+      a.bn_tile = tapgemm_pick_bn(a, F * heads);
+      make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb, a.bn_tile);
       launch(c, ma, mb, a, F * heads, "tapgemm.attn_qk", dh);
     }
     op_check(c, launch_softmax_rows(S, (long long)F * heads * N, N, 1.0f / sqrtf((float)dh), c.fmt, c.stream),
@@ -322,8 +322,8 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
                                     (unsigned long long)F, 1};
       unsigned long long st[4] = {srow, srow * N, srow * N * heads, srow * N * heads * F};
       make_a_map(&ma, S, c.fmt, dims, st, a.bw, 1, 1, 1);
+      a.bn_tile = tapgemm_pick_bn(a, F * heads);   // 64: MN-major boxes are [64 K][64 N]
       make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb, 64);
-      // the MN-major path is built for 64-wide N tiles
       launch(c, ma, mb, a, F * heads, "tapgemm.attn_pv", N);
     }
   }

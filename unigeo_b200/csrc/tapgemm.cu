@@ -17,18 +17,13 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kATileBytes = BM * BK * 2;
-
-template <int BN> struct Cfg {
-  static constexpr int b_tile_bytes = BN * BK * 2;
-  static constexpr int stage_bytes = kATileBytes + (b_tile_bytes < 1024 ? 1024 : b_tile_bytes);
-  // 3 stages for the wide tiles (<= 96 KB: two CTAs co-reside, one's epilogue hides under the
-  // other's main loop); deeper ring for the narrow ones.
-  static constexpr int stages = BN >= 256 ? 4 : (BN >= 128 ? 3 : 4);
-  static constexpr int tmem_cols = BN < 32 ? 32 : BN;
-  static constexpr int smem_bytes = stages * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
-};
+constexpr int kBTileBytes = 256 * BK * 2;            // room for the widest N tile
+constexpr int kStageBytes = kATileBytes + kBTileBytes;
+constexpr int kStages = 4;
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
@@ -140,31 +135,28 @@ __device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmAr
   }
 }
 
-template <int BN>
-__global__ void __launch_bounds__(kThreads)
+// Persistent kernel: one CTA per SM walks output tiles t = blockIdx.x, += gridDim.x.  The three
+// roles run ahead of each other across tiles: the TMA ring (kStages) never drains between
+// tiles, and the accumulator is double-buffered in TMEM (2 x 256 columns) so the MMAs of tile
+// i+1 overlap the epilogue of tile i.  BN (the UMMA N extent) is a RUNTIME multiple of 16 <= 256
+// chosen per layer so that N splits without padding (e.g. 320 -> 2 x 160).
+__global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TapGemmArgs a) {
-  using C = Cfg<BN>;
-  constexpr int STAGES = C::stages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * C::stage_bytes);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;     // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates
-  int m_tile = blockIdx.x;
-  const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
-  const int ty = m_tile % a.tiles_y;
-  const int tn = m_tile / a.tiles_y;
-  const int x0 = tx * a.bw, y0 = ty * a.bh, nn0 = tn * a.bn;
-  const int n0 = blockIdx.y * BN;
-  const int z1 = blockIdx.z / a.zdiv;
-  const int z0 = blockIdx.z - z1 * a.zdiv;
+  const int BN = a.bn_tile;
+  const int m_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int n_tiles = a.n_tiles;
+  const int total_tiles = m_tiles * n_tiles * a.batch;
   const int num_iters = a.num_taps * a.kchunks;
 
   if (warp == 0 && lane == 0) {
@@ -173,15 +165,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < STAGES; ++s) {
+      for (int s = 0; s < kStages; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
-      mbar_init(tmem_full_bar, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(&tmem_full_bar[b], 1);
+        mbar_init(&tmem_empty_bar[b], kEpiWarps);
+      }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr_smem, C::tmem_cols);
+    tmem_alloc(tmem_ptr_smem, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -192,123 +187,179 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      int base[6] = {0, 0, 0, 0, 0, 0};   // slot 5 swallows unused roles
-      base[a.dim_x] += x0;
-      base[a.dim_y] += y0;
-      base[a.dim_n] += nn0;
-      base[a.dim_z1] += z1 * a.a_z1step;
-      base[a.dim_z0] += z0 * a.a_z0step;
       const uint32_t tx_bytes = (uint32_t)(a.bw * a.bh * a.bn) * (BK * 2) +
                                 (uint32_t)(a.b_mn_major ? BK : BN) * (BK * 2);
-      const int bcol0 = a.b_c0 + z0 * a.b_z0_cstep;
-      const int brow0 = z1 * a.b_z1_rowstep + (a.b_mn_major ? 0 : n0);
-      for (int it = 0; it < num_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        const int tap = it / a.kchunks;
-        const int kc = it - tap * a.kchunks;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-        uint8_t* sa = smem + s * C::stage_bytes;
-        uint8_t* sb = sa + kATileBytes;
-        tma_load_5d(sa, &tmA, &full_bar[s], base[0] + a.tap_off[tap][0] + kc * BK, base[1] + a.tap_off[tap][1],
-                    base[2] + a.tap_off[tap][2], base[3] + a.tap_off[tap][3], base[4] + a.tap_off[tap][4]);
-        if (a.b_mn_major)  // [64 K rows][64 N elements] box of a row-major [K, N] matrix
-          tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + n0, brow0 + kc * BK);
-        else
-          tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + kc * BK, brow0 + tap * a.b_tap_rows);
+      int it_g = 0;   // ring position, continuous across tiles
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int m_tile = t % m_tiles;
+        const int rest = t / m_tiles;
+        const int n0 = (rest % n_tiles) * BN;
+        const int z = rest / n_tiles;
+        const int z1 = z / a.zdiv, z0 = z - z1 * a.zdiv;
+        const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
+        const int ty = m_tile % a.tiles_y;
+        const int tn = m_tile / a.tiles_y;
+        int base[6] = {0, 0, 0, 0, 0, 0};   // slot 5 swallows unused roles
+        base[a.dim_x] += tx * a.bw;
+        base[a.dim_y] += ty * a.bh;
+        base[a.dim_n] += tn * a.bn;
+        base[a.dim_z1] += z1 * a.a_z1step;
+        base[a.dim_z0] += z0 * a.a_z0step;
+        const int bcol0 = a.b_c0 + z0 * a.b_z0_cstep;
+        const int brow0 = z1 * a.b_z1_rowstep + (a.b_mn_major ? 0 : n0);
+        for (int it = 0; it < num_iters; ++it, ++it_g) {
+          const int s = it_g % kStages;
+          const uint32_t ph = (uint32_t)(it_g / kStages) & 1u;
+          const int tap = it / a.kchunks;
+          const int kc = it - tap * a.kchunks;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sb = sa + kATileBytes;
+          tma_load_5d(sa, &tmA, &full_bar[s], base[0] + a.tap_off[tap][0] + kc * BK, base[1] + a.tap_off[tap][1],
+                      base[2] + a.tap_off[tap][2], base[3] + a.tap_off[tap][3], base[4] + a.tap_off[tap][4]);
+          if (a.b_mn_major)  // [64 K rows][64 N elements] box of a row-major [K, N] matrix
+            tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + n0, brow0 + kc * BK);
+          else
+            tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + kc * BK, brow0 + tap * a.b_tap_rows);
+        }
       }
     }
   } else if (warp == 1) {
     // ===================== UMMA issuer =====================
     const uint32_t idesc = make_idesc_f16(BM, BN, a.fmt, a.b_mn_major);
-    for (int it = 0; it < num_iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(&full_bar[s], ph);
+    const uint32_t bstep = a.b_mn_major ? 128u : 2u;
+    int it_g = 0, tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      const int buf = tl & 1;
+      const uint32_t use = (uint32_t)(tl >> 1);
+      mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);     // epilogue drained this accumulator
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t sa = smem_u32(smem + s * C::stage_bytes);
-        const uint64_t da = make_desc_kmajor_sw128(sa);
-        // K-major: +32 B per K=16 slice inside the 128-byte swizzle row (start field += 2).
-        // MN-major: a K=16 slice is 16 rows of 128 B (start field += 128).
-        const uint64_t db = a.b_mn_major ? make_desc_mnmajor_sw128(sa + kATileBytes, 8192)
-                                         : make_desc_kmajor_sw128(sa + kATileBytes);
-        const uint32_t bstep = a.b_mn_major ? 128u : 2u;
+      const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
+      for (int it = 0; it < num_iters; ++it, ++it_g) {
+        const int s = it_g % kStages;
+        const uint32_t ph = (uint32_t)(it_g / kStages) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + s * kStageBytes);
+          const uint64_t da = make_desc_kmajor_sw128(sa);
+          // K-major: +32 B per K=16 slice inside the 128-byte swizzle row (start field += 2).
+          // MN-major: a K=16 slice is 16 rows of 128 B (start field += 128).
+          const uint64_t db = a.b_mn_major ? make_desc_mnmajor_sw128(sa + kATileBytes, 8192)
+                                           : make_desc_kmajor_sw128(sa + kATileBytes);
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          umma_f16(tmem_base, da + 2 * k, db + bstep * k, idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k)
+            umma_f16(tmem_d, da + 2 * k, db + bstep * k, idesc, (it | k) != 0 ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+          if (it == num_iters - 1) umma_commit(&tmem_full_bar[buf]);
         }
-        umma_commit(&empty_bar[s]);
-        if (it == num_iters - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
       }
-      __syncwarp();
     }
   } else {
-    // ===================== epilogue =====================
-    const int q = warp & 3;             // TMEM lane quarter this warp may read
-    const int r = q * 32 + lane;        // output row inside the tile
+    // ===================== epilogue (8 warps: 4 lane quarters x 2 column halves) =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may read
+    const int hsel = (warp - 2) >> 2;       // which half of the 32-column chunks
+    const int r = q * 32 + lane;            // output row inside the tile
     const int xi = r % a.bw;
     const int yi = (r / a.bw) % a.bh;
     const int ni = r / (a.bw * a.bh);
-    const bool row_ok = (ni < a.bn) && (x0 + xi < a.W) && (y0 + yi < a.H) && (nn0 + ni < a.N);
-    const long long pix = ((long long)(nn0 + ni) * a.H + (y0 + yi)) * a.W + (x0 + xi);
-    const long long zoff = (long long)z1 * a.out_z1stride + (long long)z0 * a.out_z0stride;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    if constexpr (BN >= 32) {
+    int tl = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
+      int m_tile = t % m_tiles;
+      const int rest = t / m_tiles;
+      const int n_tile = rest % n_tiles;
+      const int n0 = n_tile * BN;
+      const int z = rest / n_tiles;
+      const int z1 = z / a.zdiv, z0 = z - z1 * a.zdiv;
+      const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
+      const int ty = m_tile % a.tiles_y;
+      const int tn = m_tile / a.tiles_y;
+      const int x0 = tx * a.bw, y0 = ty * a.bh, nn0 = tn * a.bn;
+      const bool row_ok = (ni < a.bn) && (x0 + xi < a.W) && (y0 + yi < a.H) && (nn0 + ni < a.N);
+      const long long pix = ((long long)(nn0 + ni) * a.H + (y0 + yi)) * a.W + (x0 + xi);
+      const long long zoff = (long long)z1 * a.out_z1stride + (long long)z0 * a.out_z0stride;
+      const int buf = tl & 1;
+      mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 256u;
       if (a.geglu) {
-        if constexpr (BN == 128) {
-          const int ocol_tile = blockIdx.y * 64;
+        const int BNh = BN >> 1;
+        const int ocol_tile = n_tile * BNh;
 #pragma unroll 1
-          for (int c = 0; c < 64; c += 32) {
-            uint32_t v[32], g[32];
-            tmem_ld_32x32(trow + c, v);
-            tmem_ld_32x32(trow + 64 + c, g);
-            tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int vc = n0 + c + j, gc = n0 + 64 + c + j;
-              float val = __uint_as_float(v[j]) * a.scale;
-              float gate = __uint_as_float(g[j]) * a.scale;
-              if (a.bias != nullptr) {
-                if (vc < a.n_total) val += __ldg(a.bias + vc);
-                if (gc < a.n_total) gate += __ldg(a.bias + gc);
-              }
-              f[j] = val * gelu_erf(gate);
-            }
-            finish_and_store<32>(f, a, pix, zoff, ocol_tile + c, 0, a.n_total / 2 - (ocol_tile + c), row_ok);
-          }
-        }
-      } else {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
+        for (int c = hsel * 32; c < BNh; c += 64) {
+          uint32_t v[32], g[32];
           tmem_ld_32x32(trow + c, v);
+          tmem_ld_32x32(trow + BNh + c, g);
           tmem_ld_wait();
+          if (c + 64 >= BNh) {               // last chunk of this warp: accumulator no longer needed
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+          }
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
-          finish_and_store<32>(f, a, pix, zoff, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
+          for (int j = 0; j < 32; ++j) {
+            const int vc = n0 + c + j, gc = n0 + BNh + c + j;
+            float val = __uint_as_float(v[j]) * a.scale;
+            float gate = __uint_as_float(g[j]) * a.scale;
+            if (a.bias != nullptr) {
+              if (vc < a.n_total) val += __ldg(a.bias + vc);
+              if (gc < a.n_total) gate += __ldg(a.bias + gc);
+            }
+            f[j] = val * gelu_erf(gate);
+          }
+          finish_and_store<32>(f, a, pix, zoff, ocol_tile + c, 0, a.n_total / 2 - (ocol_tile + c), row_ok);
+        }
+      } else {
+        bool released = false;
+#pragma unroll 1
+        for (int c = hsel * 32; c < BN; c += 64) {
+          const bool last = (c + 64 >= BN);
+          if (BN - c >= 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(trow + c, v);
+            tmem_ld_wait();
+            if (last) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+              released = true;
+            }
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
+            finish_and_store<32>(f, a, pix, zoff, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
+          } else {
+            uint32_t v[16];
+            tmem_ld_32x16(trow + c, v);
+            tmem_ld_wait();
+            if (last) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
+              released = true;
+            }
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
+            finish_and_store<16>(f, a, pix, zoff, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
+          }
+        }
+        if (!released) {                     // this warp had no chunk in this tile (narrow BN)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
         }
       }
-    } else {
-      uint32_t v[16];
-      tmem_ld_32x16(trow, v);
-      tmem_ld_wait();
-      float f[16];
-#pragma unroll
-      for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
-      finish_and_store<16>(f, a, pix, zoff, n0, n0, a.n_total - n0, row_ok);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::tmem_cols);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -328,24 +379,6 @@ PFN_encodeTiled get_encode_fn() {
       fn = reinterpret_cast<PFN_encodeTiled>(p);
   });
   return fn;
-}
-
-template <int BN>
-int launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args, int batch,
-              cudaStream_t stream) {
-  using C = Cfg<BN>;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         C::smem_bytes);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  const int m_tiles = args.tiles_x * args.tiles_y * args.tiles_n;
-  const int n_tiles = (args.n_total + BN - 1) / BN;
-  dim3 grid(m_tiles, n_tiles, batch);
-  tapgemm_kernel<BN><<<grid, kThreads, C::smem_bytes, stream>>>(tmA, tmB, args);
-  return (int)cudaGetLastError();
 }
 
 }  // namespace
@@ -369,23 +402,53 @@ int encode_tmap(CUtensorMap* out, const TmapDesc& d) {
   return (int)r;
 }
 
-int tapgemm_pick_bn(int n_total, int geglu) {
-  if (geglu) return 128;
-  if (n_total <= 16) return 16;
-  if (n_total <= 32) return 32;
-  if (n_total <= 64) return 64;
-  return 128;
+int tapgemm_num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
 }
 
-int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args, int batch,
-                   cudaStream_t stream) {
-  // the MN-major B path stages [64 K][64 N] boxes: 64-wide N tiles only
-  switch (args.b_mn_major ? 64 : tapgemm_pick_bn(args.n_total, args.geglu)) {
-    case 16: return launch_bn<16>(tmA, tmB, args, batch, stream);
-    case 32: return launch_bn<32>(tmA, tmB, args, batch, stream);
-    case 64: return launch_bn<64>(tmA, tmB, args, batch, stream);
-    default: return launch_bn<128>(tmA, tmB, args, batch, stream);
+// N tile: the multiple of 16 (<= 256) that minimises waves x (columns + fixed per-tile cost).
+int tapgemm_pick_bn(const TapGemmArgs& a, int batch) {
+  if (a.b_mn_major) return 64;           // MN-major B boxes are [64 K][64 N]
+  if (a.geglu) return 256;               // [128 value | 128 gate] column tiles
+  const long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n * batch;
+  const int sms = tapgemm_num_sms();
+  int best = 16;
+  long long best_cost = -1;
+  for (int bn = 256; bn >= 16; bn -= 16) {
+    const long long tiles = m_tiles * ((a.n_total + bn - 1) / bn);
+    const long long waves = (tiles + sms - 1) / sms;
+    const long long cost = waves * (bn + 24);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
   }
+  return best;
+}
+
+int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args_in, int batch,
+                   cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  TapGemmArgs args = args_in;
+  if (args.bn_tile <= 0 || args.bn_tile > 256 || (args.bn_tile & 15)) return (int)cudaErrorInvalidValue;
+  args.batch = batch;
+  args.n_tiles = (args.n_total + args.bn_tile - 1) / args.bn_tile;
+  const long long total = (long long)args.tiles_x * args.tiles_y * args.tiles_n * args.n_tiles * batch;
+  if (total <= 0 || total > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+  const int grid = (int)(total < tapgemm_num_sms() ? total : tapgemm_num_sms());
+  tapgemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, args);
+  return (int)cudaGetLastError();
 }
 
 }  // namespace ug

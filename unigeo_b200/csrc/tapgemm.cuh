@@ -42,9 +42,11 @@ struct TapGemmArgs {
   int b_mn_major;          // B tile is [K rows][64 N elements] (e.g. V of attention): needs BN == 64
   // ---- epilogue
   int n_total;             // valid output columns (before GEGLU halving)
+  int bn_tile;             // N extent of one tile: multiple of 16, <= 256 (tapgemm_pick_bn)
+  int n_tiles, batch;      // filled by launch_tapgemm
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
   int out_fp32;
-  int geglu;               // columns [0,64) of each 128-wide tile gate-multiplied by gelu([64,128))
+  int geglu;               // columns [0,128) of each 256-wide tile gate-multiplied by gelu([128,256))
   void* out;
   long long ldc;
   long long out_z1stride, out_z0stride;   // element offsets per z1 / z0
@@ -72,10 +74,13 @@ struct TmapDesc {
 // Encodes a SWIZZLE_128B tiled tensor map; returns cudaSuccess-like 0 or non-zero.
 int encode_tmap(CUtensorMap* out, const TmapDesc& d);
 
-// Launch; BN is chosen from n_total.  Returns cudaError_t as int.
+// Launch (persistent, one CTA per SM); args.bn_tile must be set (tapgemm_pick_bn) and must equal the
+// row extent of the B tensor map's box.  Returns cudaError_t as int.
 int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args, int batch,
                    cudaStream_t stream);
 
-int tapgemm_pick_bn(int n_total, int geglu);
+// needs tiles_*, n_total, geglu, b_mn_major filled in
+int tapgemm_pick_bn(const TapGemmArgs& args, int batch);
+int tapgemm_num_sms();
 
 }  // namespace ug

@@ -93,19 +93,19 @@ void fuse_qkv(Ctx& c, const std::string& k, cudaStream_t st) {
 void fuse_geglu(Ctx& c, const std::string& k, cudaStream_t st) {
   const Weight& w = c.W(k + ".net.0.proj.weight");
   const int n = w.cout, K = w.cin, half = n / 2;
-  UG_CHECK(half % 64 == 0, UG_ERR_WEIGHT, "fuse_geglu: inner dim must be a multiple of 64: " + k);
-  // tile t of 128 output columns = [64 value rows t*64.. | 64 gate rows half + t*64..]
+  UG_CHECK(half % 128 == 0, UG_ERR_WEIGHT, "fuse_geglu: inner dim must be a multiple of 128: " + k);
+  // tile t of 256 output columns = [128 value rows t*128.. | 128 gate rows half + t*128..]
   char* dst = reinterpret_cast<char*>(c.dmalloc((size_t)n * K * 2));
   const char* src = reinterpret_cast<const char*>(w.p);
-  const size_t blk = (size_t)64 * K * 2;
-  UG_CUDA(cudaMemcpy2DAsync(dst, 2 * blk, src, blk, blk, half / 64, cudaMemcpyDeviceToDevice, st));
-  UG_CUDA(cudaMemcpy2DAsync(dst + blk, 2 * blk, src + (size_t)half * K * 2, blk, blk, half / 64,
+  const size_t blk = (size_t)128 * K * 2;
+  UG_CUDA(cudaMemcpy2DAsync(dst, 2 * blk, src, blk, blk, half / 128, cudaMemcpyDeviceToDevice, st));
+  UG_CUDA(cudaMemcpy2DAsync(dst + blk, 2 * blk, src + (size_t)half * K * 2, blk, blk, half / 128,
                             cudaMemcpyDeviceToDevice, st));
   add_weight(c, k + ".net.0.proj.geglu.weight", dst, false, 1, n, K);
   const char* bs = reinterpret_cast<const char*>(c.F(k + ".net.0.proj.bias"));
   char* bd = reinterpret_cast<char*>(c.dmalloc((size_t)n * 4));
-  UG_CUDA(cudaMemcpy2DAsync(bd, 512, bs, 256, 256, half / 64, cudaMemcpyDeviceToDevice, st));
-  UG_CUDA(cudaMemcpy2DAsync(bd + 256, 512, bs + (size_t)half * 4, 256, 256, half / 64, cudaMemcpyDeviceToDevice,
+  UG_CUDA(cudaMemcpy2DAsync(bd, 1024, bs, 512, 512, half / 128, cudaMemcpyDeviceToDevice, st));
+  UG_CUDA(cudaMemcpy2DAsync(bd + 512, 1024, bs + (size_t)half * 4, 512, 512, half / 128, cudaMemcpyDeviceToDevice,
                             st));
   add_weight(c, k + ".net.0.proj.geglu.bias", bd, true, 1, n, 1);
 }

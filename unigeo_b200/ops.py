@@ -39,11 +39,11 @@ def linear(x, W, bias=None, res=None, geglu=False, out_fp32=False):
 
 
 def geglu_interleave(W, b):
-    """[2H,K] (value rows | gate rows) -> 128-row tiles of [64 value | 64 gate] (what ug_ctx_finalize builds)."""
+    """[2H,K] (value rows | gate rows) -> 256-row tiles of [128 value | 128 gate] (what ug_ctx_finalize builds)."""
     H = W.shape[0] // 2
-    Wv, Wg = W[:H].reshape(H // 64, 64, -1), W[H:].reshape(H // 64, 64, -1)
+    Wv, Wg = W[:H].reshape(H // 128, 128, -1), W[H:].reshape(H // 128, 128, -1)
     Wi = torch.cat([Wv, Wg], dim=1).reshape(2 * H, -1).contiguous()
-    bv, bg = b[:H].reshape(H // 64, 64), b[H:].reshape(H // 64, 64)
+    bv, bg = b[:H].reshape(H // 128, 128), b[H:].reshape(H // 128, 128)
     return Wi, torch.cat([bv, bg], dim=1).reshape(2 * H).contiguous()
 
 
