@@ -151,7 +151,8 @@ def test_layernorm(cuda, dtype, rows, C, div):
 
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("Fr,N,C,dh", [(2, 256, 128, 64), (3, 48, 128, 64), (1, 192, 64, 64), (2, 128, 128, 128),
-                                       (2, 1024, 64, 64), (1, 16, 64, 64), (1, 144, 512, 512)])
+                                       (2, 1024, 64, 64), (1, 16, 64, 64), (1, 144, 512, 512),
+                                       (2, 3072, 320, 64), (3, 200, 128, 64), (1, 2304, 64, 64)])
 def test_spatial_attention(cuda, dtype, Fr, N, C, dh):
     from unigeo_b200 import ops
     qkv = rnd((Fr * N, 3 * C), dtype, cuda, 1)

@@ -93,6 +93,7 @@ struct Ctx {
   UNetModel* unet = nullptr;
   VaeModel* vae = nullptr;
   bool finalized = false;
+  bool attn_materialized = false; // true: head_dim-64 attention through QK^T / softmax / PV GEMMs (A/B debug)
   // prepared clip shape
   int T = 0, h = 0, w = 0;
   std::vector<void*> owned;      // cudaMalloc'd blocks to free at destroy

@@ -1,5 +1,6 @@
 // Op wrappers: turn layer-level calls into tensor maps + tapgemm launches / kernel launches.
 #include "ctx.cuh"
+#include "fmha.cuh"
 
 #include <cmath>
 #include <cstring>
@@ -265,6 +266,25 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
   UG_CHECK(dh == 64 || dh == C, UG_ERR_INVALID, "attention: head_dim must be 64 or C");
   UG_CHECK((N % 8) == 0 && (dh % 64) == 0, UG_ERR_INVALID, "attention: N % 8 and head_dim % 64");
   const int heads = C / dh;
+  if (dh == 64 && !c.attn_materialized) {
+    // fused flash attention (tcgen05): no score tensor in HBM
+    if (c.dry) return;
+    TmapDesc d;
+    d.ptr = qkv; d.elem_fmt = c.fmt; d.rank = 2;
+    d.dims[0] = (unsigned long long)3 * C; d.dims[1] = (unsigned long long)F * N;
+    d.strides[0] = (unsigned long long)3 * C * 2;
+    d.box[0] = 64; d.box[1] = 128;
+    CUtensorMap tm;
+    int r = encode_tmap(&tm, d);
+    if (r != 0) throw UgError(UG_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed: " + std::to_string(r));
+    FmhaArgs fa;
+    fa.N = N; fa.C = C; fa.heads = heads; fa.F = F;
+    fa.scale_log2 = 1.4426950408889634f / sqrtf((float)dh);
+    fa.out = out; fa.fmt = c.fmt;
+    op_check(c, launch_fmha_d64(tm, fa, c.stream), "fmha_d64", 4.0 * F * heads * (double)N * N * dh,
+             8.0 * F * (double)N * C);
+    return;
+  }
   const size_t m = c.ws.mark();
   void* S = c.alloc16((long long)F * heads * N * N);
   if (!c.dry) {
