@@ -127,71 +127,121 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void
   const long long r_begin = (long long)blockIdx.x * chunk_rows;
   long long r_end = r_begin + chunk_rows;
   if (r_end > rows_per_set) r_end = rows_per_set;
-  const long long n_items = (r_end - r_begin) * nvec;
+  // thread = (row slot rr, channel vector c8): scale/shift of its 8 channels stay in registers
+  const int rpb = blockDim.x / nvec;
+  const int c8 = threadIdx.x % nvec;
+  const int rr = threadIdx.x / nvec;
+  if (rr >= rpb) return;
+  float sa[8], sb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sa[j] = s_a[c8 * 8 + j]; sb[j] = s_b[c8 * 8 + j]; }
   uint4* yo = reinterpret_cast<uint4*>(y);
-  for (long long i = threadIdx.x; i < n_items; i += blockDim.x) {
-    const long long r = set * rows_per_set + r_begin + i / nvec;
-    const int c8 = (int)(i % nvec);
-    uint4 u = __ldg(cat_ptr(x1, nv1, x2, nv2, r, c8));
-    float f[8];
-    unpack8<T>(u, f);
+  long long r = r_begin + rr;
+  // two rows in flight per thread
+  for (; r + rpb < r_end; r += 2 * rpb) {
+    const long long g0 = set * rows_per_set + r, g1 = g0 + rpb;
+    const uint4 u0 = __ldg(cat_ptr(x1, nv1, x2, nv2, g0, c8));
+    const uint4 u1 = __ldg(cat_ptr(x1, nv1, x2, nv2, g1, c8));
+    float f0[8], f1[8];
+    unpack8<T>(u0, f0);
+    unpack8<T>(u1, f1);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float v = f[j] * s_a[c8 * 8 + j] + s_b[c8 * 8 + j];
-      f[j] = silu ? silu_f(v) : v;
+      const float v0 = fmaf(f0[j], sa[j], sb[j]), v1 = fmaf(f1[j], sa[j], sb[j]);
+      f0[j] = silu ? silu_f(v0) : v0;
+      f1[j] = silu ? silu_f(v1) : v1;
     }
-    yo[r * nvec + c8] = pack8<T>(f);
+    yo[g0 * nvec + c8] = pack8<T>(f0);
+    yo[g1 * nvec + c8] = pack8<T>(f1);
+  }
+  for (; r < r_end; r += rpb) {
+    const long long g0 = set * rows_per_set + r;
+    float f0[8];
+    unpack8<T>(__ldg(cat_ptr(x1, nv1, x2, nv2, g0, c8)), f0);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float v0 = fmaf(f0[j], sa[j], sb[j]);
+      f0[j] = silu ? silu_f(v0) : v0;
+    }
+    yo[g0 * nvec + c8] = pack8<T>(f0);
   }
 }
 
-// ------------------------------------------------------------------ LayerNorm (warp per row)
-template <typename T>
-__global__ void layernorm_kernel(const void* __restrict__ x, long long rows, int C,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                 const float* __restrict__ add, int add_div, void* __restrict__ y) {
+// ------------------------------------------------------------------ LayerNorm
+// A warp normalises ROWS rows at once (VPL 16-byte vectors per lane and row) so that enough loads are
+// in flight per SM to cover HBM latency; statistics are two-pass in registers.
+template <typename T, int VPL, int ROWS>
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, const float* __restrict__ add, int add_div,
+                 void* __restrict__ y) {
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+  if (row0 >= rows) return;
   const int nvec = C >> 3;
-  const uint4* xr = reinterpret_cast<const uint4*>(x) + row * nvec;
-  const float* addr = add ? add + (row / add_div) * C : nullptr;
-  float f[8][8];
-  float s = 0.f;
+  const uint4* xb = reinterpret_cast<const uint4*>(x);
+  float f[ROWS][VPL][8];
+  uint4 raw[ROWS][VPL];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int i = lane + 32 * k;
-    if (i < nvec) {
-      uint4 u = __ldg(xr + i);
-      unpack8<T>(u, f[k]);
-      if (addr) {
+  for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[k][j] += __ldg(addr + i * 8 + j);
+    for (int k = 0; k < VPL; ++k) {
+      const int i = lane + 32 * k;
+      if (row0 + r < rows && i < nvec) raw[r][k] = __ldg(xb + (row0 + r) * nvec + i);
+    }
+  float mean[ROWS], rstd[ROWS];
+#pragma unroll
+  for (int r = 0; r < ROWS; ++r) {
+    float s = 0.f;
+    const bool rok = row0 + r < rows;
+    const float* addr = (add && rok) ? add + ((row0 + r) / add_div) * C : nullptr;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {
+      const int i = lane + 32 * k;
+      if (rok && i < nvec) {
+        unpack8<T>(raw[r][k], f[r][k]);
+        if (addr) {
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(addr + i * 8));
+          const float4 a1 = __ldg(reinterpret_cast<const float4*>(addr + i * 8) + 1);
+          f[r][k][0] += a0.x; f[r][k][1] += a0.y; f[r][k][2] += a0.z; f[r][k][3] += a0.w;
+          f[r][k][4] += a1.x; f[r][k][5] += a1.y; f[r][k][6] += a1.z; f[r][k][7] += a1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += f[r][k][j];
       }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) s += f[k][j];
     }
-  }
-  const float mean = warp_sum(s) / (float)C;
-  float v = 0.f;
+    mean[r] = warp_sum(s) / (float)C;
+    float v = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < VPL; ++k) {
+      const int i = lane + 32 * k;
+      if (rok && i < nvec) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { const float d = f[r][k][j] - mean[r]; v += d * d; }
+      }
+    }
+    rstd[r] = rsqrtf(warp_sum(v) / (float)C + eps);
+  }
+  uint4* yb = reinterpret_cast<uint4*>(y);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
     const int i = lane + 32 * k;
     if (i < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + i * 8));
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + i * 8) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + i * 8));
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + i * 8) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = f[k][j] - mean; v += d * d; }
-    }
-  }
-  const float rstd = rsqrtf(warp_sum(v) / (float)C + eps);
-  uint4* yr = reinterpret_cast<uint4*>(y) + row * nvec;
+      for (int r = 0; r < ROWS; ++r) {
+        if (row0 + r < rows) {
+          float o[8];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    const int i = lane + 32 * k;
-    if (i < nvec) {
-      float o[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        o[j] = (f[k][j] - mean) * rstd * __ldg(gamma + i * 8 + j) + __ldg(beta + i * 8 + j);
-      yr[i] = pack8<T>(o);
+          for (int j = 0; j < 8; ++j) o[j] = (f[r][k][j] - mean[r]) * rstd[r] * gg[j] + bb[j];
+          yb[(row0 + r) * nvec + i] = pack8<T>(o);
+        }
+      }
     }
   }
 }
@@ -556,20 +606,32 @@ int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long ro
   GnGeom g = gn_geom(C / 8, rows_per_set, sets);
   dim3 grid(g.chunks, (unsigned)sets);
   const size_t smem = (size_t)(C * 2 + G * 2) * sizeof(float);
-  UG_DISPATCH_FMT(fmt, (gn_apply_kernel<T><<<grid, 256, smem, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
+  UG_DISPATCH_FMT(fmt, (gn_apply_kernel<T><<<grid, g.threads, smem, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
                                                                       g.chunk_rows, G, C / G, stats, gamma, beta,
                                                                       eps, silu, y)));
+  return last_err();
+}
+
+template <int VPL, int ROWS>
+int launch_ln_t(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
+                const float* add, int add_div, void* y, int fmt, cudaStream_t st) {
+  const int wpb = 8;
+  const long long rows_per_block = (long long)wpb * ROWS;
+  const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
+  UG_DISPATCH_FMT(fmt, (layernorm_kernel<T, VPL, ROWS><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, add,
+                                                                                  add_div > 0 ? add_div : 1, y)));
   return last_err();
 }
 
 int launch_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
                      const float* add, int add_div, void* y, int fmt, cudaStream_t st) {
   if ((C & 7) || C > 2048) return (int)cudaErrorInvalidValue;
-  const int wpb = 8;
-  const unsigned grid = (unsigned)((rows + wpb - 1) / wpb);
-  UG_DISPATCH_FMT(fmt, (layernorm_kernel<T><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, add,
-                                                                         add_div > 0 ? add_div : 1, y)));
-  return last_err();
+  const int vpl = (C / 8 + 31) / 32;
+  if (vpl <= 1) return launch_ln_t<1, 4>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
+  if (vpl <= 2) return launch_ln_t<2, 4>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
+  if (vpl <= 3) return launch_ln_t<3, 2>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
+  if (vpl <= 5) return launch_ln_t<5, 2>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
+  return launch_ln_t<8, 1>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
 }
 
 int launch_softmax_rows(void* s, long long rows, int n, float scale, int fmt, cudaStream_t st) {
