@@ -88,12 +88,42 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void
   }
 }
 
+// ------------------------------------------------------------------ GroupNorm finalize
+// one CTA per statistics set: (mean, rstd) per group from the per-chunk partials, summed in a fixed
+// order (thread k adds chunks k, k+8, ...; the 8 lanes of a group are then folded in lane order).
+__global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, int G, float inv_cnt, float eps,
+                                   float* __restrict__ mr) {
+  __shared__ float s_s[8][64], s_q[8][64];
+  const long long set = blockIdx.x;
+  const int g = threadIdx.x % G;
+  const int k = threadIdx.x / G;          // 0..7
+  float sa = 0.f, sq = 0.f;
+  for (int ch = k; ch < chunks; ch += 8) {
+    const float* o = part + ((set * chunks + ch) * G + g) * 2;
+    sa += o[0];
+    sq += o[1];
+  }
+  s_s[k][g] = sa;
+  s_q[k][g] = sq;
+  __syncthreads();
+  if (k == 0) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += s_s[i][g]; q += s_q[i][g]; }
+    const float mean = a * inv_cnt;
+    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+    mr[(set * G + g) * 2 + 0] = mean;
+    mr[(set * G + g) * 2 + 1] = rsqrtf(var + eps);
+  }
+}
+
 // ------------------------------------------------------------------ GroupNorm apply (+SiLU)
 template <typename T>
 __global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
                                 long long rows_per_set, long long chunk_rows, int G, int cs,
-                                const float* __restrict__ part, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float eps, int silu, void* __restrict__ y) {
+                                const float* __restrict__ part /* [sets][G] (mean, rstd) */,
+                                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                                void* __restrict__ y) {
   extern __shared__ float s_ab[];   // [C] scale, [C] shift, [G] mean, [G] rstd
   const int nvec = nv1 + nv2;
   const int C = nvec * 8;
@@ -102,19 +132,9 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void
   float* s_mean = s_b + C;
   float* s_rstd = s_mean + G;
   const long long set = blockIdx.y;
-  const float inv_cnt = 1.0f / ((float)rows_per_set * (float)cs);
   if (threadIdx.x < G) {
-    const int g = threadIdx.x;
-    float sa = 0.f, sq = 0.f;
-    for (int ch = 0; ch < (int)gridDim.x; ++ch) {
-      const float* o = part + ((set * gridDim.x + ch) * G + g) * 2;
-      sa += o[0];
-      sq += o[1];
-    }
-    const float mean = sa * inv_cnt;
-    const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
-    s_mean[g] = mean;
-    s_rstd[g] = rsqrtf(var + eps);
+    s_mean[threadIdx.x] = part[(set * G + threadIdx.x) * 2 + 0];
+    s_rstd[threadIdx.x] = part[(set * G + threadIdx.x) * 2 + 1];
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -302,7 +322,7 @@ __global__ void softmax_rows_kernel(void* __restrict__ s, long long rows, int n,
 template <typename T, int TMAX>
 __global__ void temporal_attn_kernel(const void* __restrict__ qkv, void* __restrict__ out, int Tn, long long P,
                                      int C, float scale_log2e) {
-  extern __shared__ uint32_t sm_kv[];
+  extern __shared__ __align__(16) uint32_t sm_kv[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int heads = C >> 6;
   const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
@@ -332,15 +352,18 @@ __global__ void temporal_attn_kernel(const void* __restrict__ qkv, void* __restr
     }
     float sc[TMAX];
     float m = -INFINITY;
+    const uint4* K4 = reinterpret_cast<const uint4*>(Ks);    // [T][8] x 16 B: one LDS.128 broadcast = 8 dims
+    const uint4* V4 = reinterpret_cast<const uint4*>(Vs);
 #pragma unroll
     for (int i = 0; i < TMAX; ++i) {
       if (i < Tn) {
         float acc = 0.f;
 #pragma unroll
-        for (int d2 = 0; d2 < 32; ++d2) {
-          float2 kk = Elem<T>::unpack2(Ks[i * 32 + d2]);
-          acc = fmaf(q[2 * d2], kk.x, acc);
-          acc = fmaf(q[2 * d2 + 1], kk.y, acc);
+        for (int d8 = 0; d8 < 8; ++d8) {
+          float kk[8];
+          unpack8<T>(K4[i * 8 + d8], kk);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc = fmaf(q[d8 * 8 + e], kk[e], acc);
         }
         sc[i] = acc;
         m = fmaxf(m, acc);
@@ -361,10 +384,11 @@ __global__ void temporal_attn_kernel(const void* __restrict__ qkv, void* __restr
         // probabilities are rounded to the storage type before P*V, like the 16-bit reference path
         const float pw = Elem<T>::to_f(Elem<T>::from_f(sc[i] * inv));
 #pragma unroll
-        for (int d2 = 0; d2 < 32; ++d2) {
-          float2 vv = Elem<T>::unpack2(Vs[i * 32 + d2]);
-          o[2 * d2] = fmaf(pw, vv.x, o[2 * d2]);
-          o[2 * d2 + 1] = fmaf(pw, vv.y, o[2 * d2 + 1]);
+        for (int d8 = 0; d8 < 8; ++d8) {
+          float vv[8];
+          unpack8<T>(V4[i * 8 + d8], vv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) o[d8 * 8 + e] = fmaf(pw, vv[e], o[d8 * 8 + e]);
         }
       }
     }
@@ -580,7 +604,7 @@ inline GnGeom gn_geom(int nvec, long long rows_per_set, long long sets) {
 long long gn_partial_floats(int C, long long rows, long long rows_per_set, int G) {
   const long long sets = rows / rows_per_set;
   GnGeom g = gn_geom(C / 8, rows_per_set, sets);
-  return sets * g.chunks * G * 2;
+  return sets * g.chunks * G * 2 + sets * G * 2;     // per-chunk partials, then (mean, rstd) per set
 }
 
 int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
@@ -597,6 +621,16 @@ int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long ro
   return last_err();
 }
 
+int launch_gn_finalize(int C, long long rows, long long rows_per_set, int G, float eps, float* stats,
+                       cudaStream_t st) {
+  const long long sets = rows / rows_per_set;
+  GnGeom g = gn_geom(C / 8, rows_per_set, sets);
+  float* mr = stats + sets * g.chunks * G * 2;
+  const float inv_cnt = 1.0f / ((float)rows_per_set * (float)(C / G));
+  gn_finalize_kernel<<<(unsigned)sets, 8 * G, 0, st>>>(stats, g.chunks, G, inv_cnt, eps, mr);
+  return last_err();
+}
+
 int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
                     int G, const float* stats, const float* gamma, const float* beta, float eps, int silu,
                     void* y, int fmt, cudaStream_t st) {
@@ -606,9 +640,11 @@ int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long ro
   GnGeom g = gn_geom(C / 8, rows_per_set, sets);
   dim3 grid(g.chunks, (unsigned)sets);
   const size_t smem = (size_t)(C * 2 + G * 2) * sizeof(float);
+  const float* mr = stats + sets * g.chunks * G * 2;
+  (void)eps;
   UG_DISPATCH_FMT(fmt, (gn_apply_kernel<T><<<grid, g.threads, smem, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
-                                                                      g.chunk_rows, G, C / G, stats, gamma, beta,
-                                                                      eps, silu, y)));
+                                                                            g.chunk_rows, G, C / G, mr, gamma, beta,
+                                                                            silu, y)));
   return last_err();
 }
 

@@ -16,6 +16,9 @@ namespace ug {
 long long gn_partial_floats(int C, long long rows, long long rows_per_set, int G);
 int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
                     int G, float* stats, int fmt, cudaStream_t st);
+// folds the partials into (mean, rstd) per (set, group), stored behind the partials in `stats`
+int launch_gn_finalize(int C, long long rows, long long rows_per_set, int G, float eps, float* stats,
+                       cudaStream_t st);
 // y = act((x - mean) * rstd * gamma + beta), act = SiLU when silu != 0; y is [rows][C] dense.
 int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
                     int G, const float* stats, const float* gamma, const float* beta, float eps, int silu,

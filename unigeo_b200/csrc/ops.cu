@@ -152,7 +152,8 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   a.kchunks = cdiv(K, 64);
   a.n_total = N;
   fill_epi(a, e, c.fmt);
-  const int bn = a.bn_tile = tapgemm_pick_bn(a, 1);
+  a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
+  const int bn = a.bn_tile / a.ctas;
   CUtensorMap ma, mb;
   unsigned long long dims[5] = {(unsigned long long)K, (unsigned long long)M, 1, 1, 1};
   unsigned long long st[4] = {(unsigned long long)ldx * 2, (unsigned long long)ldx * 2 * M,
@@ -181,7 +182,8 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
   a.b_tap_rows = Cout;
   a.n_total = Cout;
   fill_epi(a, e, c.fmt);
-  const int bn = a.bn_tile = tapgemm_pick_bn(a, 1);
+  a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
+  const int bn = a.bn_tile / a.ctas;
   CUtensorMap ma, mb;
   const unsigned long long rowb = (unsigned long long)C * 2;
   if (stride == 1) {
@@ -250,7 +252,8 @@ void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm,
     if (e.blend) ec.blend = reinterpret_cast<const char*>(e.blend) + tok0 * e.ldb * 2;
     if (e.fbias) ec.fbias = e.fbias + (tok0 / ec.fbias_div) * e.fbias_ld;
     fill_epi(a, ec, c.fmt);
-    const int bn = a.bn_tile = tapgemm_pick_bn(a, 1);
+    a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
+  const int bn = a.bn_tile / a.ctas;
     CUtensorMap ma, mb;
     unsigned long long dims[5] = {(unsigned long long)C, (unsigned long long)P, (unsigned long long)Tc, 1, 1};
     unsigned long long st[4] = {rowb, rowb * P, rowb * P * Tc, rowb * P * Tc};
@@ -311,8 +314,8 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
       unsigned long long dims[5] = {(unsigned long long)3 * C, (unsigned long long)F * N, 1, 1, 1};
       unsigned long long st[4] = {rowb, rowb * F * N, rowb * F * N, rowb * F * N};
       make_a_map(&ma, qkv, c.fmt, dims, st, a.bw, 1, 1, 1);
-      a.bn_tile = tapgemm_pick_bn(a, F * heads);
-      make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb, a.bn_tile);
+      a.bn_tile = tapgemm_pick_tile(a, F * heads, &a.ctas);
+      make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb, a.bn_tile / a.ctas);
       launch(c, ma, mb, a, F * heads, "tapgemm.attn_qk", dh);
     }
     op_check(c, launch_softmax_rows(S, (long long)F * heads * N, N, 1.0f / sqrtf((float)dh), c.fmt, c.stream),
@@ -342,7 +345,7 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
                                     (unsigned long long)F, 1};
       unsigned long long st[4] = {srow, srow * N, srow * N * heads, srow * N * heads * F};
       make_a_map(&ma, S, c.fmt, dims, st, a.bw, 1, 1, 1);
-      a.bn_tile = tapgemm_pick_bn(a, F * heads);   // 64: MN-major boxes are [64 K][64 N]
+      a.bn_tile = tapgemm_pick_tile(a, F * heads, &a.ctas);   // 64, 1 CTA: MN-major boxes are [64 K][64 N]
       make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb, 64);
       launch(c, ma, mb, a, F * heads, "tapgemm.attn_pv", N);
     }
@@ -361,6 +364,7 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
   if (!c.dry) {
     op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, stats, c.fmt, c.stream), "gn_stats", 0.0,
              2.0 * rows * (C1 + C2));
+    op_check(c, launch_gn_finalize(C1 + C2, rows, rows_per_set, G, eps, stats, c.stream), "gn_finalize");
     op_check(c, launch_gn_apply(x1, C1, x2, C2, rows, rows_per_set, G, stats, gamma, beta, eps, silu, y, c.fmt,
                                 c.stream),
              "gn_apply", 0.0, 4.0 * rows * (C1 + C2));

@@ -9,6 +9,7 @@
 #include "ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 namespace ug {
@@ -24,6 +25,10 @@ constexpr int kBTileBytes = 256 * BK * 2;            // room for the widest N ti
 constexpr int kStageBytes = kATileBytes + kBTileBytes;
 constexpr int kStages = 4;
 constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+// CTA-pair mode: each CTA stages 128 rows of A and at most 128 rows (half) of B
+constexpr int kStageBytes2 = kATileBytes + 128 * BK * 2;
+constexpr int kStages2 = 6;
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
 
 // exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below 16-bit output
 // resolution): 2 MUFU + ~12 FMA-pipe instructions instead of libm erff's ~30
@@ -164,29 +169,42 @@ __device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmAr
   }
 }
 
-// Persistent kernel: one CTA per SM walks output tiles t = blockIdx.x, += gridDim.x.  The three
-// roles run ahead of each other across tiles: the TMA ring (kStages) never drains between
-// tiles, and the accumulator is double-buffered in TMEM (2 x 256 columns) so the MMAs of tile
-// i+1 overlap the epilogue of tile i.  BN (the UMMA N extent) is a RUNTIME multiple of 16 <= 256
-// chosen per layer so that N splits without padding (e.g. 320 -> 2 x 160).
+// Persistent kernel: one CTA per SM walks output tiles t, t + stride, ...  The three roles run ahead of
+// each other across tiles: the TMA ring never drains between tiles, and the accumulator is
+// double-buffered in TMEM (2 x 256 columns) so the MMAs of tile i+1 overlap the epilogue of tile i.
+// BN (the UMMA N extent) is a RUNTIME multiple of 16 <= 256 chosen per layer.
+//
+// CTAS == 2: the two CTAs of a cluster (one TPC) compute a 256 x BN tile with cta_group::2 UMMAs.  Each
+// CTA stages its own 128 rows of A and HALF of the B tile, so shared-memory fill + operand-read
+// traffic per FLOP drops by 1/3 against the single-CTA 128 x 256 tile (the binding resource here).
+// The leader (rank 0) issues every MMA; commits are multicast to both CTAs' barriers; each CTA's TMA
+// counts its bytes on the leader's full barrier; both epilogues release the accumulator by arriving
+// on the leader's tmem_empty barrier.
+template <int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TapGemmArgs a) {
+  constexpr int kSt = CTAS == 2 ? kStages2 : kStages;
+  constexpr int kStB = CTAS == 2 ? kStageBytes2 : kStageBytes;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;     // [2]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSt * kStB);
+  uint64_t* empty_bar = full_bar + kSt;
+  uint64_t* tmem_full_bar = empty_bar + kSt;         // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int BN = a.bn_tile;
+  const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
+  const int BN = a.bn_tile;                          // full tile width (both CTAs see all BN columns)
+  const int BNL = BN / CTAS;                         // B rows staged by this CTA
   const int m_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
+  const int pm_tiles = (m_tiles + CTAS - 1) / CTAS;  // tiles along M per scheduling unit
   const int n_tiles = a.n_tiles;
-  const int total_tiles = m_tiles * n_tiles * a.batch;
+  const int total_tiles = pm_tiles * n_tiles * a.batch;
   const int num_iters = a.num_taps * a.kchunks;
+  const int unit0 = blockIdx.x / CTAS, unit_stride = gridDim.x / CTAS;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -194,40 +212,45 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < kStages; ++s) {
+      for (int s = 0; s < kSt; ++s) {
         mbar_init(&full_bar[s], 1);
         mbar_init(&empty_bar[s], 1);
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(&tmem_full_bar[b], 1);
-        mbar_init(&tmem_empty_bar[b], kEpiWarps);
+        mbar_init(&tmem_empty_bar[b], kEpiWarps * CTAS);
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr_smem, 512);
-    tmem_relinquish();
+    if constexpr (CTAS == 2) {
+      tmem_alloc_pair(tmem_ptr_smem, 512);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_smem, 512);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      const uint32_t tx_bytes = (uint32_t)(a.bw * a.bh * a.bn) * (BK * 2) +
-                                (uint32_t)(a.b_mn_major ? BK : BN) * (BK * 2);
+      const uint32_t tx_bytes = ((uint32_t)(a.bw * a.bh * a.bn) * (BK * 2) +
+                                 (uint32_t)(a.b_mn_major ? BK : BNL) * (BK * 2)) * CTAS;
       int it_g = 0;   // ring position, continuous across tiles
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        int m_tile = t % m_tiles;
-        const int rest = t / m_tiles;
+      for (int t = unit0; t < total_tiles; t += unit_stride) {
+        int m_tile = (t % pm_tiles) * CTAS + rank;
+        const int rest = t / pm_tiles;
         const int n0 = (rest % n_tiles) * BN;
         const int z = rest / n_tiles;
         const int z1 = z / a.zdiv, z0 = z - z1 * a.zdiv;
         const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
         const int ty = m_tile % a.tiles_y;
-        const int tn = m_tile / a.tiles_y;
+        const int tn = m_tile / a.tiles_y;             // >= tiles_n for the phantom half of an odd pair: OOB -> zeros
         int base[6] = {0, 0, 0, 0, 0, 0};   // slot 5 swallows unused roles
         base[a.dim_x] += tx * a.bw;
         base[a.dim_y] += ty * a.bh;
@@ -235,69 +258,96 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         base[a.dim_z1] += z1 * a.a_z1step;
         base[a.dim_z0] += z0 * a.a_z0step;
         const int bcol0 = a.b_c0 + z0 * a.b_z0_cstep;
-        const int brow0 = z1 * a.b_z1_rowstep + (a.b_mn_major ? 0 : n0);
+        const int brow0 = z1 * a.b_z1_rowstep + (a.b_mn_major ? 0 : n0 + rank * BNL);
         for (int it = 0; it < num_iters; ++it, ++it_g) {
-          const int s = it_g % kStages;
-          const uint32_t ph = (uint32_t)(it_g / kStages) & 1u;
+          const int s = it_g % kSt;
+          const uint32_t ph = (uint32_t)(it_g / kSt) & 1u;
           const int tap = it / a.kchunks;
           const int kc = it - tap * a.kchunks;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-          uint8_t* sa = smem + s * kStageBytes;
+          uint8_t* sa = smem + s * kStB;
           uint8_t* sb = sa + kATileBytes;
-          tma_load_5d(sa, &tmA, &full_bar[s], base[0] + a.tap_off[tap][0] + kc * BK, base[1] + a.tap_off[tap][1],
-                      base[2] + a.tap_off[tap][2], base[3] + a.tap_off[tap][3], base[4] + a.tap_off[tap][4]);
-          if (a.b_mn_major)  // [64 K rows][64 N elements] box of a row-major [K, N] matrix
-            tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + n0, brow0 + kc * BK);
-          else
-            tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + kc * BK, brow0 + tap * a.b_tap_rows);
+          if constexpr (CTAS == 2) {
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+            tma_load_5d_pair(sa, &tmA, &full_bar[s], base[0] + a.tap_off[tap][0] + kc * BK,
+                             base[1] + a.tap_off[tap][1], base[2] + a.tap_off[tap][2], base[3] + a.tap_off[tap][3],
+                             base[4] + a.tap_off[tap][4]);
+            tma_load_2d_pair(sb, &tmB, &full_bar[s], bcol0 + kc * BK, brow0 + tap * a.b_tap_rows);
+          } else {
+            mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+            tma_load_5d(sa, &tmA, &full_bar[s], base[0] + a.tap_off[tap][0] + kc * BK, base[1] + a.tap_off[tap][1],
+                        base[2] + a.tap_off[tap][2], base[3] + a.tap_off[tap][3], base[4] + a.tap_off[tap][4]);
+            if (a.b_mn_major)  // [64 K rows][64 N elements] box of a row-major [K, N] matrix
+              tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + n0, brow0 + kc * BK);
+            else
+              tma_load_2d(sb, &tmB, &full_bar[s], bcol0 + kc * BK, brow0 + tap * a.b_tap_rows);
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ===================== UMMA issuer =====================
-    const uint32_t idesc = make_idesc_f16(BM, BN, a.fmt, a.b_mn_major);
-    const uint32_t bstep = a.b_mn_major ? 128u : 2u;
-    int it_g = 0, tl = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-      const int buf = tl & 1;
-      const uint32_t use = (uint32_t)(tl >> 1);
-      mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);     // epilogue drained this accumulator
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
-      for (int it = 0; it < num_iters; ++it, ++it_g) {
-        const int s = it_g % kStages;
-        const uint32_t ph = (uint32_t)(it_g / kStages) & 1u;
-        mbar_wait(&full_bar[s], ph);
+    // ===================== UMMA issuer (leader CTA only in pair mode) =====================
+    if (rank == 0) {
+      const uint32_t idesc = make_idesc_f16(BM * CTAS, BN, a.fmt, a.b_mn_major);
+      const uint32_t bstep = a.b_mn_major ? 128u : 2u;
+      int it_g = 0, tl = 0;
+      for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
+        const int buf = tl & 1;
+        const uint32_t use = (uint32_t)(tl >> 1);
+        mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);     // epilogue(s) drained this accumulator
         tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_u32(smem + s * kStageBytes);
-          const uint64_t da = make_desc_kmajor_sw128(sa);
-          // K-major: +32 B per K=16 slice inside the 128-byte swizzle row (start field += 2).
-          // MN-major: a K=16 slice is 16 rows of 128 B (start field += 128).
-          const uint64_t db = a.b_mn_major ? make_desc_mnmajor_sw128(sa + kATileBytes, 8192)
-                                           : make_desc_kmajor_sw128(sa + kATileBytes);
+        const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
+        for (int it = 0; it < num_iters; ++it, ++it_g) {
+          const int s = it_g % kSt;
+          const uint32_t ph = (uint32_t)(it_g / kSt) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t sa = smem_u32(smem + s * kStB);
+            const uint64_t da = make_desc_kmajor_sw128(sa);
+            // K-major: +32 B per K=16 slice inside the 128-byte swizzle row (start field += 2).
+            // MN-major: a K=16 slice is 16 rows of 128 B (start field += 128).
+            const uint64_t db = a.b_mn_major ? make_desc_mnmajor_sw128(sa + kATileBytes, 8192)
+                                             : make_desc_kmajor_sw128(sa + kATileBytes);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_f16(tmem_d, da + 2 * k, db + bstep * k, idesc, (it | k) != 0 ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
-          if (it == num_iters - 1) umma_commit(&tmem_full_bar[buf]);
+            for (int k = 0; k < BK / 16; ++k) {
+              if constexpr (CTAS == 2)
+                umma_f16_pair(tmem_d, da + 2 * k, db + bstep * k, idesc, (it | k) != 0 ? 1u : 0u);
+              else
+                umma_f16(tmem_d, da + 2 * k, db + bstep * k, idesc, (it | k) != 0 ? 1u : 0u);
+            }
+            if constexpr (CTAS == 2) {
+              umma_commit_pair(&empty_bar[s]);
+              if (it == num_iters - 1) umma_commit_pair(&tmem_full_bar[buf]);
+            } else {
+              umma_commit(&empty_bar[s]);
+              if (it == num_iters - 1) umma_commit(&tmem_full_bar[buf]);
+            }
+          }
+          __syncwarp();
         }
-        __syncwarp();
       }
     }
   } else {
     // ===================== epilogue (8 warps: 4 lane quarters x 2 column halves) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
     const int hsel = (warp - 2) >> 2;       // which half of the 32-column chunks
-    const int r = q * 32 + lane;            // output row inside the tile
+    const int r = q * 32 + lane;            // output row inside this CTA's 128-row tile
     const int xi = r % a.bw;
     const int yi = (r / a.bw) % a.bh;
     const int ni = r / (a.bw * a.bh);
+    auto release = [&](int buf) {           // this warp no longer needs accumulator `buf`
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (CTAS == 2) mbar_arrive_leader(&tmem_empty_bar[buf]);
+        else mbar_arrive(&tmem_empty_bar[buf]);
+      }
+    };
     int tl = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++tl) {
-      int m_tile = t % m_tiles;
-      const int rest = t / m_tiles;
+    for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
+      int m_tile = (t % pm_tiles) * CTAS + rank;
+      const int rest = t / pm_tiles;
       const int n_tile = rest % n_tiles;
       const int n0 = n_tile * BN;
       const int z = rest / n_tiles;
@@ -322,11 +372,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_32x32(trow + c, v);
           tmem_ld_32x32(trow + BNh + c, g);
           tmem_ld_wait();
-          if (c + 64 >= BNh) {               // last chunk of this warp: accumulator no longer needed
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-          }
+          if (c + 64 >= BNh) release(buf);   // last chunk of this warp
           float f[32];
           if (a.bias != nullptr && n0 + BN <= a.n_total) {     // whole tile in range: vector bias loads
             const float4* bv = reinterpret_cast<const float4*>(a.bias + n0 + c);
@@ -363,12 +409,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t v[32];
             tmem_ld_32x32(trow + c, v);
             tmem_ld_wait();
-            if (last) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-              released = true;
-            }
+            if (last) { release(buf); released = true; }
             float f[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -381,31 +422,22 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t v[16];
             tmem_ld_32x16(trow + c, v);
             tmem_ld_wait();
-            if (last) {
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-              released = true;
-            }
+            if (last) { release(buf); released = true; }
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
             finish_and_store<16>(f, a, pix, zoff, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
           }
         }
-        if (!released) {                     // this warp had no chunk in this tile (narrow BN)
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
-        }
+        if (!released) release(buf);         // this warp had no chunk in this tile (narrow BN)
       }
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    if constexpr (CTAS == 2) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -458,43 +490,85 @@ int tapgemm_num_sms() {
   return n;
 }
 
-// N tile: the multiple of 16 (<= 256) that minimises waves x (columns + fixed per-tile cost).
-int tapgemm_pick_bn(const TapGemmArgs& a, int batch) {
+// Tile shape: (CTAs per tile, N extent).  Cost model per k-iteration in SM cycles, from the measured
+// behaviour that shared-memory bandwidth (128 B/clk: TMA fill + UMMA operand reads) binds before the
+// tensor pipe does:   1 CTA: 256 + 2 BN      CTA pair: max(2 BN, 256 + BN)
+// times the number of waves over the SMs (pairs: over SM pairs), plus a fixed per-tile cost.
+int tapgemm_pick_tile(const TapGemmArgs& a, int batch, int* ctas_out) {
+  *ctas_out = 1;
   if (a.b_mn_major) return 64;           // MN-major B boxes are [64 K][64 N]
-  if (a.geglu) return 256;               // [128 value | 128 gate] column tiles
-  const long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n * batch;
+  const long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
   const int sms = tapgemm_num_sms();
+  static const int force = [] {
+    const char* e = getenv("UG_TAPGEMM_CTAS");
+    return e ? atoi(e) : 0;
+  }();
   int best = 16;
   long long best_cost = -1;
-  for (int bn = 256; bn >= 16; bn -= 16) {
-    const long long tiles = m_tiles * ((a.n_total + bn - 1) / bn);
-    const long long waves = (tiles + sms - 1) / sms;
-    const long long cost = waves * (bn + 24);
-    if (best_cost < 0 || cost < best_cost) {
-      best_cost = cost;
-      best = bn;
+  for (int ctas = 1; ctas <= 2; ++ctas) {
+    if (force && ctas != force) continue;
+    if (ctas == 2 && (m_tiles < 2 || (sms & 1))) continue;
+    for (int bn = 256; bn >= 16 * ctas; bn -= 16 * ctas) {
+      if (a.geglu && bn != 256) continue;      // [128 value | 128 gate] column tiles
+      const long long units = ((m_tiles + ctas - 1) / ctas) * ((a.n_total + bn - 1) / bn) * batch;
+      const long long slots = sms / ctas;
+      const long long waves = (units + slots - 1) / slots;
+      const long long per = ctas == 1 ? 256 + 2 * bn : (2 * bn > 256 + bn ? 2 * bn : 256 + bn);
+      const long long cost = waves * (per + 48);
+      if (best_cost < 0 || cost < best_cost) {
+        best_cost = cost;
+        best = bn;
+        *ctas_out = ctas;
+      }
     }
   }
   return best;
+}
+
+int tapgemm_pick_bn(const TapGemmArgs& a, int batch) {
+  int ctas;
+  return tapgemm_pick_tile(a, batch, &ctas);
 }
 
 int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args_in, int batch,
                    cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(tapgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   TapGemmArgs args = args_in;
-  if (args.bn_tile <= 0 || args.bn_tile > 256 || (args.bn_tile & 15)) return (int)cudaErrorInvalidValue;
+  const int ctas = args.ctas == 2 ? 2 : 1;
+  if (args.bn_tile <= 0 || args.bn_tile > 256 || (args.bn_tile & (16 * ctas - 1))) return (int)cudaErrorInvalidValue;
+  if (ctas == 2 && args.b_mn_major) return (int)cudaErrorInvalidValue;
   args.batch = batch;
   args.n_tiles = (args.n_total + args.bn_tile - 1) / args.bn_tile;
-  const long long total = (long long)args.tiles_x * args.tiles_y * args.tiles_n * args.n_tiles * batch;
-  if (total <= 0 || total > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
-  const int grid = (int)(total < tapgemm_num_sms() ? total : tapgemm_num_sms());
-  tapgemm_kernel<<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, args);
-  return (int)cudaGetLastError();
+  const long long m_tiles = (long long)args.tiles_x * args.tiles_y * args.tiles_n;
+  const long long units = ((m_tiles + ctas - 1) / ctas) * args.n_tiles * batch;
+  if (units <= 0 || units > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
+  const int sms = tapgemm_num_sms();
+  if (ctas == 1) {
+    const int grid = (int)(units < sms ? units : sms);
+    tapgemm_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, args);
+    return (int)cudaGetLastError();
+  }
+  const long long slots = sms / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(2 * (units < slots ? units : slots)));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes2;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return (int)cudaLaunchKernelEx(&cfg, tapgemm_kernel<2>, tmA, tmB, args);
 }
 
 }  // namespace ug

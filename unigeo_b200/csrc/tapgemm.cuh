@@ -42,7 +42,8 @@ struct TapGemmArgs {
   int b_mn_major;          // B tile is [K rows][64 N elements] (e.g. V of attention): needs BN == 64
   // ---- epilogue
   int n_total;             // valid output columns (before GEGLU halving)
-  int bn_tile;             // N extent of one tile: multiple of 16, <= 256 (tapgemm_pick_bn)
+  int bn_tile;             // N extent of one tile: multiple of 16 * ctas, <= 256 (tapgemm_pick_tile)
+  int ctas;                // 1: 128 x BN tile per CTA; 2: 256 x BN tile per CTA pair (cta_group::2)
   int n_tiles, batch;      // filled by launch_tapgemm
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
   int out_fp32;
@@ -79,7 +80,9 @@ int encode_tmap(CUtensorMap* out, const TmapDesc& d);
 int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args, int batch,
                    cudaStream_t stream);
 
-// needs tiles_*, n_total, geglu, b_mn_major filled in
+// needs tiles_*, n_total, geglu, b_mn_major filled in; returns bn_tile and the CTA count per tile.
+// The B tensor map's box must have bn_tile / ctas rows.
+int tapgemm_pick_tile(const TapGemmArgs& args, int batch, int* ctas);
 int tapgemm_pick_bn(const TapGemmArgs& args, int batch);
 int tapgemm_num_sms();
 
