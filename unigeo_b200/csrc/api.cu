@@ -287,6 +287,7 @@ int ug_ctx_profile(ug_ctx* u, int enable) {
   return guard([&] {
     UG_CHECK(u, UG_ERR_INVALID, "null ctx");
     u->c.profile = enable != 0;
+    u->c.profile_shapes = enable == 2;
     u->c.prof.clear();
   });
 }

@@ -5,6 +5,7 @@
 
 #include <cstdint>
 #include <cstdio>
+#include <set>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -101,6 +102,8 @@ struct Ctx {
   // is the gap to the previous event on the (single) stream
   struct ProfRec { const char* name; double flops, bytes; cudaEvent_t ev; };
   bool profile = false;
+  bool profile_shapes = false;           // tapgemm rows keyed by shape (ug_ctx_profile(ctx, 2))
+  std::set<std::string> prof_names;
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   void prof_mark(const char* name, double flops, double bytes);

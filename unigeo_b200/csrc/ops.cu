@@ -3,6 +3,7 @@
 #include "fmha.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 namespace ug {
@@ -125,17 +126,31 @@ void make_b_map(CUtensorMap* m, const void* p, int fmt, unsigned long long cols,
   if (r != 0) throw UgError(UG_ERR_CUDA, "cuTensorMapEncodeTiled(B) failed: " + std::to_string(r));
 }
 
+// TMA tile stores need a 16-bit output whose rows start on 16-byte boundaries
+inline bool can_tma_store(const Epi& e) {
+  static const bool off = getenv("UG_NO_TMA_STORE") != nullptr;
+  return !off && !e.out_fp32 && (e.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(e.out) % 16) == 0;
+}
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline int imin(int a, int b) { return a < b ? a : b; }
 
 // algorithmic work of one tapgemm launch: 2*M*N*K flops over the REAL (unpadded) extents;
 // bytes = A read once + output written once (16-bit), weights ignored (SURVEY.md §8 convention)
 void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmArgs& a, int batch,
-            const char* what, long long k_real) {
+            const char* what, long long k_real, const CUtensorMap* mc = nullptr) {
   const double M = (double)a.W * a.H * a.N * batch;
   const double flops = 2.0 * M * a.n_total * (double)k_real * a.num_taps;
   const double bytes = M * ((double)k_real + (a.geglu ? a.n_total / 2 : a.n_total)) * 2.0;
-  op_check(c, launch_tapgemm(ma, mb, a, batch, c.stream), what, flops, bytes);
+  const char* name = what;
+  if (c.profile && c.profile_shapes) {   // per-shape rows in the profile table
+    const std::string full = std::string(what) + " M" + std::to_string((long long)M) + " N" + std::to_string(a.n_total) +
+                             " K" + std::to_string(k_real * a.num_taps) + " bn" + std::to_string(a.bn_tile) + "x" +
+                             std::to_string(a.ctas) + (a.res ? " +res" : "") + (a.blend ? " +blend" : "") +
+                             (a.fbias ? " +fbias" : "") + (a.tma_store ? "" : " direct");
+    name = c.prof_names.insert(full).first->c_str();
+  }
+  op_check(c, launch_tapgemm(ma, mb, mc, a, batch, c.stream), name, flops, bytes);
 }
 
 }  // namespace
@@ -152,15 +167,22 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   a.kchunks = cdiv(K, 64);
   a.n_total = N;
   fill_epi(a, e, c.fmt);
+  a.tma_store = can_tma_store(e);
   a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
   const int bn = a.bn_tile / a.ctas;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mc;
   unsigned long long dims[5] = {(unsigned long long)K, (unsigned long long)M, 1, 1, 1};
   unsigned long long st[4] = {(unsigned long long)ldx * 2, (unsigned long long)ldx * 2 * M,
                               (unsigned long long)ldx * 2 * M, (unsigned long long)ldx * 2 * M};
   make_a_map(&ma, x, c.fmt, dims, st, 128, 1, 1, 1);
   make_b_map(&mb, Wm, c.fmt, K, N, (unsigned long long)K * 2, bn);
-  launch(c, ma, mb, a, 1, e.geglu ? "tapgemm.linear_geglu" : "tapgemm.linear", K);
+  if (a.tma_store) {
+    const unsigned long long rb = (unsigned long long)e.ldc * 2;
+    unsigned long long od[5] = {(unsigned long long)(e.geglu ? N / 2 : N), (unsigned long long)M, 1, 1, 1};
+    unsigned long long os[4] = {rb, rb * M, rb * M, rb * M};
+    make_a_map(&mc, e.out, c.fmt, od, os, 128, 1, 1, 1);
+  }
+  launch(c, ma, mb, a, 1, e.geglu ? "tapgemm.linear_geglu" : "tapgemm.linear", K, a.tma_store ? &mc : nullptr);
 }
 
 void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* Wm, int Cout, int stride,
@@ -182,9 +204,17 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
   a.b_tap_rows = Cout;
   a.n_total = Cout;
   fill_epi(a, e, c.fmt);
+  a.tma_store = can_tma_store(e);
   a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
   const int bn = a.bn_tile / a.ctas;
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, mc;
+  if (a.tma_store) {
+    const unsigned long long rb = (unsigned long long)e.ldc * 2;
+    unsigned long long od[5] = {(unsigned long long)Cout, (unsigned long long)Wo, (unsigned long long)Ho,
+                                (unsigned long long)Nf, 1};
+    unsigned long long os[4] = {rb, rb * Wo, rb * Wo * Ho, rb * Wo * Ho * Nf};
+    make_a_map(&mc, e.out, c.fmt, od, os, a.bw, a.bh, a.bn, 1);
+  }
   const unsigned long long rowb = (unsigned long long)C * 2;
   if (stride == 1) {
     a.dim_x = 1; a.dim_y = 2; a.dim_n = 3;
@@ -219,7 +249,7 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
     make_a_map(&ma, x, c.fmt, dims, st, a.bw, 1, a.bh, a.bn);
   }
   make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)9 * Cout, rowb, bn);
-  launch(c, ma, mb, a, 1, "tapgemm.conv3x3", C);
+  launch(c, ma, mb, a, 1, "tapgemm.conv3x3", C, a.tma_store ? &mc : nullptr);
 }
 
 void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm, int Cout, int chunk,
@@ -252,14 +282,21 @@ void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm,
     if (e.blend) ec.blend = reinterpret_cast<const char*>(e.blend) + tok0 * e.ldb * 2;
     if (e.fbias) ec.fbias = e.fbias + (tok0 / ec.fbias_div) * e.fbias_ld;
     fill_epi(a, ec, c.fmt);
+    a.tma_store = can_tma_store(ec);
     a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
-  const int bn = a.bn_tile / a.ctas;
-    CUtensorMap ma, mb;
+    const int bn = a.bn_tile / a.ctas;
+    CUtensorMap ma, mb, mc;
+    if (a.tma_store) {
+      const unsigned long long rb = (unsigned long long)ec.ldc * 2;
+      unsigned long long od[5] = {(unsigned long long)Cout, (unsigned long long)P, (unsigned long long)Tc, 1, 1};
+      unsigned long long os[4] = {rb, rb * P, rb * P * Tc, rb * P * Tc};
+      make_a_map(&mc, ec.out, c.fmt, od, os, a.bw, a.bh, 1, 1);
+    }
     unsigned long long dims[5] = {(unsigned long long)C, (unsigned long long)P, (unsigned long long)Tc, 1, 1};
     unsigned long long st[4] = {rowb, rowb * P, rowb * P * Tc, rowb * P * Tc};
     make_a_map(&ma, reinterpret_cast<const char*>(x) + tok0 * rowb, c.fmt, dims, st, a.bw, a.bh, 1, 1);
     make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)3 * Cout, rowb, bn);
-    launch(c, ma, mb, a, 1, "tapgemm.tconv3", C);
+    launch(c, ma, mb, a, 1, "tapgemm.tconv3", C, a.tma_store ? &mc : nullptr);
   }
 }
 

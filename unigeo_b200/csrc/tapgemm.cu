@@ -23,18 +23,19 @@ constexpr int kThreads = 64 + kEpiWarps * 32;
 constexpr int kATileBytes = BM * BK * 2;
 constexpr int kBTileBytes = 256 * BK * 2;            // room for the widest N tile
 constexpr int kStageBytes = kATileBytes + kBTileBytes;
-constexpr int kStages = 4;
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kSlabBytes = 128 * 128;                // 128 rows x 64 16-bit columns of finished output
+constexpr int kStages = 3;
+constexpr int kSmemBytes = kStages * kStageBytes + 4 * kSlabBytes + 1024 /*align*/ + 256 /*barriers*/;
 // CTA-pair mode: each CTA stages 128 rows of A and at most 128 rows (half) of B
 constexpr int kStageBytes2 = kATileBytes + 128 * BK * 2;
-constexpr int kStages2 = 6;
-constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 1024 + 256;
+constexpr int kStages2 = 5;
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 4 * kSlabBytes + 1024 + 256;
 
 // exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below 16-bit output
 // resolution): 2 MUFU + ~12 FMA-pipe instructions instead of libm erff's ~30
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(t, 1.061405429f, -1.453152027f);
   p = fmaf(t, p, 1.421413741f);
   p = fmaf(t, p, -0.284496736f);
@@ -64,12 +65,12 @@ __device__ __forceinline__ void store16(void* base, long long idx, float v, int 
 //   f[]    accumulator values (already scaled / gated)
 //   col0   first column in OUTPUT column space; ncols_valid = how many of the NC exist
 template <int NC>
-__device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmArgs& a, long long pix,
-                                                 long long zoff, int col0, int bias_col0, int ncols_valid,
-                                                 bool row_ok) {
+__device__ __forceinline__ void finish_cols(float (&f)[NC], const TapGemmArgs& a, long long pix, long long fb_off,
+                                            int col0, int bias_col0, int ncols_valid, bool row_ok) {
   if (!row_ok || ncols_valid <= 0) return;
   const int fmt = a.fmt;
   const bool full = ncols_valid >= NC;
+  const bool vec_ok = full && ((col0 & 7) == 0);
   if (a.bias != nullptr && !a.geglu) {
     if (full && ((bias_col0 & 3) == 0)) {
 #pragma unroll
@@ -84,7 +85,7 @@ __device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmAr
     }
   }
   if (a.fbias != nullptr) {
-    const float* fb = a.fbias + (long long)(pix / a.fbias_div) * a.fbias_ld + col0;
+    const float* fb = a.fbias + fb_off + col0;        // fb_off = (pixel / fbias_div) * fbias_ld, once per tile
     if (full && ((col0 & 3) == 0) && ((a.fbias_ld & 3) == 0)) {
 #pragma unroll
       for (int j = 0; j < NC / 4; ++j) {
@@ -97,7 +98,6 @@ __device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmAr
         if (full || j < ncols_valid) f[j] += __ldg(fb + j);
     }
   }
-  const bool vec_ok = full && ((col0 & 7) == 0);
   if (a.res != nullptr) {
     const long long off = pix * a.ldr + col0;
     if (vec_ok && ((a.ldr & 7) == 0)) {
@@ -137,6 +137,15 @@ __device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmAr
         if (full || j < ncols_valid) f[j] = al * load16(a.blend, off + j, fmt) + be * f[j];
     }
   }
+}
+
+template <int NC>
+__device__ __forceinline__ void store_cols(const float (&f)[NC], const TapGemmArgs& a, long long pix,
+                                           long long zoff, int col0, int ncols_valid, bool row_ok) {
+  if (!row_ok || ncols_valid <= 0) return;
+  const int fmt = a.fmt;
+  const bool full = ncols_valid >= NC;
+  const bool vec_ok = full && ((col0 & 7) == 0);
   const long long ooff = zoff + pix * a.ldc + col0;
   if (a.out_fp32) {
     float* o = reinterpret_cast<float*>(a.out) + ooff;
@@ -169,6 +178,27 @@ __device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmAr
   }
 }
 
+template <int NC>
+__device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmArgs& a, long long pix,
+                                                 long long zoff, long long fb_off, int col0, int bias_col0,
+                                                 int ncols_valid, bool row_ok) {
+  finish_cols<NC>(f, a, pix, fb_off, col0, bias_col0, ncols_valid, row_ok);
+  store_cols<NC>(f, a, pix, zoff, col0, ncols_valid, row_ok);
+}
+
+// 32 finished columns of row r -> 64 bytes of the 128-byte-swizzled output slab (TMA-store staging)
+__device__ __forceinline__ void stage_cols32(const float (&f)[32], uint32_t slab, int r, int half, int fmt) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t c16 = (uint32_t)(half * 4 + j);
+    const uint32_t addr = slab + (uint32_t)r * 128u + ((c16 ^ (uint32_t)(r & 7)) << 4);
+    const uint32_t w0 = pack16x2(f[8 * j + 0], f[8 * j + 1], fmt), w1 = pack16x2(f[8 * j + 2], f[8 * j + 3], fmt);
+    const uint32_t w2 = pack16x2(f[8 * j + 4], f[8 * j + 5], fmt), w3 = pack16x2(f[8 * j + 6], f[8 * j + 7], fmt);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                 : "memory");
+  }
+}
+
 // Persistent kernel: one CTA per SM walks output tiles t, t + stride, ...  The three roles run ahead of
 // each other across tiles: the TMA ring never drains between tiles, and the accumulator is
 // double-buffered in TMEM (2 x 256 columns) so the MMAs of tile i+1 overlap the epilogue of tile i.
@@ -183,12 +213,14 @@ __device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmAr
 template <int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ TapGemmArgs a) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TapGemmArgs a) {
   constexpr int kSt = CTAS == 2 ? kStages2 : kStages;
   constexpr int kStB = CTAS == 2 ? kStageBytes2 : kStageBytes;
+  constexpr int G16 = 16 * CTAS;                     // granularity of the N extent of one UMMA
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kSt * kStB);
+  uint8_t* slabs = smem + kSt * kStB;                // 4 x 16 KB output staging (2 column groups x 2 buffers)
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + 4 * kSlabBytes);
   uint64_t* empty_bar = full_bar + kSt;
   uint64_t* tmem_full_bar = empty_bar + kSt;         // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
@@ -197,18 +229,23 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int rank = CTAS == 2 ? (int)cluster_ctarank() : 0;
-  const int BN = a.bn_tile;                          // full tile width (both CTAs see all BN columns)
-  const int BNL = BN / CTAS;                         // B rows staged by this CTA
+  const int BN = a.bn_tile;                          // tile width (the last N tile may be narrower)
   const int m_tiles = a.tiles_x * a.tiles_y * a.tiles_n;
   const int pm_tiles = (m_tiles + CTAS - 1) / CTAS;  // tiles along M per scheduling unit
   const int n_tiles = a.n_tiles;
   const int total_tiles = pm_tiles * n_tiles * a.batch;
   const int num_iters = a.num_taps * a.kchunks;
   const int unit0 = blockIdx.x / CTAS, unit_stride = gridDim.x / CTAS;
+  // N extent of the tile starting at column n0: ragged last tile, rounded up to the UMMA granularity
+  auto n_cur = [&](int n0) {
+    const int rem = (a.n_total - n0 + G16 - 1) / G16 * G16;
+    return rem < BN ? rem : BN;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (a.tma_store) tma_prefetch_desc(&tmC);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -240,7 +277,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===================== TMA producer =====================
     if (elect_one()) {
       const uint32_t tx_bytes = ((uint32_t)(a.bw * a.bh * a.bn) * (BK * 2) +
-                                 (uint32_t)(a.b_mn_major ? BK : BNL) * (BK * 2)) * CTAS;
+                                 (uint32_t)(a.b_mn_major ? BK : BN / CTAS) * (BK * 2)) * CTAS;
       int it_g = 0;   // ring position, continuous across tiles
       for (int t = unit0; t < total_tiles; t += unit_stride) {
         int m_tile = (t % pm_tiles) * CTAS + rank;
@@ -258,7 +295,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         base[a.dim_z1] += z1 * a.a_z1step;
         base[a.dim_z0] += z0 * a.a_z0step;
         const int bcol0 = a.b_c0 + z0 * a.b_z0_cstep;
-        const int brow0 = z1 * a.b_z1_rowstep + (a.b_mn_major ? 0 : n0 + rank * BNL);
+        // pair mode: this CTA stages the rank-th half of the tile's (possibly ragged) B rows
+        const int brow0 = z1 * a.b_z1_rowstep + (a.b_mn_major ? 0 : n0 + rank * (n_cur(n0) / CTAS));
         for (int it = 0; it < num_iters; ++it, ++it_g) {
           const int s = it_g % kSt;
           const uint32_t ph = (uint32_t)(it_g / kSt) & 1u;
@@ -288,10 +326,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== UMMA issuer (leader CTA only in pair mode) =====================
     if (rank == 0) {
-      const uint32_t idesc = make_idesc_f16(BM * CTAS, BN, a.fmt, a.b_mn_major);
       const uint32_t bstep = a.b_mn_major ? 128u : 2u;
       int it_g = 0, tl = 0;
       for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
+        const int n0 = ((t / pm_tiles) % n_tiles) * BN;
+        const uint32_t idesc = make_idesc_f16(BM * CTAS, n_cur(n0), a.fmt, a.b_mn_major);
         const int buf = tl & 1;
         const uint32_t use = (uint32_t)(tl >> 1);
         mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);     // epilogue(s) drained this accumulator
@@ -329,9 +368,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // ===================== epilogue (8 warps: 4 lane quarters x 2 column halves) =====================
+    // ===================== epilogue (8 warps: 4 lane quarters x 2 column groups) =====================
     const int q = warp & 3;                 // TMEM lane quarter this warp may read
-    const int hsel = (warp - 2) >> 2;       // which half of the 32-column chunks
+    const int hsel = (warp - 2) >> 2;       // column group
     const int r = q * 32 + lane;            // output row inside this CTA's 128-row tile
     const int xi = r % a.bw;
     const int yi = (r / a.bw) % a.bh;
@@ -344,12 +383,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else mbar_arrive(&tmem_empty_bar[buf]);
       }
     };
+    const bool issuer = (warp == 2 + 4 * hsel) && lane == 0;   // issues this group's TMA stores
+    const uint32_t slab_base = smem_u32(slabs + hsel * 2 * kSlabBytes);
+    int slab_it = 0;
     int tl = 0;
     for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
       int m_tile = (t % pm_tiles) * CTAS + rank;
       const int rest = t / pm_tiles;
       const int n_tile = rest % n_tiles;
       const int n0 = n_tile * BN;
+      const int Ncur = n_cur(n0);
       const int z = rest / n_tiles;
       const int z1 = z / a.zdiv, z0 = z - z1 * a.zdiv;
       const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
@@ -359,12 +402,74 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool row_ok = (ni < a.bn) && (x0 + xi < a.W) && (y0 + yi < a.H) && (nn0 + ni < a.N);
       const long long pix = ((long long)(nn0 + ni) * a.H + (y0 + yi)) * a.W + (x0 + xi);
       const long long zoff = (long long)z1 * a.out_z1stride + (long long)z0 * a.out_z0stride;
+      const long long fb_off = a.fbias ? (long long)((int)pix / a.fbias_div) * a.fbias_ld : 0;
       const int buf = tl & 1;
       mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 256u;
-      if (a.geglu) {
-        const int BNh = BN >> 1;
+      const int BNh = BN >> 1;              // GEGLU: [BNh value | BNh gate] accumulator columns
+
+      if (a.tma_store) {
+        // ---- coalesced path: finished 64-column slabs go through swizzled smem and a TMA tile store
+        const int out_w = a.geglu ? BNh : Ncur;               // output columns of this tile
+        const int out_c0 = a.geglu ? n_tile * BNh : n0;       // first output column
+        const int n_out = a.geglu ? a.n_total / 2 : a.n_total;
+        bool released = false;
+#pragma unroll 1
+        for (int sl = hsel; sl * 64 < out_w; sl += 2, ++slab_it) {
+          const uint32_t slab = slab_base + (uint32_t)(slab_it & 1) * kSlabBytes;
+          if (issuer) bulk_wait_group_read<1>();               // the store that last read this buffer is done
+          named_bar_sync(1 + hsel, 128);
+          const bool last_slab = (sl + 2) * 64 >= out_w;
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int c = sl * 64 + half * 32;
+            if (c >= out_w) break;
+            const bool last_ld = last_slab && (half == 1 || c + 32 >= out_w);
+            float f[32];
+            if (a.geglu) {
+              uint32_t v[32], g[32];
+              tmem_ld_32x32(trow + c, v);
+              tmem_ld_32x32(trow + BNh + c, g);
+              tmem_ld_wait();
+              if (last_ld) { release(buf); released = true; }
+              const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              const float4* bv = reinterpret_cast<const float4*>(a.bias + n0 + c);
+              const float4* bg = reinterpret_cast<const float4*>(a.bias + n0 + BNh + c);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 x = a.bias ? __ldg(bv + j) : zero4, y = a.bias ? __ldg(bg + j) : zero4;
+                f[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) + x.x) * gelu_erf(__uint_as_float(g[4 * j + 0]) + y.x);
+                f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + x.y) * gelu_erf(__uint_as_float(g[4 * j + 1]) + y.y);
+                f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + x.z) * gelu_erf(__uint_as_float(g[4 * j + 2]) + y.z);
+                f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + x.w) * gelu_erf(__uint_as_float(g[4 * j + 3]) + y.w);
+              }
+              finish_cols<32>(f, a, pix, fb_off, out_c0 + c, 0, n_out - (out_c0 + c), row_ok);
+            } else {
+              uint32_t v[32];
+              tmem_ld_32x32(trow + c, v);     // columns past Ncur are stale but never reach memory (map clips)
+              tmem_ld_wait();
+              if (last_ld) { release(buf); released = true; }
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+              if (a.scale != 1.0f) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] *= a.scale;
+              }
+              finish_cols<32>(f, a, pix, fb_off, out_c0 + c, out_c0 + c, n_out - (out_c0 + c), row_ok);
+            }
+            stage_cols32(f, slab, r, half, a.fmt);
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + hsel, 128);
+          if (issuer) {
+            tma_store_5d(&tmC, reinterpret_cast<const void*>(slabs + hsel * 2 * kSlabBytes + (slab_it & 1) * kSlabBytes),
+                         out_c0 + sl * 64, x0, y0, nn0, 0);
+            bulk_commit_group();
+          }
+        }
+        if (!released) release(buf);
+      } else if (a.geglu) {
         const int ocol_tile = n_tile * BNh;
 #pragma unroll 1
         for (int c = hsel * 32; c < BNh; c += 64) {
@@ -374,38 +479,25 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tmem_ld_wait();
           if (c + 64 >= BNh) release(buf);   // last chunk of this warp
           float f[32];
-          if (a.bias != nullptr && n0 + BN <= a.n_total) {     // whole tile in range: vector bias loads
-            const float4* bv = reinterpret_cast<const float4*>(a.bias + n0 + c);
-            const float4* bg = reinterpret_cast<const float4*>(a.bias + n0 + BNh + c);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 x = __ldg(bv + j), y = __ldg(bg + j);
-              f[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) + x.x) * gelu_erf(__uint_as_float(g[4 * j + 0]) + y.x);
-              f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + x.y) * gelu_erf(__uint_as_float(g[4 * j + 1]) + y.y);
-              f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + x.z) * gelu_erf(__uint_as_float(g[4 * j + 2]) + y.z);
-              f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + x.w) * gelu_erf(__uint_as_float(g[4 * j + 3]) + y.w);
+          for (int j = 0; j < 32; ++j) {
+            const int vc = n0 + c + j, gc = n0 + BNh + c + j;
+            float val = __uint_as_float(v[j]);
+            float gate = __uint_as_float(g[j]);
+            if (a.bias != nullptr) {
+              if (vc < a.n_total) val += __ldg(a.bias + vc);
+              if (gc < a.n_total) gate += __ldg(a.bias + gc);
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int vc = n0 + c + j, gc = n0 + BNh + c + j;
-              float val = __uint_as_float(v[j]);
-              float gate = __uint_as_float(g[j]);
-              if (a.bias != nullptr) {
-                if (vc < a.n_total) val += __ldg(a.bias + vc);
-                if (gc < a.n_total) gate += __ldg(a.bias + gc);
-              }
-              f[j] = val * gelu_erf(gate);
-            }
+            f[j] = val * gelu_erf(gate);
           }
-          finish_and_store<32>(f, a, pix, zoff, ocol_tile + c, 0, a.n_total / 2 - (ocol_tile + c), row_ok);
+          finish_and_store<32>(f, a, pix, zoff, fb_off, ocol_tile + c, 0, a.n_total / 2 - (ocol_tile + c), row_ok);
         }
       } else {
         bool released = false;
 #pragma unroll 1
-        for (int c = hsel * 32; c < BN; c += 64) {
-          const bool last = (c + 64 >= BN);
-          if (BN - c >= 32) {
+        for (int c = hsel * 32; c < Ncur; c += 64) {
+          const bool last = (c + 64 >= Ncur);
+          if (Ncur - c >= 32) {
             uint32_t v[32];
             tmem_ld_32x32(trow + c, v);
             tmem_ld_wait();
@@ -417,7 +509,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] *= a.scale;
             }
-            finish_and_store<32>(f, a, pix, zoff, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
+            finish_and_store<32>(f, a, pix, zoff, fb_off, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
           } else {
             uint32_t v[16];
             tmem_ld_32x16(trow + c, v);
@@ -426,12 +518,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
-            finish_and_store<16>(f, a, pix, zoff, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
+            finish_and_store<16>(f, a, pix, zoff, fb_off, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
           }
         }
-        if (!released) release(buf);         // this warp had no chunk in this tile (narrow BN)
+        if (!released) release(buf);         // this warp had no chunk in this tile (narrow tile)
       }
     }
+    if (issuer && a.tma_store) bulk_wait_group<0>();            // all tile stores have landed
   }
   tc_fence_before();
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
@@ -508,7 +601,8 @@ int tapgemm_pick_tile(const TapGemmArgs& a, int batch, int* ctas_out) {
   for (int ctas = 1; ctas <= 2; ++ctas) {
     if (force && ctas != force) continue;
     if (ctas == 2 && (m_tiles < 2 || (sms & 1))) continue;
-    for (int bn = 256; bn >= 16 * ctas; bn -= 16 * ctas) {
+    const int step = a.tma_store ? 64 : 16 * ctas;   // TMA-store slabs are 64 columns wide
+    for (int bn = 256; bn >= step; bn -= step) {
       if (a.geglu && bn != 256) continue;      // [128 value | 128 gate] column tiles
       const long long units = ((m_tiles + ctas - 1) / ctas) * ((a.n_total + bn - 1) / bn) * batch;
       const long long slots = sms / ctas;
@@ -530,8 +624,8 @@ int tapgemm_pick_bn(const TapGemmArgs& a, int batch) {
   return tapgemm_pick_tile(a, batch, &ctas);
 }
 
-int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args_in, int batch,
-                   cudaStream_t stream) {
+int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC,
+                   const TapGemmArgs& args_in, int batch, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -544,6 +638,10 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemm
   const int ctas = args.ctas == 2 ? 2 : 1;
   if (args.bn_tile <= 0 || args.bn_tile > 256 || (args.bn_tile & (16 * ctas - 1))) return (int)cudaErrorInvalidValue;
   if (ctas == 2 && args.b_mn_major) return (int)cudaErrorInvalidValue;
+  if (args.tma_store && (tmC == nullptr || (args.bn_tile & 63) || batch != 1 || args.out_fp32))
+    return (int)cudaErrorInvalidValue;
+  if (args.geglu && (args.bn_tile != 256 || (args.n_total & 255))) return (int)cudaErrorInvalidValue;
+  const CUtensorMap& mc = tmC ? *tmC : tmA;
   args.batch = batch;
   args.n_tiles = (args.n_total + args.bn_tile - 1) / args.bn_tile;
   const long long m_tiles = (long long)args.tiles_x * args.tiles_y * args.tiles_n;
@@ -552,7 +650,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemm
   const int sms = tapgemm_num_sms();
   if (ctas == 1) {
     const int grid = (int)(units < sms ? units : sms);
-    tapgemm_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, args);
+    tapgemm_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, mc, args);
     return (int)cudaGetLastError();
   }
   const long long slots = sms / 2;
@@ -568,7 +666,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemm
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return (int)cudaLaunchKernelEx(&cfg, tapgemm_kernel<2>, tmA, tmB, args);
+  return (int)cudaLaunchKernelEx(&cfg, tapgemm_kernel<2>, tmA, tmB, mc, args);
 }
 
 }  // namespace ug

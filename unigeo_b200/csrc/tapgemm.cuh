@@ -44,6 +44,8 @@ struct TapGemmArgs {
   int n_total;             // valid output columns (before GEGLU halving)
   int bn_tile;             // N extent of one tile: multiple of 16 * ctas, <= 256 (tapgemm_pick_tile)
   int ctas;                // 1: 128 x BN tile per CTA; 2: 256 x BN tile per CTA pair (cta_group::2)
+  int tma_store;           // finished 64-column slabs leave through smem + TMA tile stores (coalesced);
+                           // needs a 16-bit output, ldc % 8 == 0, batch 1 and the output tensor map
   int n_tiles, batch;      // filled by launch_tapgemm
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
   int out_fp32;
@@ -77,8 +79,8 @@ int encode_tmap(CUtensorMap* out, const TmapDesc& d);
 
 // Launch (persistent, one CTA per SM); args.bn_tile must be set (tapgemm_pick_bn) and must equal the
 // row extent of the B tensor map's box.  Returns cudaError_t as int.
-int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const TapGemmArgs& args, int batch,
-                   cudaStream_t stream);
+int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC,
+                   const TapGemmArgs& args, int batch, cudaStream_t stream);
 
 // needs tiles_*, n_total, geglu, b_mn_major filled in; returns bn_tile and the CTA count per tile.
 // The B tensor map's box must have bn_tile / ctas rows.

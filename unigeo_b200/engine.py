@@ -144,10 +144,10 @@ class Engine:
     def launch_count(self, reset: bool = False) -> int:
         return int(self.lib.ug_ctx_launch_count(self._ctx, 1 if reset else 0))
 
-    def profile(self, enable: bool) -> None:
-        _lib.check(self.lib.ug_ctx_profile(self._ctx, 1 if enable else 0))
+    def profile(self, enable, by_shape: bool = False) -> None:
+        _lib.check(self.lib.ug_ctx_profile(self._ctx, (2 if by_shape else 1) if enable else 0))
 
-    def profile_read(self, cap: int = 64):
+    def profile_read(self, cap: int = 512):
         """[{name, launches, ms, flops, bytes}] aggregated over the launches since profile(True)."""
         names = C.create_string_buffer(64 * cap)
         cnt = (C.c_longlong * cap)()
