@@ -94,6 +94,7 @@ struct Ctx {
   UNetModel* unet = nullptr;
   VaeModel* vae = nullptr;
   bool finalized = false;
+  unsigned int* gn_counters = nullptr;   // "last CTA" tickets of the fused GroupNorm finalize
   bool attn_materialized = false; // true: head_dim-64 attention through QK^T / softmax / PV GEMMs (A/B debug)
   // prepared clip shape
   int T = 0, h = 0, w = 0;

@@ -2,9 +2,10 @@
 //   CTA = one 128-query tile of one (frame, head); 192 threads:
 //     warp 0     TMA producer: Q once, then K_j / V_j blocks of 128 keys through 2-deep rings
 //     warp 1     TMEM owner + UMMA issuer:  S = Q K_j^T (128x128x64)  and  O += P_j V_j (128x64x128)
-//     warps 2-5  softmax: thread = query row; S read with tcgen05.ld, online max / exp2 / sum in
-//                registers, P_j written to smem as the 16-bit K-major A operand of the P.V MMA,
-//                O rescaled in TMEM (tcgen05.ld / st) when the running max moves
+//     warps 2-5  softmax: thread = query row; S read ONCE per block with tcgen05.ld (TMEM read bandwidth,
+//                64 B/clk, is the binding resource), exp2 against a lazily updated reference maximum,
+//                P_j written to smem as the 16-bit K-major A operand of the P.V MMA, O rescaled in TMEM
+//                (tcgen05.ld / st) only when a row maximum jumps by more than 2^8
 //   TMEM: S at columns [0,128), O at [128,192).  smem: Q 16K | K 2x16K | V 2x16K | P 32K = 112 KB, so
 //   two CTAs share an SM: one CTA's exp2 phase (MUFU bound) overlaps the other's MMAs.
 //   V is consumed in place as an MN-major B operand (no transpose anywhere).
@@ -130,31 +131,16 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t sP = smem_u32(smem + kOffP);
     const float sc = a.scale_log2;
-    float m = -INFINITY, l = 0.f;
-    for (int j = 0; j < nb; ++j) {
-      mbar_wait(s_full, (uint32_t)j & 1u);
-      tc_fence_after();
-      const int valid = min(128, a.N - j * 128);        // keys of this block that exist
-      // ---- pass 1: row max
-      float mx = m;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + kColS + c * 32, v);
-        tmem_ld_wait();
-        if (valid == 128) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]) * sc);
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]) * sc);
-        }
-      }
-      const float alpha = ex2_approx(m - mx);           // m = -inf on the first block -> 0
-      // ---- pass 2: p = 2^(s*scale - max), packed to 16 bit
-      uint32_t pk[64];
-      float rowsum = 0.f;
+    // Online softmax with a LAZY reference maximum: p = 2^(s*scale - m_ref) where m_ref is the row maximum
+    // known from earlier blocks.  As long as no row of the warp exceeds m_ref by more than 8 (p <= 256,
+    // exact in 16 bit) the block needs ONE pass over S in TMEM and no rescale of O; only when a row jumps
+    // past the threshold (and on the first block) the warp takes the exact two-pass route and rescales.
+    // O / l at the end is independent of the reference, so results match the exact formulation.
+    float m_ref = -INFINITY, l = 0.f;
+    uint32_t pk[64];
+    auto compute_p = [&](float mref, int valid, float& rowsum, float& pmax) {
+      rowsum = 0.f;
+      pmax = 0.f;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
@@ -162,18 +148,53 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -mx));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -mx));
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -mref));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -mref));
           if (valid != 128) {
             if (c * 32 + i >= valid) p0 = 0.f;
             if (c * 32 + i + 1 >= valid) p1 = 0.f;
           }
           rowsum += p0 + p1;
+          pmax = fmaxf(pmax, fmaxf(p0, p1));
           pk[c * 16 + (i >> 1)] = a.fmt ? Elem<__nv_bfloat16>::pack2(p0, p1) : Elem<__half>::pack2(p0, p1);
         }
       }
-      l = l * alpha + rowsum;
-      m = mx;
+    };
+    for (int j = 0; j < nb; ++j) {
+      mbar_wait(s_full, (uint32_t)j & 1u);
+      tc_fence_after();
+      const int valid = min(128, a.N - j * 128);        // keys of this block that exist
+      float rowsum, pmax, alpha = 1.0f;
+      bool exact = (j == 0);
+      if (!exact) {
+        compute_p(m_ref, valid, rowsum, pmax);
+        exact = __any_sync(0xffffffffu, !(pmax <= 256.0f));   // also catches inf / nan
+      }
+      if (exact) {
+        // ---- exact route: row max of this block first, then p against the updated reference
+        float mraw = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_addr + kColS + c * 32, v);
+          tmem_ld_wait();
+          if (valid == 128) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) mraw = fmaxf(mraw, __uint_as_float(v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c * 32 + i < valid) mraw = fmaxf(mraw, __uint_as_float(v[i]));
+          }
+        }
+        const float mx = fmaxf(m_ref, mraw * sc);        // sc > 0
+        alpha = ex2_approx(m_ref - mx);                   // m_ref = -inf on the first block -> 0
+        m_ref = mx;
+        compute_p(m_ref, valid, rowsum, pmax);
+        l = l * alpha + rowsum;
+      } else {
+        l += rowsum;
+      }
       if (j > 0) {                                       // P buffer and O are busy until P_{j-1}.V is done
         mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
         tc_fence_after();
@@ -187,8 +208,8 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
                      "r"(pk[c16 * 4 + 1]), "r"(pk[c16 * 4 + 2]), "r"(pk[c16 * 4 + 3])
                      : "memory");
       }
-      // ---- O *= alpha
-      if (j > 0) {
+      // ---- O *= alpha (only on the exact route; warp-uniform)
+      if (exact && j > 0) {
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           uint32_t o[32];

@@ -46,8 +46,10 @@ __device__ __forceinline__ const uint4* cat_ptr(const void* x1, int nv1, const v
 template <typename T>
 __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
                                 long long rows_per_set, long long chunk_rows, int G, int cs,
-                                float* __restrict__ part) {
+                                float* __restrict__ part, float* __restrict__ mr, unsigned int* __restrict__ counters,
+                                float inv_cnt, float eps) {
   extern __shared__ float s_part[];   // [rpb][C] sums, then [rpb][C] sumsq
+  __shared__ int s_last;
   const int nvec = nv1 + nv2;
   const int C = nvec * 8;
   const int rpb = blockDim.x / nvec;
@@ -85,6 +87,40 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void
     float* o = part + ((set * gridDim.x + blockIdx.x) * G + g) * 2;
     o[0] = sa;
     o[1] = sq;
+  }
+  // ---- the last CTA of this set folds the partials into (mean, rstd): fixed summation order, so
+  // the result does not depend on which CTA happens to be last
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int ticket = atomicAdd(&counters[set], 1u);
+    s_last = (ticket == gridDim.x - 1);
+    if (s_last) counters[set] = 0u;          // ready for the next GroupNorm on this stream
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int slices = blockDim.x / G;         // >= 2
+  const int g = threadIdx.x % G, k = threadIdx.x / G;
+  float* red = s_part;                       // reuse: [slices][G][2]
+  if (k < slices) {
+    float sa = 0.f, sq = 0.f;
+    for (int ch = k; ch < (int)gridDim.x; ch += slices) {
+      const volatile float* o = part + ((set * gridDim.x + ch) * G + g) * 2;
+      sa += o[0];
+      sq += o[1];
+    }
+    red[(k * G + g) * 2 + 0] = sa;
+    red[(k * G + g) * 2 + 1] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    float a = 0.f, q = 0.f;
+    for (int i = 0; i < slices; ++i) { a += red[(i * G + g) * 2]; q += red[(i * G + g) * 2 + 1]; }
+    const float mean = a * inv_cnt;
+    const float var = fmaxf(q * inv_cnt - mean * mean, 0.f);
+    mr[(set * G + g) * 2 + 0] = mean;
+    mr[(set * G + g) * 2 + 1] = rsqrtf(var + eps);
   }
 }
 
@@ -318,88 +354,151 @@ __global__ void softmax_rows_kernel(void* __restrict__ s, long long rows, int n,
 }
 
 // ------------------------------------------------------------------ temporal attention
-// one warp per (pixel, head); lane j owns query frame j (and j+32 when T > 32)
-template <typename T, int TMAX>
-__global__ void temporal_attn_kernel(const void* __restrict__ qkv, void* __restrict__ out, int Tn, long long P,
-                                     int C, float scale_log2e) {
-  extern __shared__ __align__(16) uint32_t sm_kv[];
+// One warp per (pixel, head): Q, K, V of its T <= 64 frames (64 dims) are staged in XOR-swizzled smem
+// with cp.async, S = Q K^T and O = P V run on mma.sync m16n8k16 (fp32 accumulate) 16 queries at a
+// time, softmax stays in the accumulator registers.  The problem is HBM bound (12 flop/byte): the
+// tensor-core path only exists to get the arithmetic out of the way of the loads.
+template <typename T> struct MmaK16;
+template <> struct MmaK16<__half> {
+  __device__ static __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+};
+template <> struct MmaK16<__nv_bfloat16> {
+  __device__ static __forceinline__ void mma(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+};
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// byte offset of 16-byte chunk `c` (0..7) of row `row` in a [rows][128 B] tile, XOR swizzled
+__device__ __forceinline__ uint32_t swz(int row, int c) { return (uint32_t)row * 128u + (uint32_t)((c ^ (row & 7)) << 4); }
+
+template <typename T, int TPAD>
+__global__ void __launch_bounds__(128)
+temporal_attn_kernel(const void* __restrict__ qkv, void* __restrict__ out, int Tn, long long P, int C,
+                     float scale_log2e) {
+  extern __shared__ __align__(128) uint8_t sm_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int heads = C >> 6;
   const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + warp;
   if (item >= P * heads) return;
   const long long p = item / heads;
   const int h = (int)(item % heads);
-  uint32_t* Ks = sm_kv + (size_t)warp * Tn * 64;       // [T][32] packed pairs
-  uint32_t* Vs = Ks + (size_t)Tn * 32;
-  const uint32_t* base = reinterpret_cast<const uint32_t*>(qkv);
-  const long long row_words = (long long)3 * C / 2;
-  for (int i = 0; i < Tn; ++i) {
-    const long long tok = (long long)i * P + p;
-    Ks[i * 32 + lane] = __ldg(base + tok * row_words + (C + h * 64) / 2 + lane);
-    Vs[i * 32 + lane] = __ldg(base + tok * row_words + (2 * C + h * 64) / 2 + lane);
+  uint8_t* sq = sm_raw + (size_t)warp * 3 * TPAD * 128;
+  const uint32_t aQ = smem_u32(sq), aK = aQ + TPAD * 128, aV = aK + TPAD * 128;
+  const uint16_t* base = reinterpret_cast<const uint16_t*>(qkv);
+  const long long row_elems = (long long)3 * C;
+
+  // ---- stage Q | K | V rows (16-byte chunks), zero the padding rows
+  for (int i = lane; i < 3 * TPAD * 8; i += 32) {
+    const int c = i & 7, row = (i >> 3) % TPAD, which = i / (8 * TPAD);
+    const uint32_t dst = aQ + (uint32_t)which * TPAD * 128 + swz(row, c);
+    if (row < Tn) {
+      const uint16_t* src = base + ((long long)row * P + p) * row_elems + which * C + h * 64 + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncwarp();
+
+  constexpr int NT = TPAD / 8;                      // key tiles of 8
+  const int qr = lane >> 2, qc = (lane & 3) * 2;    // accumulator row / column pair of this lane
+#pragma unroll 1
+  for (int mt = 0; mt * 16 < Tn; ++mt) {
+    float sacc[NT][4];
+#pragma unroll
+    for (int n = 0; n < NT; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {                 // 16 dims per step
+      uint32_t af[4];
+      ldsm_x4(aQ + swz(mt * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)), af);
+#pragma unroll
+      for (int np = 0; np < NT / 2; ++np) {          // two key tiles per ldmatrix.x4
+        uint32_t bf[4];
+        ldsm_x4(aK + swz(np * 16 + (lane & 7) + (lane >> 4) * 8, ks * 2 + ((lane >> 3) & 1)), bf);
+        MmaK16<T>::mma(sacc[2 * np], af, bf[0], bf[1]);
+        MmaK16<T>::mma(sacc[2 * np + 1], af, bf[2], bf[3]);
+      }
+    }
+    // ---- softmax over keys (rows qr and qr + 8 of this 16-query tile)
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = n * 8 + qc + e < Tn;
+        sacc[n][e] = ok ? sacc[n][e] * scale_log2e : -INFINITY;
+        sacc[n][2 + e] = ok ? sacc[n][2 + e] * scale_log2e : -INFINITY;
+        m0 = fmaxf(m0, sacc[n][e]);
+        m1 = fmaxf(m1, sacc[n][2 + e]);
+      }
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        sacc[n][e] = exp2f(sacc[n][e] - m0); s0 += sacc[n][e];
+        sacc[n][2 + e] = exp2f(sacc[n][2 + e] - m1); s1 += sacc[n][2 + e];
+      }
+    }
+    s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+    const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+    // ---- O = P V ; probabilities are normalised, then rounded to the storage type (A operand)
+    float oacc[8][4];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < TPAD / 16; ++kk) {         // 16 keys per step
+      uint32_t pf[4];
+      pf[0] = Elem<T>::pack2(sacc[2 * kk][0] * i0, sacc[2 * kk][1] * i0);
+      pf[1] = Elem<T>::pack2(sacc[2 * kk][2] * i1, sacc[2 * kk][3] * i1);
+      pf[2] = Elem<T>::pack2(sacc[2 * kk + 1][0] * i0, sacc[2 * kk + 1][1] * i0);
+      pf[3] = Elem<T>::pack2(sacc[2 * kk + 1][2] * i1, sacc[2 * kk + 1][3] * i1);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {               // two dim tiles (16 dims) per ldmatrix.x4.trans
+        uint32_t vf[4];
+        ldsm_x4_trans(aV + swz(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 2 + (lane >> 4)), vf);
+        MmaK16<T>::mma(oacc[2 * np], pf, vf[0], vf[1]);
+        MmaK16<T>::mma(oacc[2 * np + 1], pf, vf[2], vf[3]);
+      }
+    }
+    // ---- park the 16 x 64 output tile over this tile's (consumed) Q rows
+    __syncwarp();
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      const uint32_t w0 = Elem<T>::pack2(oacc[n][0], oacc[n][1]), w1 = Elem<T>::pack2(oacc[n][2], oacc[n][3]);
+      const uint32_t a0 = aQ + swz(mt * 16 + qr, n) + qc * 2, a1 = aQ + swz(mt * 16 + qr + 8, n) + qc * 2;
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0), "r"(w0) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1), "r"(w1) : "memory");
+    }
   }
   __syncwarp();
-  for (int j = lane; j < Tn; j += 32) {
-    const long long tok = (long long)j * P + p;
-    const uint4* qp = reinterpret_cast<const uint4*>(base + tok * row_words + (h * 64) / 2);
-    float q[64];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float f[8];
-      unpack8<T>(__ldg(qp + k), f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) q[k * 8 + e] = f[e] * scale_log2e;
-    }
-    float sc[TMAX];
-    float m = -INFINITY;
-    const uint4* K4 = reinterpret_cast<const uint4*>(Ks);    // [T][8] x 16 B: one LDS.128 broadcast = 8 dims
-    const uint4* V4 = reinterpret_cast<const uint4*>(Vs);
-#pragma unroll
-    for (int i = 0; i < TMAX; ++i) {
-      if (i < Tn) {
-        float acc = 0.f;
-#pragma unroll
-        for (int d8 = 0; d8 < 8; ++d8) {
-          float kk[8];
-          unpack8<T>(K4[i * 8 + d8], kk);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) acc = fmaf(q[d8 * 8 + e], kk[e], acc);
-        }
-        sc[i] = acc;
-        m = fmaxf(m, acc);
-      }
-    }
-    float sum = 0.f;
-#pragma unroll
-    for (int i = 0; i < TMAX; ++i) {
-      if (i < Tn) { sc[i] = exp2f(sc[i] - m); sum += sc[i]; }
-    }
-    const float inv = 1.0f / sum;
-    float o[64];
-#pragma unroll
-    for (int d = 0; d < 64; ++d) o[d] = 0.f;
-#pragma unroll
-    for (int i = 0; i < TMAX; ++i) {
-      if (i < Tn) {
-        // probabilities are rounded to the storage type before P*V, like the 16-bit reference path
-        const float pw = Elem<T>::to_f(Elem<T>::from_f(sc[i] * inv));
-#pragma unroll
-        for (int d8 = 0; d8 < 8; ++d8) {
-          float vv[8];
-          unpack8<T>(V4[i * 8 + d8], vv);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) o[d8 * 8 + e] = fmaf(pw, vv[e], o[d8 * 8 + e]);
-        }
-      }
-    }
-    uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(out) + tok * C + h * 64);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float f[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) f[e] = o[k * 8 + e];
-      op[k] = pack8<T>(f);
-    }
+  // ---- coalesced 16-byte stores of the T output rows
+  uint16_t* ob = reinterpret_cast<uint16_t*>(out);
+  for (int i = lane; i < Tn * 8; i += 32) {
+    const int c = i & 7, row = i >> 3;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(aQ + swz(row, c)));
+    *reinterpret_cast<uint4*>(ob + ((long long)row * P + p) * C + h * 64 + c * 8) = v;
   }
 }
 
@@ -608,16 +707,22 @@ long long gn_partial_floats(int C, long long rows, long long rows_per_set, int G
 }
 
 int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
-                    int G, float* stats, int fmt, cudaStream_t st) {
+                    int G, float eps, float* stats, unsigned int* counters, int fmt, cudaStream_t st) {
   const int C = C1 + C2;
   if ((C1 & 7) || (C2 & 7) || C % G || G > 64 || C / 8 > 512) return (int)cudaErrorInvalidValue;
   const long long sets = rows / rows_per_set;
   GnGeom g = gn_geom(C / 8, rows_per_set, sets);
   dim3 grid(g.chunks, (unsigned)sets);
   const int rpb = g.threads / (C / 8);
-  const size_t smem = (size_t)2 * rpb * C * sizeof(float);
+  size_t smem = (size_t)2 * rpb * C * sizeof(float);
+  const size_t smem_fin = (size_t)(g.threads / G) * G * 2 * sizeof(float);
+  if (smem < smem_fin) smem = smem_fin;
+  if (sets > kGnMaxSets || g.threads < 2 * G) return (int)cudaErrorInvalidValue;
+  float* mr = stats + sets * g.chunks * G * 2;
+  const float inv_cnt = 1.0f / ((float)rows_per_set * (float)(C / G));
   UG_DISPATCH_FMT(fmt, (gn_stats_kernel<T><<<grid, g.threads, smem, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
-                                                                           g.chunk_rows, G, C / G, stats)));
+                                                                           g.chunk_rows, G, C / G, stats, mr, counters,
+                                                                           inv_cnt, eps)));
   return last_err();
 }
 
@@ -694,14 +799,12 @@ int launch_temporal_attention(const void* qkv, void* out, int Tn, long long P, i
   const int wpb = 4;
   const long long items = P * (C / 64);
   const unsigned grid = (unsigned)((items + wpb - 1) / wpb);
-  const size_t smem = (size_t)wpb * Tn * 64 * sizeof(uint32_t);
   const float sl = scale * 1.4426950408889634f;
   if (Tn <= 32) {
-    UG_DISPATCH_FMT(fmt, {
-      cudaFuncSetAttribute(temporal_attn_kernel<T, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      temporal_attn_kernel<T, 32><<<grid, wpb * 32, smem, st>>>(qkv, out, Tn, P, C, sl);
-    });
+    const size_t smem = (size_t)wpb * 3 * 32 * 128;
+    UG_DISPATCH_FMT(fmt, (temporal_attn_kernel<T, 32><<<grid, wpb * 32, smem, st>>>(qkv, out, Tn, P, C, sl)));
   } else {
+    const size_t smem = (size_t)wpb * 3 * 64 * 128;
     UG_DISPATCH_FMT(fmt, {
       cudaFuncSetAttribute(temporal_attn_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       temporal_attn_kernel<T, 64><<<grid, wpb * 32, smem, st>>>(qkv, out, Tn, P, C, sl);

@@ -14,8 +14,11 @@ namespace ug {
 // stats: per-CTA partial (sum, sumsq) pairs, gn_partial_floats(...) floats; no zeroing needed,
 // no atomics: the result is bit-identical from run to run.
 long long gn_partial_floats(int C, long long rows, long long rows_per_set, int G);
+// The last CTA of every set also folds the partials into (mean, rstd) (stored behind the partials);
+// `counters` = kGnMaxSets zero-initialised uints owned by the caller (left zero again on exit).
+constexpr int kGnMaxSets = 1024;
 int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
-                    int G, float* stats, int fmt, cudaStream_t st);
+                    int G, float eps, float* stats, unsigned int* counters, int fmt, cudaStream_t st);
 // folds the partials into (mean, rstd) per (set, group), stored behind the partials in `stats`
 int launch_gn_finalize(int C, long long rows, long long rows_per_set, int G, float eps, float* stats,
                        cudaStream_t st);

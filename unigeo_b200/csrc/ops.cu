@@ -399,9 +399,12 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
   (void)sets;
   float* stats = c.allocf(gn_partial_floats(C1 + C2, rows, rows_per_set, G));
   if (!c.dry) {
-    op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, stats, c.fmt, c.stream), "gn_stats", 0.0,
-             2.0 * rows * (C1 + C2));
-    op_check(c, launch_gn_finalize(C1 + C2, rows, rows_per_set, G, eps, stats, c.stream), "gn_finalize");
+    if (!c.gn_counters) {
+      c.gn_counters = reinterpret_cast<unsigned int*>(c.dmalloc(kGnMaxSets * sizeof(unsigned int)));
+      UG_CUDA(cudaMemset(c.gn_counters, 0, kGnMaxSets * sizeof(unsigned int)));
+    }
+    op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, eps, stats, c.gn_counters, c.fmt, c.stream),
+             "gn_stats", 0.0, 2.0 * rows * (C1 + C2));
     op_check(c, launch_gn_apply(x1, C1, x2, C2, rows, rows_per_set, G, stats, gamma, beta, eps, silu, y, c.fmt,
                                 c.stream),
              "gn_apply", 0.0, 4.0 * rows * (C1 + C2));
