@@ -102,7 +102,7 @@ def cpu_unet_sample(a, steps, warmup):
     from unigeo_b200.config import get_config
     from unigeo_b200.weights import synthetic_state_dict, unet_param_shapes
     cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
+    torch.set_num_threads(cores)          # torchrun pins OMP_NUM_THREADS=1; the CPU arm uses every core
     cfg = get_config(a.config)
     Ts = max(1, min(a.cpu_sample_frames, a.frames))
     h, w = a.height // 8, a.width // 8
@@ -165,9 +165,9 @@ def run_b200(a):
     cfg = get_config(a.config)
     T, h, w = a.frames, a.height // 8, a.width // 8
     eng = Engine(cfg, dtype=a.dtype, device=local)
-    # weights are generated in 16 bit chunk by chunk to keep host memory flat
-    eng.load_state_dict("unet", synthetic_state_dict(unet_param_shapes(cfg.unet), 1000, torch.float16))
-    eng.load_state_dict("vae", synthetic_state_dict(vae_param_shapes(cfg.vae), 2000, torch.float16))
+    # seeded random-init weights drawn directly on the device (values are irrelevant to the timing)
+    eng.load_state_dict("unet", synthetic_state_dict(unet_param_shapes(cfg.unet), 1000, torch.float16, eng.device))
+    eng.load_state_dict("vae", synthetic_state_dict(vae_param_shapes(cfg.vae), 2000, torch.float16, eng.device))
     eng.finalize()
     eng.prepare(T, h, w)
     dev = eng.device

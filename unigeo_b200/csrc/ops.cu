@@ -167,6 +167,7 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   a.kchunks = cdiv(K, 64);
   a.n_total = N;
   fill_epi(a, e, c.fmt);
+  a.fbias_uniform = (e.fbias != nullptr && (a.fbias_div % 128) == 0) ? 1 : 0;   // tiles = 128 consecutive tokens
   a.tma_store = can_tma_store(e);
   a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
   const int bn = a.bn_tile / a.ctas;

@@ -25,11 +25,11 @@ constexpr int kBTileBytes = 256 * BK * 2;            // room for the widest N ti
 constexpr int kStageBytes = kATileBytes + kBTileBytes;
 constexpr int kSlabBytes = 128 * 128;                // 128 rows x 64 16-bit columns of finished output
 constexpr int kStages = 3;
-constexpr int kSmemBytes = kStages * kStageBytes + 4 * kSlabBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int kSmemBytes = kStages * kStageBytes + 4 * kSlabBytes + 256 /*barriers*/ + 2048 /*bias*/;
 // CTA-pair mode: each CTA stages 128 rows of A and at most 128 rows (half) of B
 constexpr int kStageBytes2 = kATileBytes + 128 * BK * 2;
 constexpr int kStages2 = 5;
-constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 4 * kSlabBytes + 1024 + 256;
+constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 4 * kSlabBytes + 256 + 2048;
 
 // exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below 16-bit output
 // resolution): 2 MUFU + ~12 FMA-pipe instructions instead of libm erff's ~30
@@ -64,27 +64,21 @@ __device__ __forceinline__ void store16(void* base, long long idx, float v, int 
 // Finishes NC (16 or 32) consecutive output columns of one row and stores them.
 //   f[]    accumulator values (already scaled / gated)
 //   col0   first column in OUTPUT column space; ncols_valid = how many of the NC exist
-template <int NC>
+template <int NC, bool AUX = true>
 __device__ __forceinline__ void finish_cols(float (&f)[NC], const TapGemmArgs& a, long long pix, long long fb_off,
-                                            int col0, int bias_col0, int ncols_valid, bool row_ok) {
+                                            int col0, const float* sb, int ncols_valid, bool row_ok) {
   if (!row_ok || ncols_valid <= 0) return;
   const int fmt = a.fmt;
   const bool full = ncols_valid >= NC;
   const bool vec_ok = full && ((col0 & 7) == 0);
-  if (a.bias != nullptr && !a.geglu) {
-    if (full && ((bias_col0 & 3) == 0)) {
+  if (sb != nullptr) {     // per-tile bias (+ frame bias when uniform over the tile), staged in smem
 #pragma unroll
-      for (int j = 0; j < NC / 4; ++j) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + bias_col0) + j);
-        f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
-      }
-    } else {
-#pragma unroll
-      for (int j = 0; j < NC; ++j)
-        if (full || j < ncols_valid) f[j] += __ldg(a.bias + bias_col0 + j);
+    for (int j = 0; j < NC / 4; ++j) {
+      const float4 b = reinterpret_cast<const float4*>(sb)[j];
+      f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
     }
   }
-  if (a.fbias != nullptr) {
+  if (a.fbias != nullptr && !a.fbias_uniform) {
     const float* fb = a.fbias + fb_off + col0;        // fb_off = (pixel / fbias_div) * fbias_ld, once per tile
     if (full && ((col0 & 3) == 0) && ((a.fbias_ld & 3) == 0)) {
 #pragma unroll
@@ -98,6 +92,7 @@ __device__ __forceinline__ void finish_cols(float (&f)[NC], const TapGemmArgs& a
         if (full || j < ncols_valid) f[j] += __ldg(fb + j);
     }
   }
+  if (!AUX) return;      // residual / blend handled by the caller (prefetched)
   if (a.res != nullptr) {
     const long long off = pix * a.ldr + col0;
     if (vec_ok && ((a.ldr & 7) == 0)) {
@@ -180,9 +175,9 @@ __device__ __forceinline__ void store_cols(const float (&f)[NC], const TapGemmAr
 
 template <int NC>
 __device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmArgs& a, long long pix,
-                                                 long long zoff, long long fb_off, int col0, int bias_col0,
+                                                 long long zoff, long long fb_off, int col0, const float* sb,
                                                  int ncols_valid, bool row_ok) {
-  finish_cols<NC>(f, a, pix, fb_off, col0, bias_col0, ncols_valid, row_ok);
+  finish_cols<NC>(f, a, pix, fb_off, col0, sb, ncols_valid, row_ok);
   store_cols<NC>(f, a, pix, zoff, col0, ncols_valid, row_ok);
 }
 
@@ -217,14 +212,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   constexpr int kSt = CTAS == 2 ? kStages2 : kStages;
   constexpr int kStB = CTAS == 2 ? kStageBytes2 : kStageBytes;
   constexpr int G16 = 16 * CTAS;                     // granularity of the N extent of one UMMA
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // no static smem in this kernel: the dynamic window starts
+  if ((smem_u32(smem) & 1023u) != 0u) __trap();      // 1024-aligned (SWIZZLE_128B tiles need it); checked, not assumed
   uint8_t* slabs = smem + kSt * kStB;                // 4 x 16 KB output staging (2 column groups x 2 buffers)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(slabs + 4 * kSlabBytes);
   uint64_t* empty_bar = full_bar + kSt;
   uint64_t* tmem_full_bar = empty_bar + kSt;         // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  float* bias_s = reinterpret_cast<float*>(slabs + 4 * kSlabBytes + 256);   // [2][256] per-tile bias vectors
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -389,6 +385,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int tl = 0;
     for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
       int m_tile = (t % pm_tiles) * CTAS + rank;
+      const int m_tile_lin = m_tile;
       const int rest = t / pm_tiles;
       const int n_tile = rest % n_tiles;
       const int n0 = n_tile * BN;
@@ -404,12 +401,128 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const long long zoff = (long long)z1 * a.out_z1stride + (long long)z0 * a.out_z0stride;
       const long long fb_off = a.fbias ? (long long)((int)pix / a.fbias_div) * a.fbias_ld : 0;
       const int buf = tl & 1;
-      mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
-      tc_fence_after();
+      // bias (+ frame bias when every row of the tile shares the frame) of this tile's columns -> smem
+      const bool have_sb = a.bias != nullptr || a.fbias_uniform;
+      float* sbt = bias_s + buf * 256;
+      if (have_sb) {
+        const int et = threadIdx.x - 64, col = n0 + et;
+        float bsum = 0.f;
+        if (col < a.n_total) {
+          if (a.bias != nullptr) bsum = __ldg(a.bias + col);
+          if (a.fbias_uniform)
+            bsum += __ldg(a.fbias + (long long)((int)((long long)m_tile_lin * BM) / a.fbias_div) * a.fbias_ld + col);
+        }
+        sbt[et] = bsum;
+        named_bar_sync(3, kEpiWarps * 32);
+      }
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 256u;
       const int BNh = BN >> 1;              // GEGLU: [BNh value | BNh gate] accumulator columns
+      const bool prefetching = a.tma_store && !a.geglu && (a.res != nullptr || a.blend != nullptr);
+      if (!prefetching) {                   // (the prefetching path waits after issuing its first loads)
+        mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
+        tc_fence_after();
+      }
 
-      if (a.tma_store) {
+      if (a.tma_store && !a.geglu && (a.res != nullptr || a.blend != nullptr)) {
+        // ---- coalesced stores + software-pipelined residual / blend loads: the 64 bytes a row needs for
+        // chunk k+1 are requested before chunk k is computed (and, for the first chunk, before the
+        // accumulator is even ready), so their L2/HBM latency hides under the MMA wait and the math.
+        const int out_w = Ncur, out_c0 = n0, n_out = a.n_total;
+        const float al = a.alpha, be = 1.0f - a.alpha;
+        uint4 rq[2][4], bq[2][4];
+        auto prefetch = [&](int which, int c) {
+          const bool ok = row_ok && (c < out_w) && (out_c0 + c + 32 <= n_out);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { rq[which][j] = make_uint4(0u, 0u, 0u, 0u); bq[which][j] = make_uint4(0u, 0u, 0u, 0u); }
+          if (ok) {
+            if (a.res != nullptr) {
+              const uint4* pr = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.res) +
+                                                              pix * a.ldr + out_c0 + c);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(rq[which][j].x), "=r"(rq[which][j].y), "=r"(rq[which][j].z), "=r"(rq[which][j].w)
+                             : "l"(pr + j));
+            }
+            if (a.blend != nullptr) {
+              const uint4* pb = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.blend) +
+                                                              pix * a.ldb + out_c0 + c);
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(bq[which][j].x), "=r"(bq[which][j].y), "=r"(bq[which][j].z), "=r"(bq[which][j].w)
+                             : "l"(pb + j));
+            }
+          }
+        };
+        auto apply_aux = [&](int which, float (&f)[32], int c) {
+          if (!(row_ok && out_c0 + c + 32 <= n_out)) return;     // ragged tail columns never reach memory
+          if (a.res != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 t0 = unpack16x2(rq[which][j].x, a.fmt), t1 = unpack16x2(rq[which][j].y, a.fmt),
+                           t2 = unpack16x2(rq[which][j].z, a.fmt), t3 = unpack16x2(rq[which][j].w, a.fmt);
+              f[8 * j + 0] += t0.x; f[8 * j + 1] += t0.y; f[8 * j + 2] += t1.x; f[8 * j + 3] += t1.y;
+              f[8 * j + 4] += t2.x; f[8 * j + 5] += t2.y; f[8 * j + 6] += t3.x; f[8 * j + 7] += t3.y;
+            }
+          }
+          if (a.blend != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 t0 = unpack16x2(bq[which][j].x, a.fmt), t1 = unpack16x2(bq[which][j].y, a.fmt),
+                           t2 = unpack16x2(bq[which][j].z, a.fmt), t3 = unpack16x2(bq[which][j].w, a.fmt);
+              f[8 * j + 0] = al * t0.x + be * f[8 * j + 0]; f[8 * j + 1] = al * t0.y + be * f[8 * j + 1];
+              f[8 * j + 2] = al * t1.x + be * f[8 * j + 2]; f[8 * j + 3] = al * t1.y + be * f[8 * j + 3];
+              f[8 * j + 4] = al * t2.x + be * f[8 * j + 4]; f[8 * j + 5] = al * t2.y + be * f[8 * j + 5];
+              f[8 * j + 6] = al * t3.x + be * f[8 * j + 6]; f[8 * j + 7] = al * t3.y + be * f[8 * j + 7];
+            }
+          }
+        };
+        auto chunk = [&](int which, int c, uint32_t slab, int half, bool last_ld, bool& released) {
+          uint32_t v[32];
+          tmem_ld_32x32(trow + c, v);
+          tmem_ld_wait();
+          if (last_ld) { release(buf); released = true; }
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (a.scale != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= a.scale;
+          }
+          if (out_c0 + c + 32 <= n_out) {
+            finish_cols<32, false>(f, a, pix, fb_off, out_c0 + c, have_sb ? sbt + c : nullptr, n_out - (out_c0 + c), row_ok);
+            apply_aux(which, f, c);
+          } else {                                               // ragged tail: guarded scalar loads
+            finish_cols<32, true>(f, a, pix, fb_off, out_c0 + c, have_sb ? sbt + c : nullptr, n_out - (out_c0 + c), row_ok);
+          }
+          stage_cols32(f, slab, r, half, a.fmt);
+        };
+        prefetch(0, hsel * 64);                                  // overlaps the wait for the accumulator
+        mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
+        tc_fence_after();
+        bool released = false;
+#pragma unroll 1
+        for (int sl = hsel; sl * 64 < out_w; sl += 2, ++slab_it) {
+          const uint32_t slab = slab_base + (uint32_t)(slab_it & 1) * kSlabBytes;
+          if (issuer) bulk_wait_group_read<1>();
+          named_bar_sync(1 + hsel, 128);
+          const bool last_slab = (sl + 2) * 64 >= out_w;
+          const int c0 = sl * 64, c1 = c0 + 32;
+          prefetch(1, c1);                                       // second half of this slab
+          chunk(0, c0, slab, 0, last_slab && c1 >= out_w, released);
+          prefetch(0, c0 + 128);                                 // first half of this warp's next slab
+          if (c1 < out_w) chunk(1, c1, slab, 1, last_slab, released);
+          fence_proxy_async_smem();
+          named_bar_sync(1 + hsel, 128);
+          if (issuer) {
+            tma_store_5d(&tmC, reinterpret_cast<const void*>(slabs + hsel * 2 * kSlabBytes + (slab_it & 1) * kSlabBytes),
+                         out_c0 + sl * 64, x0, y0, nn0, 0);
+            bulk_commit_group();
+          }
+        }
+        if (!released) release(buf);
+      } else if (a.tma_store) {
         // ---- coalesced path: finished 64-column slabs go through swizzled smem and a TMA tile store
         const int out_w = a.geglu ? BNh : Ncur;               // output columns of this tile
         const int out_c0 = a.geglu ? n_tile * BNh : n0;       // first output column
@@ -434,17 +547,17 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tmem_ld_wait();
               if (last_ld) { release(buf); released = true; }
               const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4* bv = reinterpret_cast<const float4*>(a.bias + n0 + c);
-              const float4* bg = reinterpret_cast<const float4*>(a.bias + n0 + BNh + c);
+              const float4* bv = reinterpret_cast<const float4*>(sbt + c);
+              const float4* bg = reinterpret_cast<const float4*>(sbt + BNh + c);
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
-                const float4 x = a.bias ? __ldg(bv + j) : zero4, y = a.bias ? __ldg(bg + j) : zero4;
+                const float4 x = have_sb ? bv[j] : zero4, y = have_sb ? bg[j] : zero4;
                 f[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) + x.x) * gelu_erf(__uint_as_float(g[4 * j + 0]) + y.x);
                 f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + x.y) * gelu_erf(__uint_as_float(g[4 * j + 1]) + y.y);
                 f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + x.z) * gelu_erf(__uint_as_float(g[4 * j + 2]) + y.z);
                 f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + x.w) * gelu_erf(__uint_as_float(g[4 * j + 3]) + y.w);
               }
-              finish_cols<32>(f, a, pix, fb_off, out_c0 + c, 0, n_out - (out_c0 + c), row_ok);
+              finish_cols<32>(f, a, pix, fb_off, out_c0 + c, nullptr, n_out - (out_c0 + c), row_ok);
             } else {
               uint32_t v[32];
               tmem_ld_32x32(trow + c, v);     // columns past Ncur are stale but never reach memory (map clips)
@@ -456,7 +569,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] *= a.scale;
               }
-              finish_cols<32>(f, a, pix, fb_off, out_c0 + c, out_c0 + c, n_out - (out_c0 + c), row_ok);
+              finish_cols<32>(f, a, pix, fb_off, out_c0 + c, have_sb ? sbt + c : nullptr, n_out - (out_c0 + c), row_ok);
             }
             stage_cols32(f, slab, r, half, a.fmt);
           }
@@ -484,13 +597,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int vc = n0 + c + j, gc = n0 + BNh + c + j;
             float val = __uint_as_float(v[j]);
             float gate = __uint_as_float(g[j]);
-            if (a.bias != nullptr) {
-              if (vc < a.n_total) val += __ldg(a.bias + vc);
-              if (gc < a.n_total) gate += __ldg(a.bias + gc);
+            if (have_sb) {
+              val += sbt[c + j];
+              gate += sbt[BNh + c + j];
             }
+            (void)vc; (void)gc;
             f[j] = val * gelu_erf(gate);
           }
-          finish_and_store<32>(f, a, pix, zoff, fb_off, ocol_tile + c, 0, a.n_total / 2 - (ocol_tile + c), row_ok);
+          finish_and_store<32>(f, a, pix, zoff, fb_off, ocol_tile + c, nullptr, a.n_total / 2 - (ocol_tile + c), row_ok);
         }
       } else {
         bool released = false;
@@ -509,7 +623,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] *= a.scale;
             }
-            finish_and_store<32>(f, a, pix, zoff, fb_off, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
+            finish_and_store<32>(f, a, pix, zoff, fb_off, n0 + c, have_sb ? sbt + c : nullptr, a.n_total - (n0 + c), row_ok);
           } else {
             uint32_t v[16];
             tmem_ld_32x16(trow + c, v);
@@ -518,7 +632,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
-            finish_and_store<16>(f, a, pix, zoff, fb_off, n0 + c, n0 + c, a.n_total - (n0 + c), row_ok);
+            finish_and_store<16>(f, a, pix, zoff, fb_off, n0 + c, have_sb ? sbt + c : nullptr, a.n_total - (n0 + c), row_ok);
           }
         }
         if (!released) release(buf);         // this warp had no chunk in this tile (narrow tile)

@@ -56,6 +56,8 @@ struct TapGemmArgs {
   const float* bias;       // [n_total]
   const float* fbias;      // [frames][fbias_ld], frame = pixel / fbias_div
   int fbias_ld, fbias_div;
+  int fbias_uniform;       // every 128-row tile lies inside one frame (linear ops with fbias_div % 128 == 0):
+                           // the frame bias is folded into the per-tile bias vector staged in smem
   const void* res;         // 16-bit residual, same pixel indexing
   long long ldr;
   const void* blend;       // out = alpha * blend + (1 - alpha) * value

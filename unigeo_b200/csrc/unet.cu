@@ -199,6 +199,7 @@ void unet_set_clip_context(Ctx& c, const float* enc, cudaStream_t st) {
   for (size_t i = 0; i < t.transformers.size(); ++i) {
     const std::string& k = t.transformers[i];
     const int C = t.transformer_c[i];
+    const size_t mk = c.ws.mark();
     float* tmp = c.allocf((long long)T * C);
     const std::string s = k + ".transformer_blocks.0.attn2";
     op_gemv(c, c.M(s + ".to_v.weight"), nullptr, nullptr, enc, tmp, T, C, D, 0, 0);
@@ -208,6 +209,7 @@ void unet_set_clip_context(Ctx& c, const float* enc, cudaStream_t st) {
     op_gemv(c, c.M(tt + ".to_v.weight"), nullptr, nullptr, enc, tmp, 1, C, D, 0, 0);
     op_gemv(c, c.M(tt + ".to_out.0.weight"), c.F(tt + ".to_out.0.bias"), nullptr, tmp, m.attn2_temporal[k], 1, C,
             C, 0, 0);
+    c.ws.release(mk);
   }
   m.clip_context_set = true;
 }

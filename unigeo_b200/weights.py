@@ -203,28 +203,30 @@ def _is_norm_key(key: str) -> bool:
     return leaf.startswith("norm") or leaf in ("group_norm", "conv_norm_out")
 
 
-def synthetic_state_dict(shapes: Shapes, seed: int, dtype=torch.float32) -> Dict[str, torch.Tensor]:
-    """Seeded weights for a shape inventory (CPU tensors, ``dtype``).
+def synthetic_state_dict(shapes: Shapes, seed: int, dtype=torch.float32, device="cpu") -> Dict[str, torch.Tensor]:
+    """Seeded weights for a shape inventory (``dtype`` tensors on ``device``).
 
     One generator is advanced key by key in inventory order, so the same
-    (shapes, seed) always yields the same tensors on any machine.
+    (shapes, seed, device type) always yields the same tensors.  Parity tests draw on the CPU (the
+    oracle needs the identical values); benchmarks may draw on the GPU, where 1.5 B values take
+    milliseconds instead of tens of seconds.
     """
-    g = torch.Generator().manual_seed(seed)
+    g = torch.Generator(device=device).manual_seed(seed)
     sd: Dict[str, torch.Tensor] = OrderedDict()
     for key, shape in shapes.items():
         if key.endswith("mix_factor"):
-            t = torch.randn(shape, generator=g) * 0.5
+            t = torch.randn(shape, generator=g, device=device) * 0.5
         elif _is_norm_key(key):
-            t = torch.randn(shape, generator=g) * 0.02
+            t = torch.randn(shape, generator=g, device=device) * 0.02
             if key.endswith(".weight"):
                 t = t + 1.0
         elif key.endswith(".bias"):
-            t = torch.randn(shape, generator=g) * 0.02
+            t = torch.randn(shape, generator=g, device=device) * 0.02
         else:
             fan_in = 1
             for s in shape[1:]:
                 fan_in *= s
-            t = torch.randn(shape, generator=g) / float(fan_in) ** 0.5
+            t = torch.randn(shape, generator=g, device=device) / float(fan_in) ** 0.5
         sd[key] = t.to(dtype)
     return sd
 
