@@ -63,7 +63,21 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void
 #pragma unroll
   for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
   if (rr < rpb) {
-    for (long long r = r_begin + rr; r < r_end; r += rpb) {
+    long long r = r_begin + rr;
+    // four independent 16-byte loads in flight per thread (HBM latency x bandwidth needs ~40 KB per SM)
+    for (; r + 3 * rpb < r_end; r += 4 * rpb) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r + (long long)k * rpb, c8));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float f[8];
+        unpack8<T>(u[k], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] += f[j] * f[j]; }
+      }
+    }
+    for (; r < r_end; r += rpb) {
       uint4 u = __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r, c8));
       float f[8];
       unpack8<T>(u, f);
@@ -193,22 +207,22 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void
   for (int j = 0; j < 8; ++j) { sa[j] = s_a[c8 * 8 + j]; sb[j] = s_b[c8 * 8 + j]; }
   uint4* yo = reinterpret_cast<uint4*>(y);
   long long r = r_begin + rr;
-  // two rows in flight per thread
-  for (; r + rpb < r_end; r += 2 * rpb) {
-    const long long g0 = set * rows_per_set + r, g1 = g0 + rpb;
-    const uint4 u0 = __ldg(cat_ptr(x1, nv1, x2, nv2, g0, c8));
-    const uint4 u1 = __ldg(cat_ptr(x1, nv1, x2, nv2, g1, c8));
-    float f0[8], f1[8];
-    unpack8<T>(u0, f0);
-    unpack8<T>(u1, f1);
+  // four rows in flight per thread
+  for (; r + 3 * rpb < r_end; r += 4 * rpb) {
+    uint4 u[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float v0 = fmaf(f0[j], sa[j], sb[j]), v1 = fmaf(f1[j], sa[j], sb[j]);
-      f0[j] = silu ? silu_f(v0) : v0;
-      f1[j] = silu ? silu_f(v1) : v1;
+    for (int k = 0; k < 4; ++k) u[k] = __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r + (long long)k * rpb, c8));
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float f0[8];
+      unpack8<T>(u[k], f0);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float v0 = fmaf(f0[j], sa[j], sb[j]);
+        f0[j] = silu ? silu_f(v0) : v0;
+      }
+      yo[(set * rows_per_set + r + (long long)k * rpb) * nvec + c8] = pack8<T>(f0);
     }
-    yo[g0 * nvec + c8] = pack8<T>(f0);
-    yo[g1 * nvec + c8] = pack8<T>(f1);
   }
   for (; r < r_end; r += rpb) {
     const long long g0 = set * rows_per_set + r;
