@@ -6,17 +6,25 @@
 //                64 B/clk, is the binding resource), exp2 against a lazily updated reference maximum,
 //                P_j written to smem as the 16-bit K-major A operand of the P.V MMA, O rescaled in TMEM
 //                (tcgen05.ld / st) only when a row maximum jumps by more than 2^8
-//   TMEM: S at columns [0,128), O at [128,192).  smem: Q 16K | K 2x16K | V 2x16K | P 32K = 112 KB, so
+//   TMEM: S at columns [0,128), O at [128,192).  smem: Q 16K | K 16K | V 16K | P 32K = 80 KB, so
 //   two CTAs share an SM: one CTA's exp2 phase (MUFU bound) overlaps the other's MMAs.
 //   V is consumed in place as an MN-major B operand (no transpose anywhere).
 #include "fmha.cuh"
 #include "ptx.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace ug {
 namespace {
 
 constexpr int kTile = 16384;                       // 128 rows x 128 B
-constexpr int kOffQ = 0, kOffK = kTile, kOffV = 3 * kTile, kOffP = 5 * kTile, kOffBar = 7 * kTile;
+// K and V are single-buffered: K_{j+1} is requested as soon as S_j = Q K_j^T has been issued and V_j
+// as soon as P_{j-1} V_{j-1} retires, both a whole softmax phase before they are needed -- and the
+// 80 KB footprint is what lets two CTAs share an SM.
+constexpr int kNst = 1;
+constexpr int kOffQ = 0, kOffK = kTile, kOffV = kOffK + kNst * kTile, kOffP = kOffV + kNst * kTile,
+              kOffBar = kOffP + 2 * kTile;
 constexpr int kSmem = kOffBar + 128;
 constexpr int kThreads = 192;
 constexpr uint32_t kColS = 0, kColO = 128;
@@ -74,8 +82,8 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
       mbar_arrive_expect_tx(q_full, kTile);
       tma_load_2d(smem + kOffQ, &tm, q_full, h * 64, row_base + q0);
       for (int j = 0; j < nb; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        const int s = j % kNst;
+        const uint32_t ph = (uint32_t)(j / kNst) & 1u;
         mbar_wait(&k_empty[s], ph ^ 1u);
         mbar_arrive_expect_tx(&k_full[s], kTile);
         tma_load_2d(smem + kOffK + s * kTile, &tm, &k_full[s], a.C + h * 64, row_base + j * 128);
@@ -90,8 +98,8 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
     const uint32_t idesc_pv = make_idesc_f16(128, 64, a.fmt, 1);
     const uint32_t sQ = smem_u32(smem + kOffQ), sP = smem_u32(smem + kOffP);
     auto issue_qk = [&](int j) {
-      const int s = j & 1;
-      mbar_wait(&k_full[s], (uint32_t)(j >> 1) & 1u);
+      const int s = j % kNst;
+      mbar_wait(&k_full[s], (uint32_t)(j / kNst) & 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t da = make_desc_kmajor_sw128(sQ);
@@ -106,9 +114,9 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
     mbar_wait(q_full, 0);
     issue_qk(0);
     for (int j = 0; j < nb; ++j) {
-      const int s = j & 1;
+      const int s = j % kNst;
       mbar_wait(p_full, (uint32_t)j & 1u);              // P_j in smem, O rescaled
-      mbar_wait(&v_full[s], (uint32_t)(j >> 1) & 1u);
+      mbar_wait(&v_full[s], (uint32_t)(j / kNst) & 1u);
       tc_fence_after();
       if (elect_one()) {
         const uint64_t dv = make_desc_mnmajor_sw128(smem_u32(smem + kOffV + s * kTile), 8192);
@@ -137,15 +145,17 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
     // past the threshold (and on the first block) the warp takes the exact two-pass route and rescales.
     // O / l at the end is independent of the reference, so results match the exact formulation.
     float m_ref = -INFINITY, l = 0.f;
-    uint32_t pk[64];
+    // p = 2^(s*scale - mref) for the 128 keys of the block, 32 columns at a time, written straight to the
+    // P tile in smem (K-major SWIZZLE_128B: row r, 16-byte chunk c16 of half hh at ((c16 ^ (r & 7)) * 16))
     auto compute_p = [&](float mref, int valid, float& rowsum, float& pmax) {
       rowsum = 0.f;
       pmax = 0.f;
-#pragma unroll
+#pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(lane_addr + kColS + c * 32, v);
         tmem_ld_wait();
+        uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 32; i += 2) {
           float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -mref));
@@ -156,13 +166,27 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
           }
           rowsum += p0 + p1;
           pmax = fmaxf(pmax, fmaxf(p0, p1));
-          pk[c * 16 + (i >> 1)] = a.fmt ? Elem<__nv_bfloat16>::pack2(p0, p1) : Elem<__half>::pack2(p0, p1);
+          pk[i >> 1] = a.fmt ? Elem<__nv_bfloat16>::pack2(p0, p1) : Elem<__half>::pack2(p0, p1);
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int c16 = c * 4 + q4;
+          const uint32_t addr = sP + (uint32_t)(c16 >> 3) * kTile + (uint32_t)r * 128u +
+                                (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[q4 * 4 + 0]),
+                       "r"(pk[q4 * 4 + 1]), "r"(pk[q4 * 4 + 2]), "r"(pk[q4 * 4 + 3])
+                       : "memory");
         }
       }
     };
     for (int j = 0; j < nb; ++j) {
       mbar_wait(s_full, (uint32_t)j & 1u);
       tc_fence_after();
+      // S_j complete implies P_{j-1} V_{j-1} (issued before Q K_j^T) has retired: the P tile and O are free
+      if (j > 0) {
+        mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
+        tc_fence_after();
+      }
       const int valid = min(128, a.N - j * 128);        // keys of this block that exist
       float rowsum, pmax, alpha = 1.0f;
       bool exact = (j == 0);
@@ -194,19 +218,6 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
         l = l * alpha + rowsum;
       } else {
         l += rowsum;
-      }
-      if (j > 0) {                                       // P buffer and O are busy until P_{j-1}.V is done
-        mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
-        tc_fence_after();
-      }
-      // ---- P_j -> smem, K-major SWIZZLE_128B: row r, 16-byte chunk c16 of half hh at ((c16 ^ (r & 7)) * 16)
-#pragma unroll
-      for (int c16 = 0; c16 < 16; ++c16) {
-        const uint32_t addr = sP + (uint32_t)(c16 >> 3) * kTile + (uint32_t)r * 128u +
-                              (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[c16 * 4 + 0]),
-                     "r"(pk[c16 * 4 + 1]), "r"(pk[c16 * 4 + 2]), "r"(pk[c16 * 4 + 3])
-                     : "memory");
       }
       // ---- O *= alpha (only on the exact route; warp-uniform)
       if (exact && j > 0) {
@@ -268,6 +279,28 @@ int launch_fmha_d64(const CUtensorMap& tm, const FmhaArgs& args, cudaStream_t st
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(fmha_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return (int)e;
+    // two CTAs per SM need (almost) the whole 228 KB as shared memory
+    e = cudaFuncSetAttribute(fmha_d64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return (int)e;
+    if (getenv("UG_DEBUG")) {
+      int nb = 0, dev = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
+      cudaGetDevice(&dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fmha_d64_kernel, kThreads, kSmem);
+      cudaDeviceGetAttribute(&v1, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+      cudaDeviceGetAttribute(&v2, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      cudaDeviceGetAttribute(&v3, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+      cudaDeviceGetAttribute(&v4, cudaDevAttrReservedSharedMemoryPerBlock, dev);
+      cudaFuncAttributes fa;
+      cudaFuncGetAttributes(&fa, fmha_d64_kernel);
+      fprintf(stderr, "[unigeo_b200] fmha_d64: %d CTAs/SM (smem %d B) smem/SM %d optin %d regs/SM %d reserved %d | "
+              "kernel regs %d static smem %zu maxdyn %d\n", nb, kSmem, v1, v2, v3, v4, fa.numRegs,
+              fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
+      for (int sm = 0; sm <= 112 * 1024; sm += 16 * 1024) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fmha_d64_kernel, kThreads, sm);
+        fprintf(stderr, "   dyn smem %6d -> %d CTAs/SM\n", sm, nb);
+      }
+    }
     configured = true;
   }
   if (args.C != args.heads * 64 || (args.C & 7)) return (int)cudaErrorInvalidValue;
