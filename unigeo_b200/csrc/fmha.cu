@@ -1,14 +1,22 @@
-// fmha_d64: flash attention on tcgen05.
-//   CTA = one 128-query tile of one (frame, head); 192 threads:
-//     warp 0     TMA producer: Q once, then K_j / V_j blocks of 128 keys through 2-deep rings
-//     warp 1     TMEM owner + UMMA issuer:  S = Q K_j^T (128x128x64)  and  O += P_j V_j (128x64x128)
-//     warps 2-5  softmax: thread = query row; S read ONCE per block with tcgen05.ld (TMEM read bandwidth,
-//                64 B/clk, is the binding resource), exp2 against a lazily updated reference maximum,
-//                P_j written to smem as the 16-bit K-major A operand of the P.V MMA, O rescaled in TMEM
-//                (tcgen05.ld / st) only when a row maximum jumps by more than 2^8
-//   TMEM: S at columns [0,128), O at [128,192).  smem: Q 16K | K 16K | V 16K | P 32K = 80 KB, so
-//   two CTAs share an SM: one CTA's exp2 phase (MUFU bound) overlaps the other's MMAs.
-//   V is consumed in place as an MN-major B operand (no transpose anywhere).
+// fmha_d64: flash attention on tcgen05, two query tiles per CTA in ping-pong.
+//
+//   CTA = 256 queries (tiles A and B of 128) of one (frame, head); 320 threads, one CTA per SM:
+//     warp 0      TMA producer: Q_A, Q_B once, then K_j / V_j blocks of 128 keys through 2-deep rings
+//     warp 1      TMEM owner + UMMA issuer.  Tensor-pipe order per key block j:
+//                   [P_A(j) ready] S_A(j+1) = Q_A K_{j+1}^T ; O_A += P_A(j) V_j ;
+//                   [P_B(j) ready] S_B(j+1) = Q_B K_{j+1}^T ; O_B += P_B(j) V_j
+//                 so a softmax group only ever waits for one 128x128x64 MMA, and the P.V MMAs run under
+//                 the other group's exp2 phase
+//     warps 2-5   softmax of tile A, warps 6-9 softmax of tile B (thread = query row)
+//   TMEM (512 columns): S_A [0,128) S_B [128,256) O_A [256,320) O_B [320,384).
+//   smem: Q 2x16K | K 2x16K | V 2x16K | P 2 tiles x 2 buffers x 32K = 224 KB.
+//
+//   Softmax reads S ONCE per block (TMEM read bandwidth, 64 B/clk, and MUFU exp2 are the binding
+//   resources): p = 2^(s*scale - m_ref) against a LAZY reference maximum m_ref.  While no row of the warp
+//   exceeds m_ref by more than 8 (p <= 256, exact in 16 bit) nothing is rescaled; otherwise (and on the
+//   first block) the warp takes the exact two-pass route and rescales O in TMEM (tcgen05.ld / st).  O / l is
+//   independent of the reference, so results equal the textbook formulation.
+//   P goes to smem as the 16-bit K-major A operand; V is consumed in place as an MN-major B operand.
 #include "fmha.cuh"
 #include "ptx.cuh"
 
@@ -19,32 +27,35 @@ namespace ug {
 namespace {
 
 constexpr int kTile = 16384;                       // 128 rows x 128 B
-// K and V are single-buffered: K_{j+1} is requested as soon as S_j = Q K_j^T has been issued and V_j
-// as soon as P_{j-1} V_{j-1} retires, both a whole softmax phase before they are needed -- and the
-// 80 KB footprint is what lets two CTAs share an SM.
-constexpr int kNst = 1;
-constexpr int kOffQ = 0, kOffK = kTile, kOffV = kOffK + kNst * kTile, kOffP = kOffV + kNst * kTile,
-              kOffBar = kOffP + 2 * kTile;
-constexpr int kSmem = kOffBar + 128;
-constexpr int kThreads = 192;
-constexpr uint32_t kColS = 0, kColO = 128;
+// K / V rings are 2 deep (measured with in-kernel cycle stamps: loads are never waited for); the smem
+// goes to double-buffered P tiles instead, so a group's exp2 phase for block j starts as soon as S(j)
+// lands, without waiting for P(j-1).V to finish reading the previous P tile.
+constexpr int kNst = 2;
+constexpr int kOffQ = 0;                           // Q_A, Q_B
+constexpr int kOffK = 2 * kTile;                   // K ring
+constexpr int kOffV = kOffK + kNst * kTile;        // V ring
+constexpr int kOffP = kOffV + kNst * kTile;        // P[tile][buffer], 2 x kTile each
+constexpr int kOffBar = kOffP + 8 * kTile;
+constexpr int kSmem = kOffBar + 256;
+constexpr int kThreads = 320;
+constexpr uint32_t kColS = 0, kColO = 256;
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ FmhaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* v_full = bars + 3;    // [2]
-  uint64_t* k_empty = bars + 5;   // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;
-  uint64_t* p_full = bars + 10;
-  uint64_t* o_done = bars + 11;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* k_full = bars + 1;              // [kNst]
+  uint64_t* v_full = k_full + kNst;         // [kNst]
+  uint64_t* k_empty = v_full + kNst;        // [kNst]
+  uint64_t* v_empty = k_empty + kNst;       // [kNst]
+  uint64_t* s_full = v_empty + kNst;        // [2] per query tile
+  uint64_t* p_full = s_full + 2;            // [2]
+  uint64_t* o_done = p_full + 2;            // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128;
+  const int q0 = blockIdx.x * 256;
   const int h = blockIdx.y;
   const int f = blockIdx.z;
   const int row_base = f * a.N;
@@ -56,19 +67,21 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
   if (warp == 1) {
     if (lane == 0) {
       mbar_init(q_full, 1);
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < kNst; ++i) {
         mbar_init(&k_full[i], 1);
         mbar_init(&v_full[i], 1);
         mbar_init(&k_empty[i], 1);
         mbar_init(&v_empty[i], 1);
       }
-      mbar_init(s_full, 1);
-      mbar_init(p_full, 128);
-      mbar_init(o_done, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&s_full[i], 1);
+        mbar_init(&p_full[i], 128);
+        mbar_init(&o_done[i], 1);
+      }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr_smem, 256);
+    tmem_alloc(tmem_ptr_smem, 512);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -79,8 +92,9 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
-      mbar_arrive_expect_tx(q_full, kTile);
+      mbar_arrive_expect_tx(q_full, 2 * kTile);
       tma_load_2d(smem + kOffQ, &tm, q_full, h * 64, row_base + q0);
+      tma_load_2d(smem + kOffQ + kTile, &tm, q_full, h * 64, row_base + q0 + 128);
       for (int j = 0; j < nb; ++j) {
         const int s = j % kNst;
         const uint32_t ph = (uint32_t)(j / kNst) & 1u;
@@ -97,101 +111,137 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
     const uint32_t idesc_qk = make_idesc_f16(128, 128, a.fmt, 0);
     const uint32_t idesc_pv = make_idesc_f16(128, 64, a.fmt, 1);
     const uint32_t sQ = smem_u32(smem + kOffQ), sP = smem_u32(smem + kOffP);
-    auto issue_qk = [&](int j) {
-      const int s = j % kNst;
-      mbar_wait(&k_full[s], (uint32_t)(j / kNst) & 1u);
-      tc_fence_after();
+    // S_x(j) = Q_x K_j^T into tile x's S columns
+    auto issue_qk = [&](int x, int j) {
       if (elect_one()) {
-        const uint64_t da = make_desc_kmajor_sw128(sQ);
-        const uint64_t db = make_desc_kmajor_sw128(smem_u32(smem + kOffK + s * kTile));
+        const uint64_t da = make_desc_kmajor_sw128(sQ + x * kTile);
+        const uint64_t db = make_desc_kmajor_sw128(smem_u32(smem + kOffK + (j % kNst) * kTile));
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_f16(tmem_base + kColS, da + 2 * k, db + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-        umma_commit(&k_empty[s]);
-        umma_commit(s_full);
+        for (int k = 0; k < 4; ++k)
+          umma_f16(tmem_base + kColS + x * 128, da + 2 * k, db + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+        umma_commit(&s_full[x]);
+        if (x == 1) umma_commit(&k_empty[j % kNst]);    // both tiles have consumed K_j
+      }
+      __syncwarp();
+    };
+    // O_x += P_x(j) V_j
+    auto issue_pv = [&](int x, int j) {
+      if (elect_one()) {
+        const uint64_t dv = make_desc_mnmajor_sw128(smem_u32(smem + kOffV + (j % kNst) * kTile), 8192);
+        const uint32_t pbase = sP + (uint32_t)(x * 2 + (j & 1)) * 2 * kTile;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          // A: P half (k >> 2), +32 B per 16 keys inside the swizzle row; B: 16 key rows = 2048 B
+          const uint64_t dp = make_desc_kmajor_sw128(pbase + (k >> 2) * kTile) + 2 * (k & 3);
+          umma_f16(tmem_base + kColO + x * 64, dp, dv + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&o_done[x]);
+        if (x == 1) umma_commit(&v_empty[j % kNst]);    // both tiles have consumed V_j
       }
       __syncwarp();
     };
     mbar_wait(q_full, 0);
-    issue_qk(0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    issue_qk(0, 0);
+    issue_qk(1, 0);
     for (int j = 0; j < nb; ++j) {
-      const int s = j % kNst;
-      mbar_wait(p_full, (uint32_t)j & 1u);              // P_j in smem, O rescaled
-      mbar_wait(&v_full[s], (uint32_t)(j / kNst) & 1u);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t dv = make_desc_mnmajor_sw128(smem_u32(smem + kOffV + s * kTile), 8192);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          // A: P half (k >> 2), +32 B per 16 keys inside the swizzle row; B: 16 key rows = 2048 B
-          const uint64_t dp = make_desc_kmajor_sw128(sP + (k >> 2) * kTile) + 2 * (k & 3);
-          umma_f16(tmem_base + kColO, dp, dv + 128 * k, idesc_pv, (j | k) != 0 ? 1u : 0u);
+#pragma unroll 1
+      for (int x = 0; x < 2; ++x) {
+        mbar_wait(&p_full[x], (uint32_t)j & 1u);        // P_x(j) in smem, S_x drained, O_x rescaled
+        tc_fence_after();
+        if (j + 1 < nb) {
+          if (x == 0) {
+            mbar_wait(&k_full[(j + 1) % kNst], (uint32_t)((j + 1) / kNst) & 1u);
+            tc_fence_after();
+          }
+          issue_qk(x, j + 1);
         }
-        umma_commit(&v_empty[s]);
-        umma_commit(o_done);
+        if (x == 0) {
+          mbar_wait(&v_full[j % kNst], (uint32_t)(j / kNst) & 1u);
+          tc_fence_after();
+        }
+        issue_pv(x, j);
       }
-      __syncwarp();
-      if (j + 1 < nb) issue_qk(j + 1);
     }
   } else {
-    // ===================== softmax / correction / epilogue =====================
+    // ===================== softmax / correction / epilogue (tile x = 0: warps 2-5, x = 1: warps 6-9) =====
+    const int x = (warp - 2) >> 2;
     const int q = warp & 3;
     const int r = q * 32 + lane;                        // query row in the tile
     const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
-    const uint32_t sP = smem_u32(smem + kOffP);
+    const uint32_t colS = kColS + (uint32_t)x * 128u, colO = kColO + (uint32_t)x * 64u;
+    const uint32_t sPx = smem_u32(smem + kOffP) + (uint32_t)x * 4 * kTile;
     const float sc = a.scale_log2;
-    // Online softmax with a LAZY reference maximum: p = 2^(s*scale - m_ref) where m_ref is the row maximum
-    // known from earlier blocks.  As long as no row of the warp exceeds m_ref by more than 8 (p <= 256,
-    // exact in 16 bit) the block needs ONE pass over S in TMEM and no rescale of O; only when a row jumps
-    // past the threshold (and on the first block) the warp takes the exact two-pass route and rescales.
-    // O / l at the end is independent of the reference, so results match the exact formulation.
     float m_ref = -INFINITY, l = 0.f;
     // p = 2^(s*scale - mref) for the 128 keys of the block, 32 columns at a time, written straight to the
-    // P tile in smem (K-major SWIZZLE_128B: row r, 16-byte chunk c16 of half hh at ((c16 ^ (r & 7)) * 16))
-    auto compute_p = [&](float mref, int valid, float& rowsum, float& pmax) {
-      rowsum = 0.f;
-      pmax = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_addr + kColS + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+    // P tile (K-major SWIZZLE_128B: row r, 16-byte chunk c16 of half hh at ((c16 ^ (r & 7)) * 16))
+    // The TMEM load of chunk c+1 is in flight while chunk c goes through the MUFU (both cost ~256 clk per
+    // chunk and SM; serialised they were the whole kernel time).
+    auto p_chunk = [&](const uint32_t (&v)[32], int c, uint32_t sP, float mref, int valid, float& rowsum,
+                       float& pmax) {
+      uint32_t pk[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -mref));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -mref));
-          if (valid != 128) {
-            if (c * 32 + i >= valid) p0 = 0.f;
-            if (c * 32 + i + 1 >= valid) p1 = 0.f;
-          }
-          rowsum += p0 + p1;
-          pmax = fmaxf(pmax, fmaxf(p0, p1));
-          pk[i >> 1] = a.fmt ? Elem<__nv_bfloat16>::pack2(p0, p1) : Elem<__half>::pack2(p0, p1);
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -mref));
+        float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -mref));
+        if (valid != 128) {
+          if (c * 32 + i >= valid) p0 = 0.f;
+          if (c * 32 + i + 1 >= valid) p1 = 0.f;
         }
+        rowsum += p0 + p1;
+        pk[i >> 1] = a.fmt ? Elem<__nv_bfloat16>::pack2(p0, p1) : Elem<__half>::pack2(p0, p1);
+      }
+      // threshold test on the packed pairs: one packed max per two elements (p >= 0, inf stays inf)
+      if (a.fmt) {
+        __nv_bfloat162 mx2 = *reinterpret_cast<__nv_bfloat162*>(&pk[0]);
 #pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int c16 = c * 4 + q4;
-          const uint32_t addr = sP + (uint32_t)(c16 >> 3) * kTile + (uint32_t)r * 128u +
-                                (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[q4 * 4 + 0]),
-                       "r"(pk[q4 * 4 + 1]), "r"(pk[q4 * 4 + 2]), "r"(pk[q4 * 4 + 3])
-                       : "memory");
-        }
+        for (int i = 1; i < 16; ++i) mx2 = __hmax2(mx2, *reinterpret_cast<__nv_bfloat162*>(&pk[i]));
+        pmax = fmaxf(pmax, fmaxf(__bfloat162float(mx2.x), __bfloat162float(mx2.y)));
+      } else {
+        __half2 mx2 = *reinterpret_cast<__half2*>(&pk[0]);
+#pragma unroll
+        for (int i = 1; i < 16; ++i) mx2 = __hmax2(mx2, *reinterpret_cast<__half2*>(&pk[i]));
+        pmax = fmaxf(pmax, fmaxf(__half2float(mx2.x), __half2float(mx2.y)));
+      }
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        const int c16 = c * 4 + q4;
+        const uint32_t addr = sP + (uint32_t)(c16 >> 3) * kTile + (uint32_t)r * 128u +
+                              (uint32_t)(((c16 & 7) ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pk[q4 * 4 + 0]),
+                     "r"(pk[q4 * 4 + 1]), "r"(pk[q4 * 4 + 2]), "r"(pk[q4 * 4 + 3])
+                     : "memory");
       }
     };
+    auto compute_p = [&](uint32_t sP, float mref, int valid, float& rowsum, float& pmax) {
+      rowsum = 0.f;
+      pmax = 0.f;
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32(lane_addr + colS, va);
+      tmem_ld_wait();
+      tmem_ld_32x32(lane_addr + colS + 32, vb);
+      p_chunk(va, 0, sP, mref, valid, rowsum, pmax);
+      tmem_ld_wait();
+      tmem_ld_32x32(lane_addr + colS + 64, va);
+      p_chunk(vb, 1, sP, mref, valid, rowsum, pmax);
+      tmem_ld_wait();
+      tmem_ld_32x32(lane_addr + colS + 96, vb);
+      p_chunk(va, 2, sP, mref, valid, rowsum, pmax);
+      tmem_ld_wait();
+      p_chunk(vb, 3, sP, mref, valid, rowsum, pmax);
+    };
     for (int j = 0; j < nb; ++j) {
-      mbar_wait(s_full, (uint32_t)j & 1u);
+      mbar_wait(&s_full[x], (uint32_t)j & 1u);
       tc_fence_after();
-      // S_j complete implies P_{j-1} V_{j-1} (issued before Q K_j^T) has retired: the P tile and O are free
-      if (j > 0) {
-        mbar_wait(o_done, (uint32_t)(j - 1) & 1u);
-        tc_fence_after();
-      }
+      // S_x(j) complete => every MMA issued before it has retired, in particular P_x(j-2) V_{j-2}: P buffer
+      // (j & 1) is free.  P_x(j-1) V_{j-1} may still be running; only the rescale path waits for it.
+      const uint32_t sP = sPx + (uint32_t)(j & 1) * 2 * kTile;
       const int valid = min(128, a.N - j * 128);        // keys of this block that exist
       float rowsum, pmax, alpha = 1.0f;
       bool exact = (j == 0);
       if (!exact) {
-        compute_p(m_ref, valid, rowsum, pmax);
+        compute_p(sP, m_ref, valid, rowsum, pmax);
         exact = __any_sync(0xffffffffu, !(pmax <= 256.0f));   // also catches inf / nan
       }
       if (exact) {
@@ -200,7 +250,7 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           uint32_t v[32];
-          tmem_ld_32x32(lane_addr + kColS + c * 32, v);
+          tmem_ld_32x32(lane_addr + colS + c * 32, v);
           tmem_ld_wait();
           if (valid == 128) {
 #pragma unroll
@@ -214,39 +264,41 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
         const float mx = fmaxf(m_ref, mraw * sc);        // sc > 0
         alpha = ex2_approx(m_ref - mx);                   // m_ref = -inf on the first block -> 0
         m_ref = mx;
-        compute_p(m_ref, valid, rowsum, pmax);
+        compute_p(sP, m_ref, valid, rowsum, pmax);
         l = l * alpha + rowsum;
+        if (j > 0) {                                     // O_x *= alpha once P_x(j-1) V_{j-1} has retired
+          mbar_wait(&o_done[x], (uint32_t)(j - 1) & 1u);
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t o[32];
+            tmem_ld_32x32(lane_addr + colO + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32(lane_addr + colO + c * 32, o);
+          }
+          tmem_st_wait();
+        }
       } else {
         l += rowsum;
       }
-      // ---- O *= alpha (only on the exact route; warp-uniform)
-      if (exact && j > 0) {
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          uint32_t o[32];
-          tmem_ld_32x32(lane_addr + kColO + c * 32, o);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
-          tmem_st_32x32(lane_addr + kColO + c * 32, o);
-        }
-        tmem_st_wait();
-      }
       fence_proxy_async_smem();                          // P visible to the tensor core's async proxy
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[x]);
     }
     // ---- epilogue: O / l -> out
-    mbar_wait(o_done, (uint32_t)(nb - 1) & 1u);
+    mbar_wait(&o_done[x], (uint32_t)(nb - 1) & 1u);
     tc_fence_after();
     const float inv = 1.0f / l;
-    const bool ok = (q0 + r) < a.N;
+    const int qrow = q0 + x * 128 + r;
+    const bool ok = qrow < a.N;
     uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(a.out) +
-                                          ((long long)(row_base + q0 + r) * a.C + h * 64));
+                                          ((long long)(row_base + qrow) * a.C + h * 64));
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {
       uint32_t o[32];
-      tmem_ld_32x32(lane_addr + kColO + c * 32, o);
+      tmem_ld_32x32(lane_addr + colO + c * 32, o);
       tmem_ld_wait();
       if (ok) {
 #pragma unroll
@@ -268,7 +320,7 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -279,32 +331,10 @@ int launch_fmha_d64(const CUtensorMap& tm, const FmhaArgs& args, cudaStream_t st
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(fmha_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return (int)e;
-    // two CTAs per SM need (almost) the whole 228 KB as shared memory
-    e = cudaFuncSetAttribute(fmha_d64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return (int)e;
-    if (getenv("UG_DEBUG")) {
-      int nb = 0, dev = 0, v1 = 0, v2 = 0, v3 = 0, v4 = 0;
-      cudaGetDevice(&dev);
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fmha_d64_kernel, kThreads, kSmem);
-      cudaDeviceGetAttribute(&v1, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-      cudaDeviceGetAttribute(&v2, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-      cudaDeviceGetAttribute(&v3, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
-      cudaDeviceGetAttribute(&v4, cudaDevAttrReservedSharedMemoryPerBlock, dev);
-      cudaFuncAttributes fa;
-      cudaFuncGetAttributes(&fa, fmha_d64_kernel);
-      fprintf(stderr, "[unigeo_b200] fmha_d64: %d CTAs/SM (smem %d B) smem/SM %d optin %d regs/SM %d reserved %d | "
-              "kernel regs %d static smem %zu maxdyn %d\n", nb, kSmem, v1, v2, v3, v4, fa.numRegs,
-              fa.sharedSizeBytes, fa.maxDynamicSharedSizeBytes);
-      for (int sm = 0; sm <= 112 * 1024; sm += 16 * 1024) {
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fmha_d64_kernel, kThreads, sm);
-        fprintf(stderr, "   dyn smem %6d -> %d CTAs/SM\n", sm, nb);
-      }
-    }
     configured = true;
   }
   if (args.C != args.heads * 64 || (args.C & 7)) return (int)cudaErrorInvalidValue;
-  dim3 grid((args.N + 127) / 128, args.heads, args.F);
+  dim3 grid((args.N + 255) / 256, args.heads, args.F);
   fmha_d64_kernel<<<grid, kThreads, kSmem, stream>>>(tm, args);
   return (int)cudaGetLastError();
 }

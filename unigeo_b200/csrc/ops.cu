@@ -195,8 +195,21 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
   const int Ho = H / stride, Wo = W / stride;
   a.W = Wo; a.H = Ho; a.N = Nf;
   a.bw = imin(Wo, 128);
-  a.bh = imin(Ho, 128 / a.bw);
-  a.bn = imin(Nf, 128 / (a.bw * a.bh));
+  // 128-row tile = bw x bh x bn pixels: pick the (rows, frames) split that covers the clip with the fewest
+  // tiles (e.g. 16x12 frames: 4 rows x 2 frames -> 39 tiles instead of 8 rows x 1 frame -> 50)
+  {
+    const int rows_left = 128 / a.bw;
+    long long best = -1;
+    for (int bh = 1; bh <= rows_left && bh <= Ho; ++bh) {
+      const int bn = imin(Nf, rows_left / bh);
+      const long long tiles = (long long)cdiv(Ho, bh) * cdiv(Nf, bn);
+      if (best < 0 || tiles < best || (tiles == best && bh > a.bh)) {
+        best = tiles;
+        a.bh = bh;
+        a.bn = bn;
+      }
+    }
+  }
   a.tiles_x = cdiv(Wo, a.bw);
   a.tiles_y = cdiv(Ho, a.bh);
   a.tiles_n = cdiv(Nf, a.bn);
