@@ -45,8 +45,11 @@ class DepthCrafter:
             clip_dir = os.path.join(pre_train_path, "image_encoder")
         else:
             s = int(kwargs.get("weight_seed", 0))
-            self.engine.load_state_dict("unet", synthetic_state_dict(unet_param_shapes(self.cfg.unet), 1000 + s))
-            self.engine.load_state_dict("vae", synthetic_state_dict(vae_param_shapes(self.cfg.vae), 2000 + s))
+            # device_weights=True draws the synthetic tensors on the GPU (fast, different values than the CPU draw)
+            wdev = self.device if kwargs.get("device_weights") else "cpu"
+            wdt = torch.float16 if kwargs.get("device_weights") else torch.float32
+            self.engine.load_state_dict("unet", synthetic_state_dict(unet_param_shapes(self.cfg.unet), 1000 + s, wdt, wdev))
+            self.engine.load_state_dict("vae", synthetic_state_dict(vae_param_shapes(self.cfg.vae), 2000 + s, wdt, wdev))
         self.engine.finalize()
         clip = None
         if kwargs.get("clip", "random") != "none":
@@ -72,7 +75,7 @@ class DepthCrafter:
         frames = self.prepare_input(data)
         gen = None
         if self.seed is not None:
-            gen = torch.Generator().manual_seed(int(self.seed))
+            gen = torch.Generator(device=self.device).manual_seed(int(self.seed))
         out = self.pipeline(frames, num_inference_steps=self.num_inference_steps, generator=gen,
                             output_type="pt", **debug_inputs)
         return self.prepare_output(out, data)
