@@ -63,6 +63,7 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();   // swizzled tiles need a 1024-byte aligned base
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tm);
   if (warp == 1) {
     if (lane == 0) {
@@ -88,6 +89,7 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -335,8 +337,7 @@ int launch_fmha_d64(const CUtensorMap& tm, const FmhaArgs& args, cudaStream_t st
   }
   if (args.C != args.heads * 64 || (args.C & 7)) return (int)cudaErrorInvalidValue;
   dim3 grid((args.N + 255) / 256, args.heads, args.F);
-  fmha_d64_kernel<<<grid, kThreads, kSmem, stream>>>(tm, args);
-  return (int)cudaGetLastError();
+  return (int)launch_pdl(fmha_d64_kernel, grid, dim3(kThreads), kSmem, stream, tm, args);
 }
 
 }  // namespace ug

@@ -48,6 +48,8 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void
                                 long long rows_per_set, long long chunk_rows, int G, int cs,
                                 float* __restrict__ part, float* __restrict__ mr, unsigned int* __restrict__ counters,
                                 float inv_cnt, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_part[];   // [rpb][C] sums, then [rpb][C] sumsq
   __shared__ int s_last;
   const int nvec = nv1 + nv2;
@@ -174,6 +176,8 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void
                                 const float* __restrict__ part /* [sets][G] (mean, rstd) */,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 void* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float s_ab[];   // [C] scale, [C] shift, [G] mean, [G] rstd
   const int nvec = nv1 + nv2;
   const int C = nvec * 8;
@@ -245,6 +249,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, const float* __restrict__ add, int add_div,
                  void* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
   if (row0 >= rows) return;
@@ -402,6 +408,8 @@ template <typename T, int TPAD>
 __global__ void __launch_bounds__(128)
 temporal_attn_kernel(const void* __restrict__ qkv, void* __restrict__ out, int Tn, long long P, int C,
                      float scale_log2e) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t sm_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int heads = C >> 6;
@@ -532,6 +540,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
 }
 __global__ void concat_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
                               long long rows, uint4* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int nvec = nv1 + nv2;
   const long long total = rows * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -734,10 +744,10 @@ int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long ro
   if (sets > kGnMaxSets || g.threads < 2 * G) return (int)cudaErrorInvalidValue;
   float* mr = stats + sets * g.chunks * G * 2;
   const float inv_cnt = 1.0f / ((float)rows_per_set * (float)(C / G));
-  UG_DISPATCH_FMT(fmt, (gn_stats_kernel<T><<<grid, g.threads, smem, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
-                                                                           g.chunk_rows, G, C / G, stats, mr, counters,
-                                                                           inv_cnt, eps)));
-  return last_err();
+  cudaError_t err;
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl(gn_stats_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
+                                         rows_per_set, g.chunk_rows, G, C / G, stats, mr, counters, inv_cnt, eps)));
+  return (int)err;
 }
 
 int launch_gn_finalize(int C, long long rows, long long rows_per_set, int G, float eps, float* stats,
@@ -761,10 +771,10 @@ int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long ro
   const size_t smem = (size_t)(C * 2 + G * 2) * sizeof(float);
   const float* mr = stats + sets * g.chunks * G * 2;
   (void)eps;
-  UG_DISPATCH_FMT(fmt, (gn_apply_kernel<T><<<grid, g.threads, smem, st>>>(x1, C1 / 8, x2, C2 / 8, rows_per_set,
-                                                                            g.chunk_rows, G, C / G, mr, gamma, beta,
-                                                                            silu, y)));
-  return last_err();
+  cudaError_t err;
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl(gn_apply_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
+                                         rows_per_set, g.chunk_rows, G, C / G, mr, gamma, beta, silu, y)));
+  return (int)err;
 }
 
 template <int VPL, int ROWS>
@@ -773,9 +783,10 @@ int launch_ln_t(const void* x, long long rows, int C, const float* gamma, const 
   const int wpb = 8;
   const long long rows_per_block = (long long)wpb * ROWS;
   const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
-  UG_DISPATCH_FMT(fmt, (layernorm_kernel<T, VPL, ROWS><<<grid, wpb * 32, 0, st>>>(x, rows, C, gamma, beta, eps, add,
-                                                                                  add_div > 0 ? add_div : 1, y)));
-  return last_err();
+  cudaError_t err;
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl(layernorm_kernel<T, VPL, ROWS>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, C,
+                                         gamma, beta, eps, add, add_div > 0 ? add_div : 1, y)));
+  return (int)err;
 }
 
 int launch_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
@@ -816,7 +827,10 @@ int launch_temporal_attention(const void* qkv, void* out, int Tn, long long P, i
   const float sl = scale * 1.4426950408889634f;
   if (Tn <= 32) {
     const size_t smem = (size_t)wpb * 3 * 32 * 128;
-    UG_DISPATCH_FMT(fmt, (temporal_attn_kernel<T, 32><<<grid, wpb * 32, smem, st>>>(qkv, out, Tn, P, C, sl)));
+    cudaError_t err;
+    UG_DISPATCH_FMT(fmt, (err = launch_pdl(temporal_attn_kernel<T, 32>, dim3(grid), dim3(wpb * 32), smem, st, qkv, out,
+                                           Tn, P, C, sl)));
+    return (int)err;
   } else {
     const size_t smem = (size_t)wpb * 3 * 64 * 128;
     UG_DISPATCH_FMT(fmt, {
@@ -838,8 +852,8 @@ int launch_upsample2x(const void* x, void* y, int N, int H, int W, int C, cudaSt
 int launch_concat(const void* x1, int C1, const void* x2, int C2, long long rows, void* y, cudaStream_t st) {
   if ((C1 & 7) || (C2 & 7)) return (int)cudaErrorInvalidValue;
   const long long total = rows * ((C1 + C2) / 8);
-  concat_kernel<<<grid_for(total, 256), 256, 0, st>>>(x1, C1 / 8, x2, C2 / 8, rows, reinterpret_cast<uint4*>(y));
-  return last_err();
+  return (int)launch_pdl(concat_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, x1, C1 / 8, x2, C2 / 8, rows,
+                         reinterpret_cast<uint4*>(y));
 }
 
 int launch_nchw_to_nhwc(const float* x, const float* noise, float noise_scale, float scale, float shift, int N,

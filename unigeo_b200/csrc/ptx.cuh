@@ -3,6 +3,8 @@
 // 5th-gen tensor cores consume.  Everything else in csrc/ builds on these.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
+#include <utility>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
@@ -22,6 +24,31 @@ __device__ __forceinline__ bool elect_one() {
       "selp.b32 %0, 1, 0, P;\n\t}"
       : "=r"(pred));
   return pred != 0;
+}
+
+// ------------------------------------------------------------------ programmatic dependent launch
+// launch_dependents: the next kernel in the stream (if launched with the programmatic-serialization
+// attribute) may start scheduling its CTAs; wait: block until the previous kernel has fully completed
+// and its writes are visible.  Both are no-ops for kernels launched without the attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Host: launch with the programmatic stream serialization attribute (UG_NO_PDL=1 disables it).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  static const bool off = getenv("UG_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = off ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
 }
 
 // ------------------------------------------------------------------ mbarrier

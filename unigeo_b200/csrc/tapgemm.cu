@@ -238,6 +238,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     return rem < BN ? rem : BN;
   };
 
+  pdl_launch_dependents();   // the next kernel may stage its prologue while this one drains
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -268,6 +269,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if constexpr (CTAS == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();                // everything above (barriers, TMEM, descriptors) overlapped the previous kernel
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -764,8 +766,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   const int sms = tapgemm_num_sms();
   if (ctas == 1) {
     const int grid = (int)(units < sms ? units : sms);
-    tapgemm_kernel<1><<<grid, kThreads, kSmemBytes, stream>>>(tmA, tmB, mc, args);
-    return (int)cudaGetLastError();
+    return (int)launch_pdl(tapgemm_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, mc, args);
   }
   const long long slots = sms / 2;
   cudaLaunchConfig_t cfg = {};
@@ -773,13 +774,16 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes2;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  static const bool no_pdl = getenv("UG_NO_PDL") != nullptr;
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = no_pdl ? 1 : 2;
   return (int)cudaLaunchKernelEx(&cfg, tapgemm_kernel<2>, tmA, tmB, mc, args);
 }
 
