@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define UG_VERSION 100
+#define UG_VERSION 101
 
 typedef struct ug_ctx ug_ctx;
 
@@ -66,6 +66,22 @@ typedef struct ug_model_cfg {
   /* Euler / Karras scheduler */
   float sigma_min, sigma_max, rho;
 } ug_model_cfg;
+
+/* 2-D conditional UNet / ControlNet of the StableNormal path (SD-2.1 class; SURVEY.md App. A.5,
+ * reference call site model/stablenormal.py:16,39).  Optional: set before ug_ctx_finalize when weights
+ * of such a network are loaded.  The 2-D VAE ("vae2d." keys) shares the vae_* fields of ug_model_cfg. */
+typedef struct ug_unet2d_cfg {
+  int32_t in_channels, out_channels;
+  int32_t num_blocks;
+  int32_t block_out[4];
+  int32_t heads[4];
+  int32_t layers_per_block;
+  int32_t cross_attention_dim;
+  float eps_resnet, eps_transformer_norm, ln_eps;
+  /* DDIM scheduler: scaled-linear betas */
+  int32_t num_train_timesteps;
+  float beta_start, beta_end;
+} ug_unet2d_cfg;
 
 int ug_version(void);
 const char* ug_last_error(void);
@@ -111,6 +127,35 @@ int ug_vae_encode(ug_ctx* ctx, const float* img, const float* noise, float noise
 int ug_vae_decode_temporal(ug_ctx* ctx, const float* lat, int T, int h, int w, int chunk, float* img,
                            void* stream);
 
+/* ---- StableNormal path: 2-D UNet (+ ControlNet) over per-frame latents ---------------------------
+ * Networks are addressed by the key prefix their weights were loaded under ("unet2d.", "controlnet.",
+ * "yoso_unet.", ...); ug_ctx_finalize discovers every 2-D network among the loaded weights. */
+int ug_ctx_set_unet2d_cfg(ug_ctx* ctx, const ug_unet2d_cfg* cfg);
+/* encoder_hidden_states of network `net_prefix`: tokens fp32 [frames][len][cross_attention_dim], frames = 1
+ * (one prompt shared by all frames, StableNormal's fixed prompt) or the frame count; len <= 128.
+ * Precomputes K | V of every cross-attention (they do not depend on the latents or the timestep). */
+int ug_set_text_context(ug_ctx* ctx, const char* net_prefix, const float* tokens, int frames, int len,
+                        void* stream);
+/* Replaces unet(sample, t, encoder_hidden_states, down_block_additional_residuals=controlnet(...)...)[0]:
+ * x, controlnet_sample fp32 [F][in_channels][h][w]; out fp32 [F][out_channels][h][w];
+ * controlnet_prefix / controlnet_sample nullable (plain UNet). */
+int ug_unet2d_forward(ug_ctx* ctx, const char* unet_prefix, const float* x, int F, int h, int w, float timestep,
+                      const char* controlnet_prefix, const float* controlnet_sample, float* out, void* stream);
+/* Replaces the refinement loop of the hub predictor (DDIM, prediction_type "sample", eta 0, trailing
+ * spacing from t_start, or from num_train_timesteps-1 when t_start < 0): image_latent, latents_in,
+ * latents_out fp32 [F][4][h][w] (scaled latents). */
+int ug_refine_frames_2d(ug_ctx* ctx, const char* unet_prefix, const char* controlnet_prefix,
+                        const float* image_latent, const float* latents_in, int F, int h, int w, int steps,
+                        int t_start, float* latents_out, void* stream);
+/* 2-D AutoencoderKL ("vae2d." keys): encode = latent_dist.mode() * out_scale; decode: lat / scaling_factor ->
+ * post_quant_conv -> decoder.  img (nullable) fp32 [N][3][8h][8w]; normals_u8 (nullable) uint8 [N][8h][8w][3] =
+ * unit-normalised, clipped, ((n+1)/2*255) truncated -- the 8-bit image the predictor returns
+ * (model/stablenormal.py:39-40). */
+int ug_vae2d_encode(ug_ctx* ctx, const float* img, int N, int H, int W, float out_scale, float* lat,
+                    void* stream);
+int ug_vae2d_decode(ug_ctx* ctx, const float* lat, int N, int h, int w, float* img, unsigned char* normals_u8,
+                    void* stream);
+
 /* Kernels launched on behalf of this context since the last reset (bench "gpu_launches"). */
 long long ug_ctx_launch_count(ug_ctx* ctx, int reset);
 /* Bytes of workspace currently reserved. */
@@ -143,6 +188,9 @@ int ug_op_layernorm(int dtype, const void* x, long long rows, int C, const float
 int ug_op_spatial_attention(int dtype, const void* qkv, int F, int N, int C, int dh, void* y, void* stream);
 /* qkv [T][P][3C] -> y [T][P][C]; attention over T per pixel and 64-wide head */
 int ug_op_temporal_attention(int dtype, const void* qkv, int T, long long P, int C, void* y, void* stream);
+/* q [F*N][C], kv [Fk*Lk][2C] (K | V; Fk = F if kv_per_frame else 1) -> y [F*N][C]; head_dim 64, Lk <= 128 */
+int ug_op_cross_attention(int dtype, const void* q, const void* kv, int F, int N, int C, int Lk, int kv_per_frame,
+                          void* y, void* stream);
 
 #ifdef __cplusplus
 }

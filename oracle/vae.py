@@ -79,3 +79,26 @@ def vae_decode(sd: SD, cfg, latents: torch.Tensor, chunk: int = 8) -> torch.Tens
         zc = z[i:i + chunk]
         outs.append(vae_decode_chunk(sd, cfg, zc, zc.shape[0]))
     return torch.cat(outs, dim=0)
+
+
+def vae_decode_2d(sd: SD, cfg, latents: torch.Tensor) -> torch.Tensor:
+    """AutoencoderKL.decode of the 2-D (StableNormal, SD-2.1 class) VAE: latents [N,4,h,w] (scaled) ->
+    [N,3,8h,8w]; z / scaling_factor -> post_quant_conv -> Decoder ([UPSTREAM] diffusers
+    ``autoencoder_kl.py`` / ``vae.py`` Decoder: mid Res-Attn-Res, 4 UpDecoderBlock2D of 3 resnets).
+    Reference call site: model/stablenormal.py:39 (inside the hub predictor)."""
+    g, eps = cfg.norm_groups, cfg.eps
+    nb = len(cfg.block_out_channels)
+    z = latents / cfg.scaling_factor
+    x = conv2d(sd, "post_quant_conv", z, padding=0)
+    x = conv2d(sd, "decoder.conv_in", x)
+    x = resnet_block_2d(sd, "decoder.mid_block.resnets.0", x, None, g, eps)
+    x = _mid_attention(sd, "decoder.mid_block.attentions.0", x, g, eps)
+    x = resnet_block_2d(sd, "decoder.mid_block.resnets.1", x, None, g, eps)
+    for i in range(nb):
+        for j in range(cfg.layers_per_block + 1):
+            x = resnet_block_2d(sd, f"decoder.up_blocks.{i}.resnets.{j}", x, None, g, eps)
+        if i < nb - 1:
+            x = F.interpolate(x, scale_factor=2.0, mode="nearest")
+            x = conv2d(sd, f"decoder.up_blocks.{i}.upsamplers.0.conv", x)
+    x = F.silu(group_norm(sd, "decoder.conv_norm_out", x, g, eps))
+    return conv2d(sd, "decoder.conv_out", x)

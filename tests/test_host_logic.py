@@ -120,7 +120,7 @@ def test_abi_header_and_library_agree():
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ug_version() == 100
+    assert lib.ug_version() == 101
 
 
 def test_abi_fails_cleanly_without_gpu():

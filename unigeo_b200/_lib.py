@@ -44,6 +44,20 @@ class ModelCfg(C.Structure):
     ]
 
 
+class UNet2DCfg(C.Structure):
+    _fields_ = [
+        ("in_channels", C.c_int32), ("out_channels", C.c_int32),
+        ("num_blocks", C.c_int32),
+        ("block_out", C.c_int32 * 4),
+        ("heads", C.c_int32 * 4),
+        ("layers_per_block", C.c_int32),
+        ("cross_attention_dim", C.c_int32),
+        ("eps_resnet", C.c_float), ("eps_transformer_norm", C.c_float), ("ln_eps", C.c_float),
+        ("num_train_timesteps", C.c_int32),
+        ("beta_start", C.c_float), ("beta_end", C.c_float),
+    ]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 _SIGNATURES = {
@@ -59,6 +73,12 @@ _SIGNATURES = {
     "ug_denoise_clip": ([_P, _P, _P, C.POINTER(C.c_float), _I, _P, _P], C.c_int),
     "ug_vae_encode": ([_P, _P, _P, _F, _I, _I, _I, _P, _P], C.c_int),
     "ug_vae_decode_temporal": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
+    "ug_ctx_set_unet2d_cfg": ([_P, C.POINTER(UNet2DCfg)], C.c_int),
+    "ug_set_text_context": ([_P, C.c_char_p, _P, _I, _I, _P], C.c_int),
+    "ug_unet2d_forward": ([_P, C.c_char_p, _P, _I, _I, _I, _F, C.c_char_p, _P, _P, _P], C.c_int),
+    "ug_refine_frames_2d": ([_P, C.c_char_p, C.c_char_p, _P, _P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
+    "ug_vae2d_encode": ([_P, _P, _I, _I, _I, _F, _P, _P], C.c_int),
+    "ug_vae2d_decode": ([_P, _P, _I, _I, _I, _P, _P, _P], C.c_int),
     "ug_ctx_launch_count": ([_P, _I], C.c_longlong),
     "ug_ctx_workspace_bytes": ([_P], C.c_longlong),
     "ug_ctx_profile": ([_P, _I], C.c_int),
@@ -71,6 +91,7 @@ _SIGNATURES = {
     "ug_op_layernorm": ([_I, _P, _L, _I, _P, _P, _F, _P, _I, _P, _P], C.c_int),
     "ug_op_spatial_attention": ([_I, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "ug_op_temporal_attention": ([_I, _P, _I, _L, _I, _P, _P], C.c_int),
+    "ug_op_cross_attention": ([_I, _P, _P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
@@ -125,4 +146,21 @@ def cfg_struct(cfg, dtype: int) -> ModelCfg:
     m.vae_norm_groups = v.norm_groups
     m.vae_eps, m.vae_temporal_eps, m.vae_scaling_factor = v.eps, v.temporal_eps, v.scaling_factor
     m.sigma_min, m.sigma_max, m.rho = cfg.sigma_min, cfg.sigma_max, cfg.rho
+    return m
+
+
+def unet2d_cfg_struct(sn_cfg) -> UNet2DCfg:
+    """unigeo_b200.config.StableNormalConfig -> ug_unet2d_cfg."""
+    u = sn_cfg.unet2d
+    m = UNet2DCfg()
+    m.in_channels, m.out_channels = u.in_channels, u.out_channels
+    m.num_blocks = len(u.block_out_channels)
+    for i, (c, h) in enumerate(zip(u.block_out_channels, u.num_attention_heads)):
+        m.block_out[i] = c
+        m.heads[i] = h
+    m.layers_per_block = u.layers_per_block
+    m.cross_attention_dim = u.cross_attention_dim
+    m.eps_resnet, m.eps_transformer_norm, m.ln_eps = u.eps_resnet, u.eps_transformer_norm, u.ln_eps
+    m.num_train_timesteps = sn_cfg.num_train_timesteps
+    m.beta_start, m.beta_end = sn_cfg.beta_start, sn_cfg.beta_end
     return m

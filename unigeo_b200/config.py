@@ -72,6 +72,48 @@ class PipelineConfig:
     decode_chunk_size: int = 8
 
 
+@dataclass(frozen=True)
+class UNet2DConfig:
+    """SD-2.1 class ``UNet2DConditionModel`` / ``ControlNetModel`` dims."""
+    in_channels: int = 4
+    out_channels: int = 4
+    block_out_channels: Tuple[int, ...] = (320, 640, 1280, 1280)
+    num_attention_heads: Tuple[int, ...] = (5, 10, 20, 20)    # head_dim 64 everywhere
+    layers_per_block: int = 2
+    cross_attention_dim: int = 1024
+    context_len: int = 77                                     # CLIP text tokens of the fixed prompt
+    norm_groups: int = 32
+    eps_resnet: float = 1e-5
+    eps_transformer_norm: float = 1e-6
+    ln_eps: float = 1e-5
+
+    @property
+    def time_embed_dim(self) -> int:
+        return self.block_out_channels[0] * 4
+
+
+@dataclass(frozen=True)
+class StableNormalConfig:
+    unet2d: UNet2DConfig = field(default_factory=UNet2DConfig)
+    vae2d: VAEConfig = field(default_factory=VAEConfig)       # AutoencoderKL: same encoder, 2-D decoder
+    num_train_timesteps: int = 1000
+    beta_start: float = 0.00085
+    beta_end: float = 0.012
+    num_inference_steps: int = 10
+    processing_multiple: int = 64                             # predictor resizes to a multiple of this
+
+
+def stablenormal_config(name: str = "full") -> StableNormalConfig:
+    if name == "full":
+        return StableNormalConfig()
+    if name == "tiny":
+        return StableNormalConfig(
+            unet2d=UNet2DConfig(block_out_channels=(64, 128, 256, 256), num_attention_heads=(1, 2, 4, 4),
+                                cross_attention_dim=64, context_len=13),
+            vae2d=VAEConfig(block_out_channels=(32, 64, 128, 128)))
+    raise ValueError(f"unknown config {name!r} (expected 'full' or 'tiny')")
+
+
 def full_config() -> PipelineConfig:
     return PipelineConfig()
 

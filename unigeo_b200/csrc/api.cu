@@ -107,6 +107,7 @@ int ug_ctx_destroy(ug_ctx* u) {
     if (u->c.ws.base) cudaFree(u->c.ws.base);
     delete u->c.unet;
     delete u->c.vae;
+    delete u->c.nets2d;
     delete u;
   });
 }
@@ -159,6 +160,7 @@ int ug_ctx_finalize(ug_ctx* u, void* stream) {
     UG_CUDA(cudaSetDevice(c.device));
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     unet_finalize(c, st);
+    unet2d_finalize(c, st);
     vae_finalize(c, st);
     UG_CUDA(cudaStreamSynchronize(st));
     c.finalized = true;
@@ -253,7 +255,7 @@ int ug_vae_encode(ug_ctx* u, const float* img, const float* noise, float noise_s
       if (!c.dry)
         op_check(c, launch_nchw_to_nhwc(img, noise, noise_strength, 1.f, 0.f, N, c.cfg.vae_in_channels, H, W, 8,
                                         img16, c.fmt, c.stream), "image in");
-      vae_encode(c, img16, N, H, W, lat_mean);
+      vae_encode(c, "vae.", img16, N, H, W, 1.f, lat_mean);
     });
   });
 }
@@ -271,6 +273,148 @@ int ug_vae_decode_temporal(ug_ctx* u, const float* lat, int T, int h, int w, int
         op_check(c, launch_nchw_to_nhwc(lat, nullptr, 0.f, 1.0f / c.cfg.vae_scaling_factor, 0.f, T,
                                         c.cfg.vae_latent_channels, h, w, 8, z16, c.fmt, c.stream), "latents in");
       vae_decode(c, z16, T, h, w, chunk, img);
+    });
+  });
+}
+
+// ------------------------------------------------------------------ StableNormal path (2-D UNet)
+int ug_ctx_set_unet2d_cfg(ug_ctx* u, const ug_unet2d_cfg* cfg) {
+  return guard([&] {
+    UG_CHECK(u && cfg, UG_ERR_INVALID, "null argument");
+    UG_CHECK(cfg->num_blocks >= 2 && cfg->num_blocks <= 4, UG_ERR_INVALID, "2-D UNet needs 2..4 blocks");
+    UG_CHECK(cfg->in_channels >= 1 && cfg->in_channels <= 8 && cfg->out_channels >= 1 && cfg->out_channels <= 8,
+             UG_ERR_INVALID, "2-D UNet I/O channels must be 1..8");
+    UG_CHECK(cfg->num_train_timesteps >= 1 && cfg->num_train_timesteps <= 100000, UG_ERR_INVALID,
+             "num_train_timesteps out of range");
+    u->c.cfg2d = *cfg;
+    u->c.finalized = false;
+  });
+}
+
+int ug_set_text_context(ug_ctx* u, const char* net_prefix, const float* tokens, int frames, int len, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && net_prefix && tokens, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_set_text_context");
+    const std::string P = norm_prefix(net_prefix);
+    run_sized(u, "textctx:" + std::to_string(frames) + "x" + std::to_string(len), stream,
+              [&](Ctx& c) { unet2d_set_context(c, P, tokens, frames, len); });
+  });
+}
+
+namespace {
+// fp32 NCHW [F][Cin][h][w] -> 16-bit tokens [F][hw][8]
+void* latents_to_tokens(Ctx& c, const float* x, int F, int h, int w, int Cin) {
+  void* x16 = c.alloc16((long long)F * h * w * 8);
+  if (!c.dry)
+    op_check(c, launch_nchw_to_nhwc(x, nullptr, 0.f, 1.f, 0.f, F, Cin, h, w, 8, x16, c.fmt, c.stream), "nchw_to_nhwc");
+  return x16;
+}
+}  // namespace
+
+int ug_unet2d_forward(ug_ctx* u, const char* unet_prefix, const float* x, int F, int h, int w, float timestep,
+                      const char* controlnet_prefix, const float* controlnet_sample, float* out, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && unet_prefix && x && out, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_unet2d_forward");
+    UG_CHECK(F >= 1 && h >= 1 && w >= 1, UG_ERR_INVALID, "bad shape");
+    UG_CHECK((controlnet_prefix == nullptr) == (controlnet_sample == nullptr), UG_ERR_INVALID,
+             "controlnet_prefix and controlnet_sample go together");
+    const std::string P = norm_prefix(unet_prefix), Q = norm_prefix(controlnet_prefix);
+    const std::string sig = "unet2d:" + P + Q + ":" + std::to_string(F) + "x" + std::to_string(h) + "x" + std::to_string(w);
+    run_sized(u, sig, stream, [&](Ctx& c) {
+      const int Ci = c.cfg2d.in_channels, Co = c.cfg2d.out_channels;
+      const long long hw = (long long)h * w;
+      void* x16 = latents_to_tokens(c, x, F, h, w, Ci);
+      void* c16 = controlnet_sample ? latents_to_tokens(c, controlnet_sample, F, h, w, Ci) : nullptr;
+      float* v = c.allocf(F * hw * Co);
+      unet2d_forward(c, P, x16, F, h, w, timestep, controlnet_prefix ? &Q : nullptr, c16, v);
+      if (!c.dry) op_check(c, launch_f32_nhwc_to_nchw(v, F, hw, Co, 1.f, out, c.stream), "f32 swap");
+    });
+  });
+}
+
+int ug_refine_frames_2d(ug_ctx* u, const char* unet_prefix, const char* controlnet_prefix, const float* image_latent,
+                        const float* latents_in, int F, int h, int w, int steps, int t_start, float* latents_out,
+                        void* stream) {
+  return guard([&] {
+    UG_CHECK(u && unet_prefix && latents_in && latents_out, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_refine_frames_2d");
+    UG_CHECK((controlnet_prefix == nullptr) || image_latent, UG_ERR_INVALID, "a ControlNet needs image_latent");
+    const ug_unet2d_cfg& g = u->c.cfg2d;
+    UG_CHECK(g.num_blocks > 0, UG_ERR_STATE, "ug_ctx_set_unet2d_cfg was not called");
+    UG_CHECK(g.in_channels == 4 && g.out_channels == 4, UG_ERR_INVALID, "refinement needs a 4 -> 4 channel UNet");
+    const int NT = g.num_train_timesteps;
+    UG_CHECK(steps >= 1 && steps <= NT && t_start < NT, UG_ERR_INVALID, "steps / t_start out of range");
+    // scaled-linear betas -> cumulative alpha products (double, like the host-side scheduler)
+    std::vector<double> ac(NT);
+    {
+      const double b0 = std::sqrt((double)g.beta_start), b1 = std::sqrt((double)g.beta_end);
+      double prod = 1.0;
+      for (int i = 0; i < NT; ++i) {
+        const double sb = NT > 1 ? b0 + (b1 - b0) * i / (NT - 1) : b0;
+        prod *= 1.0 - sb * sb;
+        ac[i] = prod;
+      }
+    }
+    const int top = t_start < 0 ? NT : t_start + 1;
+    std::vector<int> ts(steps);
+    for (int k = 0; k < steps; ++k) ts[k] = (int)std::nearbyint((double)top - (double)k * top / steps) - 1;
+    const std::string P = norm_prefix(unet_prefix), Q = norm_prefix(controlnet_prefix);
+    const std::string sig = "refine2d:" + P + Q + ":" + std::to_string(F) + "x" + std::to_string(h) + "x" + std::to_string(w);
+    run_sized(u, sig, stream, [&](Ctx& c) {
+      const long long hw = (long long)h * w, tok = hw * F;
+      float* lat = c.allocf(tok * 4);
+      float* x0 = c.allocf(tok * 4);
+      void* x16 = c.alloc16(tok * 8);
+      void* c16 = controlnet_prefix ? latents_to_tokens(c, image_latent, F, h, w, 4) : nullptr;
+      if (!c.dry) op_check(c, launch_f32_nchw_to_nhwc(latents_in, F, hw, 4, 1.f, lat, c.stream), "latents in");
+      const size_t mk = c.ws.mark();
+      const int n_iter = c.dry ? 1 : steps;
+      for (int i = 0; i < n_iter; ++i) {
+        c.ws.release(mk);
+        const int t = ts[i], tp = i + 1 < steps ? ts[i + 1] : -1;
+        UG_CHECK(t >= 0 && t < NT, UG_ERR_INVALID, "timestep out of range");
+        if (!c.dry) op_check(c, launch_f32_to_tokens(lat, 4, 8, tok, x16, c.fmt, c.stream), "unet input");
+        unet2d_forward(c, P, x16, F, h, w, (float)t, controlnet_prefix ? &Q : nullptr, c16, x0);
+        const double a_t = ac[t], a_p = tp >= 0 ? ac[tp] : 1.0;
+        const double cx = std::sqrt((1.0 - a_p) / (1.0 - a_t));
+        const double cx0 = std::sqrt(a_p) - std::sqrt(a_t) * cx;
+        if (!c.dry) op_check(c, launch_axpby(lat, x0, (float)cx0, (float)cx, tok * 4, c.stream), "ddim step");
+      }
+      if (!c.dry) op_check(c, launch_f32_nhwc_to_nchw(lat, F, hw, 4, 1.f, latents_out, c.stream), "latents out");
+    });
+  });
+}
+
+int ug_vae2d_encode(ug_ctx* u, const float* img, int N, int H, int W, float out_scale, float* lat, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && img && lat, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_vae2d_encode");
+    UG_CHECK(N >= 1 && H % 8 == 0 && W % 8 == 0, UG_ERR_INVALID, "H and W must be multiples of 8");
+    const std::string sig = "enc2d:" + std::to_string(N) + "x" + std::to_string(H) + "x" + std::to_string(W);
+    run_sized(u, sig, stream, [&](Ctx& c) {
+      void* img16 = c.alloc16((long long)N * H * W * 8);
+      if (!c.dry)
+        op_check(c, launch_nchw_to_nhwc(img, nullptr, 0.f, 1.f, 0.f, N, c.cfg.vae_in_channels, H, W, 8, img16, c.fmt,
+                                        c.stream), "image in");
+      vae_encode(c, "vae2d.", img16, N, H, W, out_scale, lat);
+    });
+  });
+}
+
+int ug_vae2d_decode(ug_ctx* u, const float* lat, int N, int h, int w, float* img, unsigned char* normals_u8,
+                    void* stream) {
+  return guard([&] {
+    UG_CHECK(u && lat && (img || normals_u8), UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_vae2d_decode");
+    UG_CHECK(N >= 1 && h >= 1 && w >= 1, UG_ERR_INVALID, "bad shape");
+    const std::string sig = "dec2d:" + std::to_string(N) + "x" + std::to_string(h) + "x" + std::to_string(w);
+    run_sized(u, sig, stream, [&](Ctx& c) {
+      void* z16 = c.alloc16((long long)N * h * w * 8);
+      if (!c.dry)
+        op_check(c, launch_nchw_to_nhwc(lat, nullptr, 0.f, 1.0f / c.cfg.vae_scaling_factor, 0.f, N,
+                                        c.cfg.vae_latent_channels, h, w, 8, z16, c.fmt, c.stream), "latents in");
+      vae2d_decode(c, z16, N, h, w, img, normals_u8);
     });
   });
 }
@@ -401,6 +545,15 @@ int ug_op_temporal_attention(int dtype, const void* qkv, int T, long long P, int
     ug_ctx* u = scratch_ctx(dtype);
     u->c.stream = reinterpret_cast<cudaStream_t>(stream);
     op_temporal_attention(u->c, qkv, y, T, P, C);
+  });
+}
+
+int ug_op_cross_attention(int dtype, const void* q, const void* kv, int F, int N, int C, int Lk, int kv_per_frame,
+                          void* y, void* stream) {
+  return guard([&] {
+    ug_ctx* u = scratch_ctx(dtype);
+    u->c.stream = reinterpret_cast<cudaStream_t>(stream);
+    op_cross_attention(u->c, q, C, kv, y, F, N, C, Lk, kv_per_frame);
   });
 }
 

@@ -81,6 +81,7 @@ struct Epi {                     // epilogue description for tapgemm-backed ops
 
 struct UNetModel;
 struct VaeModel;
+struct Nets2D;
 
 struct Ctx {
   int device = 0;
@@ -93,6 +94,8 @@ struct Ctx {
   long long launches = 0;        // kernels launched since the last reset (bench "gpu_launches")
   UNetModel* unet = nullptr;
   VaeModel* vae = nullptr;
+  ug_unet2d_cfg cfg2d{};         // StableNormal path (ug_ctx_set_unet2d_cfg); num_blocks == 0: not configured
+  Nets2D* nets2d = nullptr;
   bool finalized = false;
   unsigned int* gn_counters = nullptr;   // "last CTA" tickets of the fused GroupNorm finalize
   bool attn_materialized = false; // true: head_dim-64 attention through QK^T / softmax / PV GEMMs (A/B debug)
@@ -135,6 +138,9 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
 void op_layernorm(Ctx& c, const void* x, long long rows, int C, const float* g, const float* b, float eps,
                   const float* add, int add_div, void* y);
 void op_temporal_attention(Ctx& c, const void* qkv, void* out, int T, long long P, int C);
+// q [F*N][ldq] against kv [Fk*Lk][2C] (K | V), head_dim 64 -> out [F*N][C]
+void op_cross_attention(Ctx& c, const void* q, int ldq, const void* kv, void* out, int F, int N, int C, int Lk,
+                        int kv_per_frame);
 void op_upsample2x(Ctx& c, const void* x, void* y, int N, int H, int W, int C);
 void op_concat(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long rows, void* y);
 void op_gemv(Ctx& c, const void* Wm, const float* b, const float* addend, const float* x, float* out, int M,

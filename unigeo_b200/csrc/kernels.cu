@@ -243,9 +243,11 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void
 
 // ------------------------------------------------------------------ LayerNorm
 // A warp normalises ROWS rows at once (VPL 16-byte vectors per lane and row) so that enough loads are
-// in flight per SM to cover HBM latency; statistics are two-pass in registers.
+// in flight per SM to cover HBM latency.  Only the packed 16-bit vectors stay in registers (they are
+// unpacked again for each of the three passes: mean, variance, output), which keeps the kernel at
+// >= 3 CTAs (24 warps) per SM; statistics are two-pass in fp32.
 template <typename T, int VPL, int ROWS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, const float* __restrict__ add, int add_div,
                  void* __restrict__ y) {
@@ -256,47 +258,54 @@ layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float*
   if (row0 >= rows) return;
   const int nvec = C >> 3;
   const uint4* xb = reinterpret_cast<const uint4*>(x);
-  float f[ROWS][VPL][8];
   uint4 raw[ROWS][VPL];
 #pragma unroll
   for (int r = 0; r < ROWS; ++r)
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
       const int i = lane + 32 * k;
+      raw[r][k] = make_uint4(0u, 0u, 0u, 0u);
       if (row0 + r < rows && i < nvec) raw[r][k] = __ldg(xb + (row0 + r) * nvec + i);
     }
+  // value of vector (r, k) with the optional per-frame addend applied
+  auto value = [&](int r, int k, const float* addr, float (&f)[8]) {
+    unpack8<T>(raw[r][k], f);
+    if (addr) {
+      const int i = lane + 32 * k;
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(addr + i * 8));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(addr + i * 8) + 1);
+      f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
+      f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+    }
+  };
   float mean[ROWS], rstd[ROWS];
+  const float inv_c = 1.0f / (float)C;
 #pragma unroll
   for (int r = 0; r < ROWS; ++r) {
-    float s = 0.f;
     const bool rok = row0 + r < rows;
     const float* addr = (add && rok) ? add + ((row0 + r) / add_div) * C : nullptr;
+    float s = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      const int i = lane + 32 * k;
-      if (rok && i < nvec) {
-        unpack8<T>(raw[r][k], f[r][k]);
-        if (addr) {
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(addr + i * 8));
-          const float4 a1 = __ldg(reinterpret_cast<const float4*>(addr + i * 8) + 1);
-          f[r][k][0] += a0.x; f[r][k][1] += a0.y; f[r][k][2] += a0.z; f[r][k][3] += a0.w;
-          f[r][k][4] += a1.x; f[r][k][5] += a1.y; f[r][k][6] += a1.z; f[r][k][7] += a1.w;
-        }
+      if (rok && lane + 32 * k < nvec) {
+        float f[8];
+        value(r, k, addr, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s += f[r][k][j];
+        for (int j = 0; j < 8; ++j) s += f[j];
       }
     }
-    mean[r] = warp_sum(s) / (float)C;
+    mean[r] = warp_sum(s) * inv_c;
     float v = 0.f;
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {
-      const int i = lane + 32 * k;
-      if (rok && i < nvec) {
+      if (rok && lane + 32 * k < nvec) {
+        float f[8];
+        value(r, k, addr, f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = f[r][k][j] - mean[r]; v += d * d; }
+        for (int j = 0; j < 8; ++j) { const float d = f[j] - mean[r]; v += d * d; }
       }
     }
-    rstd[r] = rsqrtf(warp_sum(v) / (float)C + eps);
+    rstd[r] = rsqrtf(warp_sum(v) * inv_c + eps);
   }
   uint4* yb = reinterpret_cast<uint4*>(y);
 #pragma unroll
@@ -312,9 +321,11 @@ layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float*
 #pragma unroll
       for (int r = 0; r < ROWS; ++r) {
         if (row0 + r < rows) {
-          float o[8];
+          const float* addr = add ? add + ((row0 + r) / add_div) * C : nullptr;
+          float f[8], o[8];
+          value(r, k, addr, f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = (f[r][k][j] - mean[r]) * rstd[r] * gg[j] + bb[j];
+          for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean[r]) * rstd[r] * gg[j] + bb[j];
           yb[(row0 + r) * nvec + i] = pack8<T>(o);
         }
       }
@@ -521,6 +532,170 @@ temporal_attn_kernel(const void* __restrict__ qkv, void* __restrict__ out, int T
     asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(aQ + swz(row, c)));
     *reinterpret_cast<uint4*>(ob + ((long long)row * P + p) * C + h * 64 + c * 8) = v;
+  }
+}
+
+
+// ------------------------------------------------------------------ cross-attention (short context)
+// Attention of N queries per frame against a SHORT key/value set (Lk <= 128 tokens: the 77 CLIP text
+// tokens of StableNormal's fixed prompt).  CTA = 64 queries of one (frame, head): K and V of the head are
+// staged once in XOR-swizzled smem and shared by 4 warps of 16 queries each; S = Q K^T and O = P V run on
+// mma.sync m16n8k16 with the softmax in accumulator registers (same scheme as temporal attention).
+// HBM bound: Q read once, O written once, K/V come from L2.
+//   q  [F*N][ldq]   (head h at columns h*64..)          kv [Fk*Lk][2C]  (K | V; Fk = 1 when shared)
+template <typename T, int KPAD>
+__global__ void __launch_bounds__(128)
+cross_attn_kernel(const void* __restrict__ q, int ldq, const void* __restrict__ kv, void* __restrict__ out, int N,
+                  int C, int Lk, long long kv_frame_rows, float scale_log2e) {
+  pdl_launch_dependents();
+  pdl_wait();
+  extern __shared__ __align__(128) uint8_t sm_raw[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int h = blockIdx.y, f = blockIdx.z;
+  const int q0 = blockIdx.x * 64 + warp * 16;
+  const uint32_t aK = smem_u32(sm_raw), aV = aK + KPAD * 128, aQ = aV + KPAD * 128 + (uint32_t)warp * 16 * 128;
+  const uint16_t* kvb = reinterpret_cast<const uint16_t*>(kv) + (long long)f * kv_frame_rows * 2 * C;
+  const uint16_t* qb = reinterpret_cast<const uint16_t*>(q);
+
+  for (int i = threadIdx.x; i < 2 * KPAD * 8; i += 128) {        // K | V rows of this head
+    const int c = i & 7, row = (i >> 3) % KPAD, which = i / (8 * KPAD);
+    const uint32_t dst = aK + (uint32_t)which * KPAD * 128 + swz(row, c);
+    if (row < Lk) {
+      const uint16_t* src = kvb + (long long)row * 2 * C + which * C + h * 64 + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+    }
+  }
+  for (int i = lane; i < 16 * 8; i += 32) {                       // this warp's 16 query rows
+    const int c = i & 7, row = i >> 3;
+    const uint32_t dst = aQ + swz(row, c);
+    if (q0 + row < N) {
+      const uint16_t* src = qb + ((long long)f * N + q0 + row) * ldq + h * 64 + c * 8;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    } else {
+      asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(dst), "r"(0u) : "memory");
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+  if (q0 >= N) return;
+
+  constexpr int NT = KPAD / 8;
+  const int qr = lane >> 2, qc = (lane & 3) * 2;
+  float sacc[NT][4];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) { sacc[n][0] = sacc[n][1] = sacc[n][2] = sacc[n][3] = 0.f; }
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t af[4];
+    ldsm_x4(aQ + swz((lane & 7) + ((lane >> 3) & 1) * 8, ks * 2 + (lane >> 4)), af);
+#pragma unroll
+    for (int np = 0; np < NT / 2; ++np) {
+      uint32_t bf[4];
+      ldsm_x4(aK + swz(np * 16 + (lane & 7) + (lane >> 4) * 8, ks * 2 + ((lane >> 3) & 1)), bf);
+      MmaK16<T>::mma(sacc[2 * np], af, bf[0], bf[1]);
+      MmaK16<T>::mma(sacc[2 * np + 1], af, bf[2], bf[3]);
+    }
+  }
+  float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const bool ok = n * 8 + qc + e < Lk;
+      sacc[n][e] = ok ? sacc[n][e] * scale_log2e : -INFINITY;
+      sacc[n][2 + e] = ok ? sacc[n][2 + e] * scale_log2e : -INFINITY;
+      m0 = fmaxf(m0, sacc[n][e]);
+      m1 = fmaxf(m1, sacc[n][2 + e]);
+    }
+  }
+  m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+  m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+  float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+  for (int n = 0; n < NT; ++n) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      sacc[n][e] = exp2f(sacc[n][e] - m0); s0 += sacc[n][e];
+      sacc[n][2 + e] = exp2f(sacc[n][2 + e] - m1); s1 += sacc[n][2 + e];
+    }
+  }
+  s0 += __shfl_xor_sync(0xffffffffu, s0, 1); s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 1); s1 += __shfl_xor_sync(0xffffffffu, s1, 2);
+  const float i0 = 1.0f / s0, i1 = 1.0f / s1;
+  float oacc[8][4];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) { oacc[n][0] = oacc[n][1] = oacc[n][2] = oacc[n][3] = 0.f; }
+#pragma unroll
+  for (int kk = 0; kk < KPAD / 16; ++kk) {
+    uint32_t pf[4];
+    pf[0] = Elem<T>::pack2(sacc[2 * kk][0] * i0, sacc[2 * kk][1] * i0);
+    pf[1] = Elem<T>::pack2(sacc[2 * kk][2] * i1, sacc[2 * kk][3] * i1);
+    pf[2] = Elem<T>::pack2(sacc[2 * kk + 1][0] * i0, sacc[2 * kk + 1][1] * i0);
+    pf[3] = Elem<T>::pack2(sacc[2 * kk + 1][2] * i1, sacc[2 * kk + 1][3] * i1);
+#pragma unroll
+    for (int np = 0; np < 4; ++np) {
+      uint32_t vf[4];
+      ldsm_x4_trans(aV + swz(kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8, np * 2 + (lane >> 4)), vf);
+      MmaK16<T>::mma(oacc[2 * np], pf, vf[0], vf[1]);
+      MmaK16<T>::mma(oacc[2 * np + 1], pf, vf[2], vf[3]);
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    const uint32_t w0 = Elem<T>::pack2(oacc[n][0], oacc[n][1]), w1 = Elem<T>::pack2(oacc[n][2], oacc[n][3]);
+    const uint32_t a0 = aQ + swz(qr, n) + qc * 2, a1 = aQ + swz(qr + 8, n) + qc * 2;
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a0), "r"(w0) : "memory");
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(a1), "r"(w1) : "memory");
+  }
+  __syncwarp();
+  uint16_t* ob = reinterpret_cast<uint16_t*>(out);
+  for (int i = lane; i < 16 * 8; i += 32) {
+    const int c = i & 7, row = i >> 3;
+    if (q0 + row >= N) continue;
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(aQ + swz(row, c)));
+    *reinterpret_cast<uint4*>(ob + ((long long)f * N + q0 + row) * C + h * 64 + c * 8) = v;
+  }
+}
+
+// ------------------------------------------------------------------ 2-D (StableNormal) scheduler glue
+// DDIM step, prediction_type = "sample", eta = 0, in place on fp32 latents:
+//   x <- c_x0 * x0 + c_x * x   with  c_x = sqrt((1-a_prev)/(1-a_t)),  c_x0 = sqrt(a_prev) - sqrt(a_t) * c_x
+__global__ void axpby_kernel(float* __restrict__ x, const float* __restrict__ x0, float c_x0, float c_x,
+                             long long n) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = c_x0 * x0[i] + c_x * x[i];
+}
+// fp32 [tokens][Cs] -> 16-bit [tokens][Cd] (Cd >= Cs, zero padded): the UNet input of the 2-D path
+template <typename T>
+__global__ void f32_to_tokens_kernel(const float* __restrict__ x, int Cs, int Cd, long long tokens, T* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long n = tokens * Cd;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long t = i / Cd;
+    const int c = (int)(i % Cd);
+    y[i] = Elem<T>::from_f(c < Cs ? x[t * Cs + c] : 0.f);
+  }
+}
+// decoded normals: 16-bit NHWC [N][HW][Cs] (3 valid) -> unit vectors, clip, 8-bit HWC [N][HW][3]
+template <typename T>
+__global__ void normals_to_u8_kernel(const T* __restrict__ x, int Cs, long long pixels, uint8_t* __restrict__ y) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+    const float a = Elem<T>::to_f(x[i * Cs]), b = Elem<T>::to_f(x[i * Cs + 1]), c = Elem<T>::to_f(x[i * Cs + 2]);
+    const float inv = 1.0f / fmaxf(sqrtf(a * a + b * b + c * c), 1e-6f);
+    const float v[3] = {a * inv, b * inv, c * inv};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) y[i * 3 + k] = (uint8_t)((fminf(fmaxf(v[k], -1.f), 1.f) + 1.f) * 0.5f * 255.f);
   }
 }
 
@@ -839,6 +1014,44 @@ int launch_temporal_attention(const void* qkv, void* out, int Tn, long long P, i
     });
   }
   return last_err();
+}
+
+int launch_cross_attention(const void* q, int ldq, const void* kv, void* out, int F, int N, int C, int Lk,
+                           int kv_per_frame, float scale, int fmt, cudaStream_t st) {
+  if ((C & 63) || (ldq & 7) || Lk < 1 || Lk > 128 || N < 1) return (int)cudaErrorInvalidValue;
+  const int kpad = (Lk + 15) & ~15;
+  const dim3 grid((N + 63) / 64, C / 64, F);
+  const size_t smem = (size_t)(2 * kpad + 64) * 128;
+  const float sl = scale * 1.4426950408889634f;
+  const long long fr = kv_per_frame ? Lk : 0;
+  cudaError_t err = cudaErrorInvalidValue;
+#define UG_XATTN(KP)                                                                                             \
+  case KP:                                                                                                       \
+    UG_DISPATCH_FMT(fmt, (err = launch_pdl(cross_attn_kernel<T, KP>, grid, dim3(128), smem, st, q, ldq, kv, out, N, C, \
+                                           Lk, fr, sl)));                                                        \
+    break;
+  switch (kpad) {
+    UG_XATTN(16) UG_XATTN(32) UG_XATTN(48) UG_XATTN(64) UG_XATTN(80) UG_XATTN(96) UG_XATTN(112) UG_XATTN(128)
+    default: break;
+  }
+#undef UG_XATTN
+  return (int)err;
+}
+
+int launch_axpby(float* x, const float* x0, float c_x0, float c_x, long long n, cudaStream_t st) {
+  return (int)launch_pdl(axpby_kernel, dim3(grid_for(n, 256)), dim3(256), 0, st, x, x0, c_x0, c_x, n);
+}
+int launch_f32_to_tokens(const float* x, int Cs, int Cd, long long tokens, void* y, int fmt, cudaStream_t st) {
+  cudaError_t err;
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl(f32_to_tokens_kernel<T>, dim3(grid_for(tokens * Cd, 256)), dim3(256), 0, st, x,
+                                         Cs, Cd, tokens, reinterpret_cast<T*>(y))));
+  return (int)err;
+}
+int launch_normals_to_u8(const void* x, int Cs, long long pixels, unsigned char* y, int fmt, cudaStream_t st) {
+  cudaError_t err;
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl(normals_to_u8_kernel<T>, dim3(grid_for(pixels, 256)), dim3(256), 0, st,
+                                         reinterpret_cast<const T*>(x), Cs, pixels, y)));
+  return (int)err;
 }
 
 int launch_upsample2x(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st) {

@@ -39,6 +39,17 @@ int launch_softmax_rows(void* s, long long rows, int n, float scale, int fmt, cu
 int launch_temporal_attention(const void* qkv, void* out, int T, long long P, int C, float scale, int fmt,
                               cudaStream_t st);
 
+// ---- cross-attention against a short context (Lk <= 128 keys), head_dim 64 --------------
+// q [F*N][ldq]; kv [Fk*Lk][2C] (K | V), Fk = F when kv_per_frame else 1; out [F*N][C].
+int launch_cross_attention(const void* q, int ldq, const void* kv, void* out, int F, int N, int C, int Lk,
+                           int kv_per_frame, float scale, int fmt, cudaStream_t st);
+// x <- c_x0 * x0 + c_x * x (DDIM "sample"-prediction step on fp32 latents)
+int launch_axpby(float* x, const float* x0, float c_x0, float c_x, long long n, cudaStream_t st);
+// fp32 [tokens][Cs] -> 16-bit [tokens][Cd], zero padded channels
+int launch_f32_to_tokens(const float* x, int Cs, int Cd, long long tokens, void* y, int fmt, cudaStream_t st);
+// 16-bit [pixels][Cs] (3 valid) -> unit normals -> uint8 [pixels][3]
+int launch_normals_to_u8(const void* x, int Cs, long long pixels, unsigned char* y, int fmt, cudaStream_t st);
+
 // ---- layout / elementwise -------------------------------------------------------------
 int launch_upsample2x(const void* x, void* y, int N, int H, int W, int C, cudaStream_t st);   // nearest
 int launch_concat(const void* x1, int C1, const void* x2, int C2, long long rows, void* y, cudaStream_t st);

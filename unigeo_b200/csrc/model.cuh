@@ -27,6 +27,21 @@ struct VaeModel {
   int dummy = 0;
 };
 
+// One 2-D conditional UNet or ControlNet (StableNormal path), addressed by its weight-key prefix.
+struct Net2D {
+  std::string prefix;                                   // "unet2d." / "controlnet." / ...
+  bool controlnet = false;
+  std::unordered_map<std::string, int> temb_offset;     // resnet key -> offset in temb_out
+  int temb_total = 0;
+  float* temb_out = nullptr;                            // per-step conv1 biases of every resnet
+  float* scratch = nullptr;
+  std::unordered_map<std::string, void*> kv;            // transformer key -> K | V of the context [Fk*Lk][2C]
+  int ctx_len = 0, ctx_frames = 0;
+};
+struct Nets2D {
+  std::unordered_map<std::string, Net2D> nets;
+};
+
 // shared blocks -------------------------------------------------------------------------
 // ResnetBlock2D on x = [x1 | x2] (x2 optional): returns new activation [frames][HW][cout].
 // bias1: per-step (time-embedding) bias for conv1, or nullptr -> conv1.bias.
@@ -46,9 +61,22 @@ void unet_set_clip_context(Ctx& c, const float* enc, cudaStream_t st);
 // x16: [T][hw][8] 16-bit; v_out: fp32 [T][hw][4]
 void unet_forward(Ctx& c, const void* x16, float timestep, const float ids[3], float* v_out);
 
+std::string norm_prefix(const char* p);   // "unet2d" / "unet2d." -> "unet2d."
+void unet2d_finalize(Ctx& c, cudaStream_t st);
+// tokens fp32 [frames][len][cross_attention_dim] -> K | V of every cross-attention of network `prefix`
+void unet2d_set_context(Ctx& c, const std::string& prefix, const float* tokens, int frames, int len);
+// x16 / ctrl_x16: [F][hw][8] 16-bit (in_channels valid); out_tokens fp32 [F][hw][out_channels]
+void unet2d_forward(Ctx& c, const std::string& prefix, const void* x16, int F, int h, int w, float timestep,
+                    const std::string* ctrl_prefix, const void* ctrl_x16, float* out_tokens);
+
 void vae_finalize(Ctx& c, cudaStream_t st);
-// img16 [N][H][W][8] 16-bit (3 valid channels) -> lat fp32 NCHW [N][4][H/8][W/8]
-void vae_encode(Ctx& c, const void* img16, int N, int H, int W, float* lat_nchw);
+// V = "vae." (SVD temporal-decoder VAE) or "vae2d." (AutoencoderKL of the StableNormal path)
+// img16 [N][H][W][8] 16-bit (3 valid channels) -> lat fp32 NCHW [N][4][H/8][W/8] * out_scale
+void vae_encode(Ctx& c, const std::string& V, const void* img16, int N, int H, int W, float out_scale,
+                float* lat_nchw);
+// 2-D decoder ("vae2d."): z16 [N][h*w][8] (4 valid, already / scaling) -> img fp32 NCHW [N][3][8h][8w] (nullable)
+// and / or 8-bit unit normals [N][8h][8w][3] (nullable)
+void vae2d_decode(Ctx& c, const void* z16, int N, int h, int w, float* img_nchw, unsigned char* normals_u8);
 // z16 [T][h*w][8] (4 valid, already / scaling) -> img fp32 NCHW [T][3][8h][8w]
 void vae_decode(Ctx& c, const void* z16, int T, int h, int w, int chunk, float* img_nchw);
 

@@ -56,6 +56,12 @@ void Ctx::prof_mark(const char* name, double flops, double bytes) {
   prof.push_back({name, flops, bytes, ev});
 }
 
+// profile row name: `what` or, in by-shape mode, `what` + " " + shape (interned for the run)
+static const char* prof_name(Ctx& c, const char* what, const std::string& shape) {
+  if (!(c.profile && c.profile_shapes)) return what;
+  return c.prof_names.insert(std::string(what) + " " + shape).first->c_str();
+}
+
 void op_check(Ctx& c, int err, const char* what, double flops, double bytes) {
   if (err != 0)
     throw UgError(UG_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString((cudaError_t)err) + " (" +
@@ -335,7 +341,9 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
     fa.N = N; fa.C = C; fa.heads = heads; fa.F = F;
     fa.scale_log2 = 1.4426950408889634f / sqrtf((float)dh);
     fa.out = out; fa.fmt = c.fmt;
-    op_check(c, launch_fmha_d64(tm, fa, c.stream), "fmha_d64", 4.0 * F * heads * (double)N * N * dh,
+    op_check(c, launch_fmha_d64(tm, fa, c.stream),
+             prof_name(c, "fmha_d64", "F" + std::to_string(F) + " N" + std::to_string(N) + " heads" + std::to_string(heads)),
+             4.0 * F * heads * (double)N * N * dh,
              8.0 * F * (double)N * C);
     return;
   }
@@ -410,7 +418,6 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
   const int G = c.cfg.norm_groups;
   const long long sets = rows / rows_per_set;
   const size_t m = c.ws.mark();
-  (void)sets;
   float* stats = c.allocf(gn_partial_floats(C1 + C2, rows, rows_per_set, G));
   if (!c.dry) {
     if (!c.gn_counters) {
@@ -418,23 +425,33 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
       UG_CUDA(cudaMemset(c.gn_counters, 0, kGnMaxSets * sizeof(unsigned int)));
     }
     op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, eps, stats, c.gn_counters, c.fmt, c.stream),
-             "gn_stats", 0.0, 2.0 * rows * (C1 + C2));
+             prof_name(c, "gn_stats", "rows" + std::to_string(rows) + " C" + std::to_string(C1 + C2) + " sets" + std::to_string(sets)),
+             0.0, 2.0 * rows * (C1 + C2));
     op_check(c, launch_gn_apply(x1, C1, x2, C2, rows, rows_per_set, G, stats, gamma, beta, eps, silu, y, c.fmt,
                                 c.stream),
-             "gn_apply", 0.0, 4.0 * rows * (C1 + C2));
+             prof_name(c, "gn_apply", "rows" + std::to_string(rows) + " C" + std::to_string(C1 + C2) + " sets" + std::to_string(sets)),
+             0.0, 4.0 * rows * (C1 + C2));
   }
   c.ws.release(m);
 }
 void op_layernorm(Ctx& c, const void* x, long long rows, int C, const float* g, const float* b, float eps,
                   const float* add, int add_div, void* y) {
   if (c.dry) return;
-  op_check(c, launch_layernorm(x, rows, C, g, b, eps, add, add_div, y, c.fmt, c.stream), "layernorm", 0.0,
-           4.0 * rows * C);
+  op_check(c, launch_layernorm(x, rows, C, g, b, eps, add, add_div, y, c.fmt, c.stream),
+           prof_name(c, "layernorm", "rows" + std::to_string(rows) + " C" + std::to_string(C)), 0.0, 4.0 * rows * C);
 }
 void op_temporal_attention(Ctx& c, const void* qkv, void* out, int T, long long P, int C) {
   if (c.dry) return;
-  op_check(c, launch_temporal_attention(qkv, out, T, P, C, 0.125f, c.fmt, c.stream), "temporal_attention",
+  op_check(c, launch_temporal_attention(qkv, out, T, P, C, 0.125f, c.fmt, c.stream),
+           prof_name(c, "temporal_attention", "P" + std::to_string(P) + " C" + std::to_string(C)),
            4.0 * T * T * 64.0 * P * (C / 64), 8.0 * T * P * C);
+}
+void op_cross_attention(Ctx& c, const void* q, int ldq, const void* kv, void* out, int F, int N, int C, int Lk,
+                        int kv_per_frame) {
+  if (c.dry) return;
+  op_check(c, launch_cross_attention(q, ldq, kv, out, F, N, C, Lk, kv_per_frame, 0.125f, c.fmt, c.stream),
+           prof_name(c, "cross_attention", "F" + std::to_string(F) + " N" + std::to_string(N) + " C" + std::to_string(C)),
+           4.0 * F * (double)N * Lk * C, 4.0 * F * (double)N * C);
 }
 void op_upsample2x(Ctx& c, const void* x, void* y, int N, int H, int W, int C) {
   if (c.dry) return;

@@ -30,7 +30,7 @@ def _f32(t: torch.Tensor, device) -> torch.Tensor:
 class Engine:
     """One context = one GPU = one model replica (clip-sharded data parallelism above it)."""
 
-    def __init__(self, cfg: PipelineConfig, dtype: str = "fp16", device: int = 0):
+    def __init__(self, cfg: PipelineConfig, dtype: str = "fp16", device: int = 0, sn_cfg=None):
         if not torch.cuda.is_available():
             raise RuntimeError("unigeo_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
         if dtype not in _DTYPES:
@@ -44,6 +44,12 @@ class Engine:
         _lib.check(self.lib.ug_ctx_create(C.byref(self._ctx), device, C.byref(self._cfg_struct)))
         self._shape: Tuple[int, int, int] | None = None
         self._finalized = False
+        self.sn_cfg = sn_cfg
+        if sn_cfg is not None:       # StableNormal path: 2-D UNet / ControlNet dims (the 2-D VAE uses cfg.vae)
+            if sn_cfg.unet2d.norm_groups != cfg.unet.norm_groups or sn_cfg.vae2d != cfg.vae:
+                raise ValueError("the 2-D path shares GroupNorm groups and VAE dims with the pipeline config")
+            self._cfg2d = _lib.unet2d_cfg_struct(sn_cfg)
+            _lib.check(self.lib.ug_ctx_set_unet2d_cfg(self._ctx, C.byref(self._cfg2d)))
 
     # ------------------------------------------------------------------ weights
     def load_state_dict(self, prefix: str, sd: Dict[str, torch.Tensor]) -> None:
@@ -139,6 +145,76 @@ class Engine:
             _lib.check(self.lib.ug_vae_decode_temporal(self._ctx, lat.data_ptr(), T, h, w, int(chunk),
                                                        out.data_ptr(), _stream()))
         return out
+
+    # ------------------------------------------------------------------ StableNormal path (2-D UNet)
+    def set_text_context(self, net: str, tokens: torch.Tensor) -> None:
+        """tokens [L,D] (shared prompt) or [F,L,D]: encoder_hidden_states of network ``net`` ("unet2d", ...)."""
+        if not self._finalized:
+            self.finalize()
+        t = _f32(tokens, self.device)
+        if t.dim() == 2:
+            t = t.unsqueeze(0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_set_text_context(self._ctx, net.encode(), t.data_ptr(), t.shape[0], t.shape[1],
+                                                    _stream()))
+
+    def unet2d_forward(self, net: str, x: torch.Tensor, timestep: float, controlnet: str | None = None,
+                       controlnet_sample: torch.Tensor | None = None) -> torch.Tensor:
+        """x [F,Cin,h,w] -> [F,Cout,h,w]; with ``controlnet`` its residuals (computed from
+        ``controlnet_sample``) are added to the skips / mid block."""
+        if not self._finalized:
+            self.finalize()
+        x = _f32(x, self.device)
+        F_, _, h, w = x.shape
+        out = torch.empty((F_, self.sn_cfg.unet2d.out_channels, h, w), dtype=torch.float32, device=self.device)
+        cs = _f32(controlnet_sample, self.device) if controlnet is not None else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_unet2d_forward(self._ctx, net.encode(), x.data_ptr(), F_, h, w, float(timestep),
+                                                  controlnet.encode() if controlnet else None,
+                                                  cs.data_ptr() if cs is not None else None, out.data_ptr(),
+                                                  _stream()))
+        return out
+
+    def refine_2d(self, net: str, controlnet: str | None, image_latent: torch.Tensor | None,
+                  latents: torch.Tensor, steps: int, t_start: int = -1) -> torch.Tensor:
+        """DDIM ("sample" prediction) refinement loop over [F,4,h,w] latents."""
+        if not self._finalized:
+            self.finalize()
+        lat = _f32(latents, self.device)
+        F_, _, h, w = lat.shape
+        il = _f32(image_latent, self.device) if image_latent is not None else None
+        out = torch.empty_like(lat)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_refine_frames_2d(self._ctx, net.encode(), controlnet.encode() if controlnet else None,
+                                                    il.data_ptr() if il is not None else None, lat.data_ptr(), F_, h, w,
+                                                    int(steps), int(t_start), out.data_ptr(), _stream()))
+        return out
+
+    def vae2d_encode(self, img: torch.Tensor, out_scale: float = 1.0) -> torch.Tensor:
+        """img [N,3,H,W] in [-1,1] -> latent mode * out_scale [N,4,H/8,W/8] ("vae2d" weights)."""
+        if not self._finalized:
+            self.finalize()
+        img = _f32(img, self.device)
+        N, _, H, W = img.shape
+        out = torch.empty((N, self.cfg.vae.latent_channels, H // 8, W // 8), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_vae2d_encode(self._ctx, img.data_ptr(), N, H, W, float(out_scale), out.data_ptr(),
+                                                _stream()))
+        return out
+
+    def vae2d_decode(self, latents: torch.Tensor, want_image: bool = True, want_normals_u8: bool = False):
+        """latents [N,4,h,w] (scaled) -> (image [N,3,8h,8w] fp32 | None, unit normals uint8 [N,8h,8w,3] | None)."""
+        if not self._finalized:
+            self.finalize()
+        lat = _f32(latents, self.device)
+        N, _, h, w = lat.shape
+        img = torch.empty((N, 3, 8 * h, 8 * w), dtype=torch.float32, device=self.device) if want_image else None
+        nrm = torch.empty((N, 8 * h, 8 * w, 3), dtype=torch.uint8, device=self.device) if want_normals_u8 else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_vae2d_decode(self._ctx, lat.data_ptr(), N, h, w,
+                                                img.data_ptr() if img is not None else None,
+                                                nrm.data_ptr() if nrm is not None else None, _stream()))
+        return img, nrm
 
     # ------------------------------------------------------------------ bookkeeping
     def launch_count(self, reset: bool = False) -> int:

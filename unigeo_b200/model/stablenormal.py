@@ -1,15 +1,19 @@
 """``StableNormal`` plugin adapter (reference: /root/reference/model/stablenormal.py).
 
-The reference pulls ``Stable-X/StableNormal`` through ``torch.hub.load`` (:16, network) and its
-arithmetic (YOSO init + SD-2.1 UNet/ControlNet + DINOv2) is not available in
-this environment in any form.  What IS in-tree and reproduced here exactly is the adapter-side
-contract: per-frame 8-bit predictor output, the uint8 x-flip wraparound (:43, App. B.10),
-``/255*2-1`` (:45) and zero depths (:49).  The predictor is injectable: any callable
-``PIL.Image -> PIL.Image`` (the hub predictor's signature, :39).  The 2-D UNet kernels it needs
-are the spatial half of the DepthCrafter path (conv3x3 / GroupNorm / attention / GEGLU in
-libunigeo_b200.so); wiring a 2-D SD UNet graph over them is listed as "next" in DESIGN.md.
+The reference pulls ``Stable-X/StableNormal`` through ``torch.hub.load`` (:16, network) and calls
+``predictor(PIL image) -> PIL image`` per frame (:39).  Here the predictor is the B200 engine:
+2-D VAE encode -> [YOSO one-step start] -> DDIM refinement with the SD-2.1 class UNet + ControlNet ->
+2-D VAE decode -> 8-bit unit normals (``unigeo_b200/pipeline_stablenormal.py``, all frames of the clip
+in one batch).  The adapter-side contract is reproduced exactly: per-frame 8-bit predictor output, the
+uint8 x-flip wraparound (:43, App. B.10), ``/255*2-1`` (:45) and zero depths (:49).
+``model_params`` (ride in **kwargs like the reference tolerates): ``config="full"|"tiny"``,
+``dtype``, ``num_inference_steps=10``, ``seed``, ``weights="synthetic"|<dir>``, ``controlnet=True``,
+``yoso=False``, ``device=0``; or ``predictor=<callable PIL -> PIL>`` to inject one (the hub signature).
+There is no CPU path: constructing this class without a B200 (and without ``predictor``) raises.
 """
 from __future__ import annotations
+
+import os
 
 import numpy as np
 import torch
@@ -17,11 +21,46 @@ import torch
 
 class StableNormal:
     def __init__(self, model_dir=None, predictor=None, **kwargs):
-        if predictor is None:
-            raise RuntimeError(
-                "StableNormal needs a predictor (PIL.Image -> PIL.Image); the reference obtains it with "
-                "torch.hub.load('Stable-X/StableNormal', ...) which is unavailable offline")
         self.predictor = predictor
+        self.pipeline = None
+        if predictor is not None:
+            return
+        from ..config import get_config, stablenormal_config
+        from ..engine import Engine
+        from ..pipeline_stablenormal import StableNormalPipelineB200 as P
+        from ..weights import (controlnet_param_shapes, load_diffusers_dir, synthetic_state_dict,
+                               unet2d_param_shapes, vae2d_param_shapes)
+        name = kwargs.get("config", "full")
+        self.sn_cfg = stablenormal_config(name)
+        self.device = torch.device("cuda", int(kwargs.get("device", 0)))
+        self.num_inference_steps = int(kwargs.get("num_inference_steps", self.sn_cfg.num_inference_steps))
+        self.seed = kwargs.get("seed")
+        use_ctrl, use_yoso = bool(kwargs.get("controlnet", True)), bool(kwargs.get("yoso", False))
+        self.engine = Engine(get_config(name), dtype=kwargs.get("dtype", "fp16"), device=self.device.index,
+                             sn_cfg=self.sn_cfg)
+        nets = [(P.UNET, unet2d_param_shapes)] + ([(P.CONTROLNET, controlnet_param_shapes)] if use_ctrl else [])
+        if use_yoso:
+            nets += [(P.YOSO_UNET, unet2d_param_shapes)] + ([(P.YOSO_CONTROLNET, controlnet_param_shapes)] if use_ctrl else [])
+        weights = kwargs.get("weights", "synthetic")
+        u = self.sn_cfg.unet2d
+        if weights == "synthetic":
+            s = int(kwargs.get("weight_seed", 0))
+            wdev = self.device if kwargs.get("device_weights") else "cpu"
+            wdt = torch.float16 if kwargs.get("device_weights") else torch.float32
+            for i, (net, shapes) in enumerate(nets):
+                self.engine.load_state_dict(net, synthetic_state_dict(shapes(u), 3000 + 10 * i + s, wdt, wdev))
+            self.engine.load_state_dict("vae2d", synthetic_state_dict(vae2d_param_shapes(self.sn_cfg.vae2d), 4000 + s,
+                                                                      wdt, wdev))
+            g = torch.Generator().manual_seed(5000 + s)
+            prompt = torch.randn(u.context_len, u.cross_attention_dim, generator=g)
+        else:                                  # a directory laid out like the hub checkpoint
+            for net, _ in nets:
+                self.engine.load_state_dict(net, load_diffusers_dir(os.path.join(weights, net)))
+            self.engine.load_state_dict("vae2d", load_diffusers_dir(os.path.join(weights, "vae")))
+            prompt = torch.load(os.path.join(weights, "prompt_embeds.pt")).float().reshape(-1, u.cross_attention_dim)
+        self.engine.finalize()
+        self.pipeline = P(self.sn_cfg, self.engine, prompt, controlnet=use_ctrl, yoso=use_yoso)
+        print(f"Using device: {self.device}")
 
     def prepare_input(self, data):
         frames = [np.asarray(x).transpose(1, 2, 0).astype(np.uint8) for x in data["images"]]
@@ -38,8 +77,16 @@ class StableNormal:
         pn = torch.stack(out, dim=0)
         return {"pred_normals": pn, "pred_depths": torch.zeros_like(pn[..., 0])}
 
-    def forward(self, data):
-        from PIL import Image
-        images = [Image.fromarray(np.asarray(x).transpose(1, 2, 0).astype(np.uint8)) for x in data["images"]]
-        preds = [np.array(self.predictor(im)) for im in images]
-        return self.postprocess(preds)
+    def forward(self, data, **debug_inputs):
+        """``debug_inputs``: ``init_noise`` [F,4,h,w] to pin the random draw (parity tests)."""
+        if self.predictor is not None:
+            from PIL import Image
+            images = [Image.fromarray(np.asarray(x).transpose(1, 2, 0).astype(np.uint8)) for x in data["images"]]
+            preds = [np.array(self.predictor(im)) for im in images]
+            return self.postprocess(preds)
+        frames = np.stack([np.asarray(x).transpose(1, 2, 0).astype(np.uint8) for x in data["images"]], axis=0)
+        gen = None
+        if self.seed is not None:
+            gen = torch.Generator(device=self.device).manual_seed(int(self.seed))
+        normals = self.pipeline(frames, self.num_inference_steps, generator=gen, **debug_inputs)
+        return self.postprocess(list(normals.cpu().numpy()))

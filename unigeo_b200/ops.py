@@ -104,3 +104,12 @@ def temporal_attention(qkv, T, P, C):
     y = torch.empty((T, P, C), device=qkv.device, dtype=qkv.dtype)
     _lib.check(_lib.load().ug_op_temporal_attention(d, qkv.data_ptr(), T, P, C, y.data_ptr(), _s()))
     return y
+
+
+def cross_attention(q, kv, F, N, C, Lk, kv_per_frame=False):
+    """q [F*N,C], kv [Fk*Lk,2C] (K | V; Fk = F if kv_per_frame else 1) -> [F*N,C]; heads of 64, Lk <= 128."""
+    d = _chk16(q, kv)
+    y = torch.empty((F * N, C), device=q.device, dtype=q.dtype)
+    _lib.check(_lib.load().ug_op_cross_attention(d, q.data_ptr(), kv.data_ptr(), F, N, C, Lk, int(kv_per_frame),
+                                                 y.data_ptr(), _s()))
+    return y

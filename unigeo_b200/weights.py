@@ -15,7 +15,7 @@ from typing import Dict, Tuple
 
 import torch
 
-from .config import UNetSTConfig, VAEConfig
+from .config import UNet2DConfig, UNetSTConfig, VAEConfig
 
 Shapes = "OrderedDict[str, Tuple[int, ...]]"
 
@@ -194,6 +194,106 @@ def vae_param_shapes(cfg: VAEConfig) -> Shapes:
     _norm(d, "decoder.conv_norm_out", boc[0])
     _conv(d, "decoder.conv_out", boc[0], cfg.in_channels, 3)
     _conv3d(d, "decoder.time_conv_out", cfg.in_channels, cfg.in_channels)
+    return d
+
+
+# --------------------------------------------------------------------------- 2-D UNet / ControlNet / VAE
+def _transformer2d(d, key, c, ctx):
+    _norm(d, key + ".norm", c)
+    _lin(d, key + ".proj_in", c, c)
+    b = key + ".transformer_blocks.0"
+    _norm(d, b + ".norm1", c)
+    _attention(d, b + ".attn1", c, c)
+    _norm(d, b + ".norm2", c)
+    _attention(d, b + ".attn2", c, ctx)
+    _norm(d, b + ".norm3", c)
+    _feed_forward(d, b + ".ff", c)
+    _lin(d, key + ".proj_out", c, c)
+
+
+def _encoder_half_2d(d, cfg: UNet2DConfig):
+    boc = cfg.block_out_channels
+    temb, ctx, nb = cfg.time_embed_dim, cfg.cross_attention_dim, len(boc)
+    _conv(d, "conv_in", cfg.in_channels, boc[0], 3)
+    _lin(d, "time_embedding.linear_1", boc[0], temb)
+    _lin(d, "time_embedding.linear_2", temb, temb)
+    skip_channels = [boc[0]]
+    cout = boc[0]
+    for i in range(nb):
+        cin, cout = cout, boc[i]
+        for j in range(cfg.layers_per_block):
+            _resnet2d(d, f"down_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout, temb)
+            if i < nb - 1:
+                _transformer2d(d, f"down_blocks.{i}.attentions.{j}", cout, ctx)
+            skip_channels.append(cout)
+        if i < nb - 1:
+            _conv(d, f"down_blocks.{i}.downsamplers.0.conv", cout, cout, 3)
+            skip_channels.append(cout)
+    _resnet2d(d, "mid_block.resnets.0", boc[-1], boc[-1], temb)
+    _transformer2d(d, "mid_block.attentions.0", boc[-1], ctx)
+    _resnet2d(d, "mid_block.resnets.1", boc[-1], boc[-1], temb)
+    return skip_channels
+
+
+def unet2d_param_shapes(cfg: UNet2DConfig) -> Shapes:
+    """Ordered {diffusers key: shape} of ``UNet2DConditionModel`` (SD-2.1 class, App. A.5)."""
+    d: Shapes = OrderedDict()
+    boc = cfg.block_out_channels
+    temb, ctx, nb = cfg.time_embed_dim, cfg.cross_attention_dim, len(boc)
+    _encoder_half_2d(d, cfg)
+    rev = tuple(reversed(boc))
+    cout = rev[0]
+    for i in range(nb):
+        prev = cout
+        cout = rev[i]
+        cin = rev[min(i + 1, nb - 1)]
+        for j in range(cfg.layers_per_block + 1):
+            skip = cin if j == cfg.layers_per_block else cout
+            rin = prev if j == 0 else cout
+            _resnet2d(d, f"up_blocks.{i}.resnets.{j}", rin + skip, cout, temb)
+            if i > 0:
+                _transformer2d(d, f"up_blocks.{i}.attentions.{j}", cout, ctx)
+        if i < nb - 1:
+            _conv(d, f"up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)
+    _norm(d, "conv_norm_out", boc[0])
+    _conv(d, "conv_out", boc[0], cfg.out_channels, 3)
+    return d
+
+
+def controlnet_param_shapes(cfg: UNet2DConfig) -> Shapes:
+    """``ControlNetModel`` without conditioning embedding: encoder half + 1x1 'zero' convs."""
+    d: Shapes = OrderedDict()
+    skips = _encoder_half_2d(d, cfg)
+    for i, c in enumerate(skips):
+        _conv(d, f"controlnet_down_blocks.{i}", c, c, 1)
+    _conv(d, "controlnet_mid_block", cfg.block_out_channels[-1], cfg.block_out_channels[-1], 1)
+    return d
+
+
+def vae2d_param_shapes(cfg: VAEConfig) -> Shapes:
+    """``AutoencoderKL`` (SD class): the 2-D encoder of ``vae_param_shapes`` + a 2-D decoder."""
+    d: Shapes = OrderedDict()
+    for k, v in vae_param_shapes(cfg).items():
+        if not k.startswith("decoder."):
+            d[k] = v
+    boc = cfg.block_out_channels
+    nb, c = len(boc), boc[-1]
+    _conv(d, "post_quant_conv", cfg.latent_channels, cfg.latent_channels, 1)
+    _conv(d, "decoder.conv_in", cfg.latent_channels, c, 3)
+    _resnet2d(d, "decoder.mid_block.resnets.0", c, c, 0)
+    _norm(d, "decoder.mid_block.attentions.0.group_norm", c)
+    _attention(d, "decoder.mid_block.attentions.0", c, c, qkv_bias=True)
+    _resnet2d(d, "decoder.mid_block.resnets.1", c, c, 0)
+    rev = tuple(reversed(boc))
+    cout = rev[0]
+    for i in range(nb):
+        cin, cout = cout, rev[i]
+        for j in range(cfg.layers_per_block + 1):
+            _resnet2d(d, f"decoder.up_blocks.{i}.resnets.{j}", cin if j == 0 else cout, cout, 0)
+        if i < nb - 1:
+            _conv(d, f"decoder.up_blocks.{i}.upsamplers.0.conv", cout, cout, 3)
+    _norm(d, "decoder.conv_norm_out", boc[0])
+    _conv(d, "decoder.conv_out", boc[0], cfg.in_channels, 3)
     return d
 
 
