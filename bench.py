@@ -30,6 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 UNET_TFLOP_PER_STEP = {(25, 384, 512): 23.16}       # SURVEY.md §8(d) algorithmic count
+# algorithmic work of the VAE stages per clip (TFLOP, GB of minimal 16-bit traffic)
+VAE_WORK = {(25, 384, 512): {"decode": (56.9, 68.5), "encode": (20.8, 23.3)}}
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")   # per-launch DRAM bytes from the ncu capture
 
 
 def parse():
@@ -227,12 +230,42 @@ def run_b200(a):
         tot_ms = sum(r["ms"] for r in table)
         tg_ms, tg_fl, tg_n = sum(r["ms"] for r in tg), sum(r["flops"] for r in tg), sum(r["launches"] for r in tg)
         ach = tg_fl / (tg_ms * 1e-3) / 1e12 if tg_ms > 0 else 0.0
+        traffic = {}
+        try:
+            traffic = json.load(open(TRAFFIC_JSON))
+        except (OSError, ValueError):
+            pass
         roof = {"bound": "tensor", "kernel": "tapgemm_kernel<BN> (tcgen05 implicit GEMM: conv3x3 / temporal conv / linear / attention GEMMs)",
-                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf, "traffic": None,
+                "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
+                "traffic": traffic.get("tapgemm", {}).get("dram_bytes_per_launch"),
+                "traffic_source": traffic.get("source"),
+                "algorithmic_bytes_per_launch_avg": sum(r["bytes"] for r in tg) / max(tg_n, 1),
                 "peak_source": peak_src, "launches_per_step": tg_n, "flops_per_launch_avg": tg_fl / max(tg_n, 1),
                 "avg_launch_us": 1e3 * tg_ms / max(tg_n, 1), "share_of_step": tg_ms / tot_ms if tot_ms else None,
                 "step_tflops_algorithmic": UNET_TFLOP_PER_STEP.get((a.frames, a.height, a.width)),
                 "how": "CUDA events after every launch of one extra step on the launching stream (ug_ctx_profile)"}
+        # the other kernel families of the step, each against the bound that applies (north_star: tensor-pipe on the
+        # attention path, HBM GB/s on the normalisation / VAE path)
+        hbm = peaks.get("hbm_gbs", 6500.0)
+        fam = {}
+        for r in table:
+            k = r["name"].split(".")[0].split(" ")[0]
+            f_ = fam.setdefault(k, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "launches": 0})
+            for q in ("ms", "flops", "bytes", "launches"):
+                f_[q] += r[q]
+        others = []
+        for k, f_ in sorted(fam.items(), key=lambda kv: -kv[1]["ms"]):
+            if k == "tapgemm" or f_["ms"] <= 0:
+                continue
+            tensor = k.startswith("fmha")
+            achv = (f_["flops"] / 1e12 if tensor else f_["bytes"] / 1e9) / (f_["ms"] * 1e-3)
+            others.append({"kernel": k, "bound": "tensor" if tensor else "hbm", "achieved": achv,
+                           "unit": "TFLOP/s" if tensor else "GB/s", "peak": peak_tf if tensor else hbm,
+                           "frac": achv / (peak_tf if tensor else hbm), "launches_per_step": f_["launches"],
+                           "share_of_step": f_["ms"] / tot_ms,
+                           "traffic": traffic.get(k, {}).get("dram_bytes_per_launch")})
+        roof["other_kernels"] = others[:6]
+        roof["stages"] = vae_stage_rooflines(a, eng, cfg, peak_tf, hbm)
         if a.profile_out:
             with open(a.profile_out, "w") as f:
                 json.dump({"ms_per_step_timed": ms_per_step, "instrumented_step_ms": tot_ms, "kernels": sorted(table, key=lambda r: -r["ms"])}, f, indent=1)
@@ -265,6 +298,35 @@ def run_b200(a):
         dist.destroy_process_group()
 
 
+def vae_stage_rooflines(a, eng, cfg, peak_tf, hbm):
+    """VAE encode / temporal decode of one clip through the C ABI, CUDA events, inputs resident: the whole stage
+    against both bounds (report achieved GB/s vs the minimal traffic AND TFLOP/s)."""
+    import torch
+    work = VAE_WORK.get((a.frames, a.height, a.width))
+    if work is None:
+        return None
+    T, H, W = a.frames, a.height, a.width
+    g = torch.Generator().manual_seed(7)
+    frames = torch.rand(T, H, W, 3, generator=g).to(eng.device)
+    lat = (torch.randn(T, 4, H // 8, W // 8, generator=g) * 0.5).to(eng.device)
+    out = {}
+    for name, fn in (("encode", lambda: eng.vae_encode_frames(frames)),
+                     ("decode", lambda: eng.vae_decode_frames(lat, cfg.decode_chunk_size))):
+        fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        ms = sorted(ts)[1]
+        tf, gb = work[name]
+        out["vae_" + name] = {"ms_per_clip": ms, "tflops": tf / (ms * 1e-3), "frac_tensor": tf / (ms * 1e-3) / peak_tf,
+                              "gbs_algorithmic": gb / (ms * 1e-3), "frac_hbm": gb / (ms * 1e-3) / hbm,
+                              "work": {"tflop": tf, "gb": gb}}
+    return out
+
+
 def run_e2e(a, eng, cfg, world, rank, dev):
     """steps/s through the reference-facing plugin call with HOST buffers, every rank one clip."""
     import numpy as np
@@ -276,7 +338,7 @@ def run_e2e(a, eng, cfg, world, rank, dev):
     from unigeo_b200.pipeline import DepthCrafterPipelineB200
     plug = object.__new__(DepthCrafter)                       # reuse the already-loaded engine (one copy of weights)
     plug.device, plug.cfg, plug.dtype, plug.engine = dev, cfg, a.dtype, eng
-    plug.num_inference_steps, plug.seed = a.e2e_steps, 1234 + rank
+    plug.num_inference_steps, plug.seed, plug._stage = a.e2e_steps, 1234 + rank, None
     clip = ClipEmbedder(cfg.clip_embed_dim, dev, torch.float16 if a.dtype == "fp16" else torch.bfloat16)
     plug.pipeline = DepthCrafterPipelineB200(cfg, eng, clip)
     data = make_clip(a.frames, a.height, a.width, seed=1234 + rank)
@@ -296,7 +358,8 @@ def run_e2e(a, eng, cfg, world, rank, dev):
     d2h = out["pred_depths"].numel() * 4 + out["pred_normals"].numel() * 4
     return {"value": world * a.e2e_steps / dt, "unit": "steps/s", "h2d_bytes_per_step": h2d / a.e2e_steps,
             "d2h_bytes_per_step": d2h / a.e2e_steps, "clip_seconds": dt, "num_inference_steps": a.e2e_steps,
-            "call": "unigeo_b200.model.DepthCrafter.forward(data) (CLIP + VAE encode + denoise + VAE decode + post-processing)"}
+            "call": "unigeo_b200.model.DepthCrafter.forward(data) (H2D images + prepare_input + CLIP + VAE encode + denoise + "
+                    "VAE decode + depth/normal post-processing + D2H)"}
 
 
 if __name__ == "__main__":

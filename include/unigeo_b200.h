@@ -156,6 +156,24 @@ int ug_vae2d_encode(ug_ctx* ctx, const float* img, int N, int H, int W, float ou
 int ug_vae2d_decode(ug_ctx* ctx, const float* lat, int N, int h, int w, float* img, unsigned char* normals_u8,
                     void* stream);
 
+/* ---- adapter-side glue of the DepthCrafter plugin, on the device ------------------------------------
+ * ug_vae_encode_frames = ug_vae_encode on the pipeline's own input layout: frames fp32 [T][H][W][3] in [0,1]
+ * (model/depthcrafter.py:39-45 output), x*2-1 and the noise augmentation (noise fp32 [T][3][H][W], nullable)
+ * fused into the layout conversion; video_nchw (nullable) receives x*2-1 as fp32 [T][3][H][W] for the CLIP branch.
+ * ug_vae_decode_frames = ug_vae_decode_temporal + postprocess_video("np"): frames fp32 [T][8h][8w][3] =
+ * clamp(img/2+0.5, 0, 1), the `.frames[0]` the reference reads at model/depthcrafter.py:80-90. */
+/* Replaces DepthCrafter.prepare_input (model/depthcrafter.py:39-45) on the device: images fp32 [T][3][H][W]
+ * in 0..255 (the dataset dict's `images`, stacked) -> frames fp32 [T][H][W][3] = float(uint8(v)) / 255. */
+int ug_prepare_frames(ug_ctx* ctx, const float* images, int T, int H, int W, float* frames, void* stream);
+int ug_vae_encode_frames(ug_ctx* ctx, const float* frames, const float* noise, float noise_strength, int T, int H,
+                         int W, float* video_nchw, float* lat_mean, void* stream);
+int ug_vae_decode_frames(ug_ctx* ctx, const float* lat, int T, int h, int w, int chunk, float* frames, void* stream);
+/* Replaces model/depthcrafter.py:92-97 (channel mean, clip-wide min-max, 1/(x+0.1)) and :48-69 (backprojection
+ * utils/geometry_utils.py:246-253, plane-fit normals :9-70, OpenCV->OpenGL flip): frames fp32 [T][H][W][3],
+ * intrinsics fp32 [T][3][3] (device) -> depths fp32 [T][H][W], normals fp32 [T][H][W][3]. */
+int ug_depth_postprocess(ug_ctx* ctx, const float* frames, const float* intrinsics, int T, int H, int W,
+                         float* depths, float* normals, void* stream);
+
 /* Kernels launched on behalf of this context since the last reset (bench "gpu_launches"). */
 long long ug_ctx_launch_count(ug_ctx* ctx, int reset);
 /* Bytes of workspace currently reserved. */

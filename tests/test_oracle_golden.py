@@ -60,16 +60,6 @@ def test_normals_within_reference_noise():
     assert ((n_cv * pts).sum(-1) <= 1e-6).all()
 
 
-def test_product_postprocess_matches_reference_golden():
-    """unigeo_b200.postprocess (torch ops, closed-form fp64 solve) against the reference adapter's output."""
-    from unigeo_b200.postprocess import depth_and_normals
-    g = np.load(os.path.join(G, "depthcrafter_post.npz"))
-    d, n = depth_and_normals(torch.from_numpy(g["frames"]), torch.from_numpy(g["intrinsics"]))
-    assert torch.equal(d, torch.from_numpy(g["pred_depths"]))
-    ang = _angle(n.numpy(), g["pred_normals"])
-    assert ang.max() <= 0.1 and np.median(ang) <= 0.01, (ang.max(), np.median(ang))
-
-
 def test_stablenormal_post_bit_exact():
     from oracle import postprocess as P
     from unigeo_b200.model.stablenormal import StableNormal

@@ -22,9 +22,10 @@ def wrap(obj, name, label):
         return r
     setattr(obj, name, g)
 wrap(plug.pipeline, "clip", "clip")
-wrap(eng, "vae_encode", "vae_encode"); wrap(eng, "denoise", "denoise"); wrap(eng, "vae_decode", "vae_decode")
+wrap(eng, "vae_encode_frames", "vae_encode"); wrap(eng, "denoise", "denoise"); wrap(eng, "vae_decode_frames", "vae_decode")
+wrap(eng, "depth_postprocess", "  of which depth_postprocess kernel")
 wrap(eng, "set_clip_context", "clip_context")
-wrap(plug, "prepare_input", "prepare_input(host)"); wrap(plug, "prepare_output", "prepare_output(gpu post + D2H)")
+wrap(plug, "prepare_input_device", "prepare_input(stack + H2D + kernel)"); wrap(plug, "prepare_output", "prepare_output(gpu post + D2H)")
 t0 = time.perf_counter(); plug.forward(data); torch.cuda.synchronize(); tot = time.perf_counter() - t0
 for k, v in marks.items(): print(f"{k:34s} {v*1e3:8.1f} ms")
 print(f"{'total':34s} {tot*1e3:8.1f} ms  (unaccounted {1e3*(tot-sum(marks.values())):.1f})")

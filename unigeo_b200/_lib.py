@@ -79,6 +79,10 @@ _SIGNATURES = {
     "ug_refine_frames_2d": ([_P, C.c_char_p, C.c_char_p, _P, _P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
     "ug_vae2d_encode": ([_P, _P, _I, _I, _I, _F, _P, _P], C.c_int),
     "ug_vae2d_decode": ([_P, _P, _I, _I, _I, _P, _P, _P], C.c_int),
+    "ug_prepare_frames": ([_P, _P, _I, _I, _I, _P, _P], C.c_int),
+    "ug_vae_encode_frames": ([_P, _P, _P, _F, _I, _I, _I, _P, _P, _P], C.c_int),
+    "ug_vae_decode_frames": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
+    "ug_depth_postprocess": ([_P, _P, _P, _I, _I, _I, _P, _P, _P], C.c_int),
     "ug_ctx_launch_count": ([_P, _I], C.c_longlong),
     "ug_ctx_workspace_bytes": ([_P], C.c_longlong),
     "ug_ctx_profile": ([_P, _I], C.c_int),

@@ -260,6 +260,69 @@ int ug_vae_encode(ug_ctx* u, const float* img, const float* noise, float noise_s
   });
 }
 
+int ug_prepare_frames(ug_ctx* u, const float* images, int T, int H, int W, float* frames, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && images && frames, UG_ERR_INVALID, "null argument");
+    UG_CHECK(T >= 1 && H >= 1 && W >= 1, UG_ERR_INVALID, "bad shape");
+    Ctx& c = u->c;
+    UG_CUDA(cudaSetDevice(c.device));
+    c.stream = reinterpret_cast<cudaStream_t>(stream);
+    op_check(c, launch_images_in(images, T, (long long)H * W, frames, c.stream), "images_in");
+  });
+}
+
+int ug_vae_encode_frames(ug_ctx* u, const float* frames, const float* noise, float noise_strength, int T, int H,
+                         int W, float* video_nchw, float* lat_mean, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && frames && lat_mean, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_vae_encode_frames");
+    UG_CHECK(T >= 1 && H % 8 == 0 && W % 8 == 0, UG_ERR_INVALID, "H and W must be multiples of 8");
+    UG_CHECK(u->c.cfg.vae_in_channels == 3, UG_ERR_INVALID, "frames are RGB");
+    const std::string sig = "enc:" + std::to_string(T) + "x" + std::to_string(H) + "x" + std::to_string(W);
+    run_sized(u, sig, stream, [&](Ctx& c) {
+      void* img16 = c.alloc16((long long)T * H * W * 8);
+      if (!c.dry)
+        op_check(c, launch_frames_in(frames, noise, noise_strength, T, (long long)H * W, img16, video_nchw, c.fmt,
+                                     c.stream), "frames_in");
+      vae_encode(c, "vae.", img16, T, H, W, 1.f, lat_mean);
+    });
+  });
+}
+
+int ug_vae_decode_frames(ug_ctx* u, const float* lat, int T, int h, int w, int chunk, float* frames, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && lat && frames, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_vae_decode_frames");
+    UG_CHECK(T >= 1 && chunk >= 1, UG_ERR_INVALID, "T and chunk must be positive");
+    const std::string sig = "dec:" + std::to_string(T) + "x" + std::to_string(h) + "x" + std::to_string(w) + "/" +
+                            std::to_string(chunk);
+    run_sized(u, sig, stream, [&](Ctx& c) {
+      void* z16 = c.alloc16((long long)T * h * w * 8);
+      if (!c.dry)
+        op_check(c, launch_nchw_to_nhwc(lat, nullptr, 0.f, 1.0f / c.cfg.vae_scaling_factor, 0.f, T,
+                                        c.cfg.vae_latent_channels, h, w, 8, z16, c.fmt, c.stream), "latents in");
+      vae_decode(c, z16, T, h, w, chunk, nullptr, frames);
+    });
+  });
+}
+
+int ug_depth_postprocess(ug_ctx* u, const float* frames, const float* intrinsics, int T, int H, int W, float* depths,
+                         float* normals, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && frames && intrinsics && depths && normals, UG_ERR_INVALID, "null argument");
+    UG_CHECK(T >= 1 && H >= 1 && W >= 1, UG_ERR_INVALID, "bad shape");
+    const std::string sig = "post:" + std::to_string(T) + "x" + std::to_string(H) + "x" + std::to_string(W);
+    run_sized(u, sig, stream, [&](Ctx& c) {
+      float* ws = c.allocf(post_workspace_floats((long long)T * H * W));
+      if (!c.dry) {
+        op_check(c, launch_depth_postprocess(frames, intrinsics, T, H, W, depths, normals, ws, c.stream),
+                 "depth_postprocess", 0.0, 28.0 * T * H * W);
+        c.launches += 2;   // three kernels behind one launcher
+      }
+    });
+  });
+}
+
 int ug_vae_decode_temporal(ug_ctx* u, const float* lat, int T, int h, int w, int chunk, float* img, void* stream) {
   return guard([&] {
     UG_CHECK(u && lat && img, UG_ERR_INVALID, "null argument");

@@ -44,7 +44,7 @@ __device__ __forceinline__ const uint4* cat_ptr(const void* x1, int nv1, const v
 // order and writes one (sum, sumsq) pair per group to part[set][chunk][G][2]; the apply
 // kernel adds the chunks in index order.  Reruns are bit-identical.
 template <typename T>
-__global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
+__global__ void __launch_bounds__(320, 3) gn_stats_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
                                 long long rows_per_set, long long chunk_rows, int G, int cs,
                                 float* __restrict__ part, float* __restrict__ mr, unsigned int* __restrict__ counters,
                                 float inv_cnt, float eps) {
@@ -66,25 +66,22 @@ __global__ void gn_stats_kernel(const void* __restrict__ x1, int nv1, const void
   for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
   if (rr < rpb) {
     long long r = r_begin + rr;
-    // four independent 16-byte loads in flight per thread (HBM latency x bandwidth needs ~40 KB per SM)
-    for (; r + 3 * rpb < r_end; r += 4 * rpb) {
-      uint4 u[4];
+    // eight independent 16-byte loads in flight per thread (the kernel is latency bound: a thread only
+    // makes a few trips); rows past the end are predicated off and contribute zeros
+    for (; r < r_end; r += 8 * rpb) {
+      uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r + (long long)k * rpb, c8));
+      for (int k = 0; k < 8; ++k) {
+        const long long rk = r + (long long)k * rpb;
+        u[k] = rk < r_end ? __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
+      }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < 8; ++k) {
         float f[8];
         unpack8<T>(u[k], f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] += f[j] * f[j]; }
+        for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
       }
-    }
-    for (; r < r_end; r += rpb) {
-      uint4 u = __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r, c8));
-      float f[8];
-      unpack8<T>(u, f);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] += f[j] * f[j]; }
     }
     float* ps = s_part + (size_t)rr * C + c8 * 8;
     float* pq = s_part + (size_t)(rpb + rr) * C + c8 * 8;
@@ -171,7 +168,7 @@ __global__ void gn_finalize_kernel(const float* __restrict__ part, int chunks, i
 
 // ------------------------------------------------------------------ GroupNorm apply (+SiLU)
 template <typename T>
-__global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
+__global__ void __launch_bounds__(320, 3) gn_apply_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
                                 long long rows_per_set, long long chunk_rows, int G, int cs,
                                 const float* __restrict__ part /* [sets][G] (mean, rstd) */,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
@@ -211,13 +208,17 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void
   for (int j = 0; j < 8; ++j) { sa[j] = s_a[c8 * 8 + j]; sb[j] = s_b[c8 * 8 + j]; }
   uint4* yo = reinterpret_cast<uint4*>(y);
   long long r = r_begin + rr;
-  // four rows in flight per thread
-  for (; r + 3 * rpb < r_end; r += 4 * rpb) {
-    uint4 u[4];
+  // six rows in flight per thread; rows past the end are predicated off
+  for (; r < r_end; r += 6 * rpb) {
+    uint4 u[6];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r + (long long)k * rpb, c8));
+    for (int k = 0; k < 6; ++k) {
+      const long long rk = r + (long long)k * rpb;
+      u[k] = rk < r_end ? __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
+    }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 6; ++k) {
+      const long long rk = r + (long long)k * rpb;
       float f0[8];
       unpack8<T>(u[k], f0);
 #pragma unroll
@@ -225,110 +226,84 @@ __global__ void gn_apply_kernel(const void* __restrict__ x1, int nv1, const void
         const float v0 = fmaf(f0[j], sa[j], sb[j]);
         f0[j] = silu ? silu_f(v0) : v0;
       }
-      yo[(set * rows_per_set + r + (long long)k * rpb) * nvec + c8] = pack8<T>(f0);
+      if (rk < r_end) yo[(set * rows_per_set + rk) * nvec + c8] = pack8<T>(f0);
     }
-  }
-  for (; r < r_end; r += rpb) {
-    const long long g0 = set * rows_per_set + r;
-    float f0[8];
-    unpack8<T>(__ldg(cat_ptr(x1, nv1, x2, nv2, g0, c8)), f0);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float v0 = fmaf(f0[j], sa[j], sb[j]);
-      f0[j] = silu ? silu_f(v0) : v0;
-    }
-    yo[g0 * nvec + c8] = pack8<T>(f0);
   }
 }
 
 // ------------------------------------------------------------------ LayerNorm
-// A warp normalises ROWS rows at once (VPL 16-byte vectors per lane and row) so that enough loads are
-// in flight per SM to cover HBM latency.  Only the packed 16-bit vectors stay in registers (they are
-// unpacked again for each of the three passes: mean, variance, output), which keeps the kernel at
-// >= 3 CTAs (24 warps) per SM; statistics are two-pass in fp32.
-template <typename T, int VPL, int ROWS>
-__global__ void __launch_bounds__(256, 3)
+// LPR lanes share a row (32 / LPR rows per warp at once); lane l of a row owns the 16-byte vectors
+// l, l + LPR, ... (VPL of them), so every lane is busy for C = 320 / 640 / 1280 (LPR = 8 / 16 / 32,
+// VPL = 5) and a load instruction touches whole 128-byte lines.  The kernel is instruction-issue bound
+// before it is HBM bound (ncu: 300 instructions per row in the one-warp-per-row form), hence: values are
+// unpacked once and stay in registers, reductions take log2(LPR) shuffles, statistics are two-pass fp32.
+template <typename T, int LPR, int VPL>
+__global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, const float* __restrict__ add, int add_div,
                  void* __restrict__ y) {
   pdl_launch_dependents();
   pdl_wait();
+  constexpr int RPW = 32 / LPR;                       // rows per warp
   const int lane = threadIdx.x & 31;
-  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
-  if (row0 >= rows) return;
+  const int sub = lane % LPR;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool rok = row < rows;
   const int nvec = C >> 3;
-  const uint4* xb = reinterpret_cast<const uint4*>(x);
-  uint4 raw[ROWS][VPL];
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r)
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      const int i = lane + 32 * k;
-      raw[r][k] = make_uint4(0u, 0u, 0u, 0u);
-      if (row0 + r < rows && i < nvec) raw[r][k] = __ldg(xb + (row0 + r) * nvec + i);
-    }
-  // value of vector (r, k) with the optional per-frame addend applied
-  auto value = [&](int r, int k, const float* addr, float (&f)[8]) {
-    unpack8<T>(raw[r][k], f);
-    if (addr) {
-      const int i = lane + 32 * k;
-      const float4 a0 = __ldg(reinterpret_cast<const float4*>(addr + i * 8));
-      const float4 a1 = __ldg(reinterpret_cast<const float4*>(addr + i * 8) + 1);
-      f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w;
-      f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
-    }
-  };
-  float mean[ROWS], rstd[ROWS];
-  const float inv_c = 1.0f / (float)C;
-#pragma unroll
-  for (int r = 0; r < ROWS; ++r) {
-    const bool rok = row0 + r < rows;
-    const float* addr = (add && rok) ? add + ((row0 + r) / add_div) * C : nullptr;
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      if (rok && lane + 32 * k < nvec) {
-        float f[8];
-        value(r, k, addr, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) s += f[j];
-      }
-    }
-    mean[r] = warp_sum(s) * inv_c;
-    float v = 0.f;
-#pragma unroll
-    for (int k = 0; k < VPL; ++k) {
-      if (rok && lane + 32 * k < nvec) {
-        float f[8];
-        value(r, k, addr, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { const float d = f[j] - mean[r]; v += d * d; }
-      }
-    }
-    rstd[r] = rsqrtf(warp_sum(v) * inv_c + eps);
-  }
-  uint4* yb = reinterpret_cast<uint4*>(y);
+  const uint4* xb = reinterpret_cast<const uint4*>(x) + (rok ? row : 0) * nvec;
+  uint4 raw[VPL];
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
-    const int i = lane + 32 * k;
+    const int i = sub + LPR * k;
+    raw[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (rok && i < nvec) raw[k] = __ldg(xb + i);
+  }
+  float f[VPL][8];
+  const float* addr = (add && rok) ? add + (row / add_div) * C : nullptr;
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = sub + LPR * k;
+    unpack8<T>(raw[k], f[k]);
+    if (addr && i < nvec) {
+      const float4 a0 = __ldg(reinterpret_cast<const float4*>(addr + i * 8));
+      const float4 a1 = __ldg(reinterpret_cast<const float4*>(addr + i * 8) + 1);
+      f[k][0] += a0.x; f[k][1] += a0.y; f[k][2] += a0.z; f[k][3] += a0.w;
+      f[k][4] += a1.x; f[k][5] += a1.y; f[k][6] += a1.z; f[k][7] += a1.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s += f[k][j];         // padding vectors are zero
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float v = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    if (sub + LPR * k < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { f[k][j] -= mean; v = fmaf(f[k][j], f[k][j], v); }
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / (float)C + eps);
+  if (!rok) return;
+  uint4* yb = reinterpret_cast<uint4*>(y) + row * nvec;
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = sub + LPR * k;
     if (i < nvec) {
       const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + i * 8));
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + i * 8) + 1);
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + i * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + i * 8) + 1);
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-      for (int r = 0; r < ROWS; ++r) {
-        if (row0 + r < rows) {
-          const float* addr = add ? add + ((row0 + r) / add_div) * C : nullptr;
-          float f[8], o[8];
-          value(r, k, addr, f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] = (f[j] - mean[r]) * rstd[r] * gg[j] + bb[j];
-          yb[(row0 + r) * nvec + i] = pack8<T>(o);
-        }
-      }
+      float o[8];
+      o[0] = fmaf(f[k][0] * rstd, g0.x, b0.x); o[1] = fmaf(f[k][1] * rstd, g0.y, b0.y);
+      o[2] = fmaf(f[k][2] * rstd, g0.z, b0.z); o[3] = fmaf(f[k][3] * rstd, g0.w, b0.w);
+      o[4] = fmaf(f[k][4] * rstd, g1.x, b1.x); o[5] = fmaf(f[k][5] * rstd, g1.y, b1.y);
+      o[6] = fmaf(f[k][6] * rstd, g1.z, b1.z); o[7] = fmaf(f[k][7] * rstd, g1.w, b1.w);
+      yb[i] = pack8<T>(o);
     }
   }
 }
@@ -952,27 +927,33 @@ int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long ro
   return (int)err;
 }
 
-template <int VPL, int ROWS>
+template <int LPR, int VPL>
 int launch_ln_t(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
                 const float* add, int add_div, void* y, int fmt, cudaStream_t st) {
   const int wpb = 8;
-  const long long rows_per_block = (long long)wpb * ROWS;
+  const long long rows_per_block = (long long)wpb * (32 / LPR);
   const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
   cudaError_t err;
-  UG_DISPATCH_FMT(fmt, (err = launch_pdl(layernorm_kernel<T, VPL, ROWS>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, C,
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl(layernorm_kernel<T, LPR, VPL>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, C,
                                          gamma, beta, eps, add, add_div > 0 ? add_div : 1, y)));
   return (int)err;
 }
 
 int launch_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
                      const float* add, int add_div, void* y, int fmt, cudaStream_t st) {
-  if ((C & 7) || C > 2048) return (int)cudaErrorInvalidValue;
-  const int vpl = (C / 8 + 31) / 32;
-  if (vpl <= 1) return launch_ln_t<1, 4>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
-  if (vpl <= 2) return launch_ln_t<2, 4>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
-  if (vpl <= 3) return launch_ln_t<3, 2>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
-  if (vpl <= 5) return launch_ln_t<5, 2>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
-  return launch_ln_t<8, 1>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st);
+  if ((C & 7) || C > 2048 || C < 8) return (int)cudaErrorInvalidValue;
+  const int nvec = C / 8;
+#define UG_LN(LPR, VPL) return launch_ln_t<LPR, VPL>(x, rows, C, gamma, beta, eps, add, add_div, y, fmt, st)
+  if (nvec <= 8) UG_LN(8, 1);          // C <= 64
+  if (nvec <= 16) UG_LN(16, 1);        // C <= 128
+  if (nvec <= 32) UG_LN(32, 1);        // C <= 256
+  if (nvec <= 40) UG_LN(8, 5);         // C = 320
+  if (nvec <= 64) UG_LN(32, 2);        // C <= 512
+  if (nvec <= 80) UG_LN(16, 5);        // C = 640
+  if (nvec <= 128) UG_LN(32, 4);       // C <= 1024
+  if (nvec <= 160) UG_LN(32, 5);       // C = 1280
+  UG_LN(32, 8);                        // C <= 2048
+#undef UG_LN
 }
 
 int launch_softmax_rows(void* s, long long rows, int n, float scale, int fmt, cudaStream_t st) {

@@ -82,6 +82,21 @@ int launch_build_unet_input(const float* latents, const void* cond, float sigma,
 int launch_euler_step(float* latents, const float* v, float sigma, float sigma_next, long long n,
                       cudaStream_t st);
 
+// ---- adapter-side glue (post.cu) ---------------------------------------------------------
+// depth post-processing of one clip: frames fp32 [T][H][W][3] in [0,1], K fp32 [T][3][3] ->
+// depth fp32 [T][H][W], normals fp32 [T][H][W][3] (OpenGL frame); ws: post_workspace_floats(T*H*W) floats
+long long post_workspace_floats(long long pixels);
+int launch_depth_postprocess(const float* frames, const float* K, int T, int H, int W, float* depth, float* normals,
+                             float* ws, cudaStream_t st);
+// frames fp32 [T][HW][3] in [0,1] (+ noise fp32 [T][3][HW] * ns) -> 16-bit [T][HW][8]; video_nchw (nullable)
+// receives frames*2-1 as fp32 [T][3][HW] (the CLIP branch's input)
+int launch_frames_in(const float* frames, const float* noise, float ns, int T, long long HW, void* y,
+                     float* video_nchw, int fmt, cudaStream_t st);
+// images fp32 [T][3][HW] 0..255 -> frames fp32 [T][HW][3] = float(uint8(v)) / 255
+int launch_images_in(const float* img, int T, long long HW, float* frames, cudaStream_t st);
+// 16-bit [pixels][8] -> fp32 [pixels][3] = clamp(x/2+0.5, 0, 1)
+int launch_frames_out(const void* x, long long pixels, float* y, int fmt, cudaStream_t st);
+
 // weights: src fp32/16-bit [Cout][Cin][taps] -> dst 16-bit [taps][Cout][CinPad] (dst pre-zeroed when padded)
 int launch_convert_weight(const void* src, int src_dtype /*0 f16,1 bf16,2 f32*/, void* dst, int Cout, int Cin,
                           int CinPad, int taps, int fmt, cudaStream_t st);

@@ -77,8 +77,10 @@ void vae_encode(Ctx& c, const std::string& V, const void* img16, int N, int H, i
 // 2-D decoder ("vae2d."): z16 [N][h*w][8] (4 valid, already / scaling) -> img fp32 NCHW [N][3][8h][8w] (nullable)
 // and / or 8-bit unit normals [N][8h][8w][3] (nullable)
 void vae2d_decode(Ctx& c, const void* z16, int N, int h, int w, float* img_nchw, unsigned char* normals_u8);
-// z16 [T][h*w][8] (4 valid, already / scaling) -> img fp32 NCHW [T][3][8h][8w]
-void vae_decode(Ctx& c, const void* z16, int T, int h, int w, int chunk, float* img_nchw);
+// z16 [T][h*w][8] (4 valid, already / scaling) -> img fp32 NCHW [T][3][8h][8w] (nullable) and / or
+// frames fp32 [T][8h][8w][3] = clamp(img/2+0.5, 0, 1) (nullable; postprocess_video "np" layout)
+void vae_decode(Ctx& c, const void* z16, int T, int h, int w, int chunk, float* img_nchw,
+                float* frames_hwc = nullptr);
 
 float sigmoidf_host(float x);
 

@@ -83,7 +83,7 @@ void vae_encode(Ctx& c, const std::string& V, const void* img16, int N, int H, i
              "nhwc_to_nchw");
 }
 
-void vae_decode(Ctx& c, const void* z16, int T, int h, int w, int chunk, float* img_nchw) {
+void vae_decode(Ctx& c, const void* z16, int T, int h, int w, int chunk, float* img_nchw, float* frames_hwc) {
   const ug_model_cfg& g = c.cfg;
   const int nb = g.vae_num_blocks;
   const float eps = g.vae_eps, teps = g.vae_temporal_eps;
@@ -127,10 +127,12 @@ void vae_decode(Ctx& c, const void* z16, int T, int h, int w, int chunk, float* 
       op_conv3x3(c, n, F, x.H, x.W, x.C, c.M(V + "decoder.conv_out.weight"), g.vae_in_channels, 1, 0, e); }
     { Epi e; e.out = rgb2; e.ldc = 8; e.bias = c.F(V + "decoder.time_conv_out.bias");
       op_tconv3(c, rgb, F, hw, 8, c.M(V + "decoder.time_conv_out.weight"), g.vae_in_channels, F, e); }
-    if (!c.dry)
+    if (!c.dry && img_nchw)
       op_check(c, launch_nhwc_to_nchw(rgb2, F, H, W, 8, g.vae_in_channels, 1.f, 0.f, 0,
                                       img_nchw + (size_t)t0 * g.vae_in_channels * hw, c.fmt, c.stream),
                "nhwc_to_nchw");
+    if (!c.dry && frames_hwc)
+      op_check(c, launch_frames_out(rgb2, rows, frames_hwc + (size_t)t0 * 3 * hw, c.fmt, c.stream), "frames_out");
     c.ws.release(m);
   }
 }

@@ -146,6 +146,59 @@ class Engine:
                                                        out.data_ptr(), _stream()))
         return out
 
+    def prepare_frames(self, images: torch.Tensor) -> torch.Tensor:
+        """images [T,3,H,W] fp32 0..255 (CUDA) -> frames [T,H,W,3] = float(uint8(v))/255 (reference :39-45)."""
+        img = _f32(images, self.device)
+        T, _, H, W = img.shape
+        out = torch.empty((T, H, W, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_prepare_frames(self._ctx, img.data_ptr(), T, H, W, out.data_ptr(), _stream()))
+        return out
+
+    def vae_encode_frames(self, frames: torch.Tensor, noise: torch.Tensor | None = None, noise_strength: float = 0.0,
+                          want_video: bool = False):
+        """frames [T,H,W,3] fp32 in [0,1] (the adapter's ``prepare_input`` layout) -> latent mean [T,4,H/8,W/8];
+        x*2-1 and the noise augmentation (noise [T,3,H,W]) are fused into the layout kernel.  With
+        ``want_video`` also returns x*2-1 as [T,3,H,W] (input of the CLIP branch)."""
+        if not self._finalized:
+            self.finalize()
+        fr = _f32(frames, self.device)
+        T, H, W, _ = fr.shape
+        nz = _f32(noise, self.device) if noise is not None else None
+        out = torch.empty((T, self.cfg.vae.latent_channels, H // 8, W // 8), dtype=torch.float32, device=self.device)
+        video = torch.empty((T, 3, H, W), dtype=torch.float32, device=self.device) if want_video else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_vae_encode_frames(self._ctx, fr.data_ptr(), nz.data_ptr() if nz is not None else None,
+                                                     float(noise_strength), T, H, W,
+                                                     video.data_ptr() if video is not None else None, out.data_ptr(),
+                                                     _stream()))
+        return (out, video) if want_video else out
+
+    def vae_decode_frames(self, latents: torch.Tensor, chunk: int = 8) -> torch.Tensor:
+        """latents [T,4,h,w] (scaled) -> ``.frames[0]``: [T,8h,8w,3] fp32 = clamp(decode/2+0.5, 0, 1)."""
+        if not self._finalized:
+            self.finalize()
+        lat = _f32(latents, self.device)
+        T, _, h, w = lat.shape
+        out = torch.empty((T, 8 * h, 8 * w, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_vae_decode_frames(self._ctx, lat.data_ptr(), T, h, w, int(chunk), out.data_ptr(),
+                                                     _stream()))
+        return out
+
+    def depth_postprocess(self, frames: torch.Tensor, intrinsics: torch.Tensor):
+        """frames [T,H,W,3] in [0,1], intrinsics [T,3,3] -> (pred_depths [T,H,W], pred_normals [T,H,W,3] OpenGL)."""
+        fr = _f32(frames, self.device)
+        K = _f32(intrinsics, self.device)
+        T, H, W, _ = fr.shape
+        assert K.shape == (T, 3, 3)
+        depth = torch.empty((T, H, W), dtype=torch.float32, device=self.device)
+        normals = torch.empty((T, H, W, 3), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_depth_postprocess(self._ctx, fr.data_ptr(), K.data_ptr(), T, H, W, depth.data_ptr(),
+                                                     normals.data_ptr(), _stream()))
+        return depth, normals
+
     # ------------------------------------------------------------------ StableNormal path (2-D UNet)
     def set_text_context(self, net: str, tokens: torch.Tensor) -> None:
         """tokens [L,D] (shared prompt) or [F,L,D]: encoder_hidden_states of network ``net`` ("unet2d", ...)."""

@@ -3,7 +3,8 @@
 (guidance_scale=1.0, window_size=len(frames) => one window, output_type="np").
 
 Host side only moves data: CLIP embeddings (torch library code), then three C-ABI calls --
-``ug_vae_encode`` -> ``ug_denoise_clip`` -> ``ug_vae_decode_temporal`` -- on the current stream.
+``ug_vae_encode_frames`` -> ``ug_denoise_clip`` -> ``ug_vae_decode_frames`` -- on the current stream
+(x*2-1, the noise augmentation and postprocess_video's clamp / layout ride in the layout kernels).
 """
 from __future__ import annotations
 
@@ -38,25 +39,25 @@ class DepthCrafterPipelineB200:
         if H % 64 or W % 64:
             raise ValueError("height and width must be multiples of 64 (three stride-2 levels below /8 latents)")
         h, w = H // 8, W // 8
-        video = frames.to(self.device, non_blocking=True).float().permute(0, 3, 1, 2).contiguous() * 2.0 - 1.0
-        if enc is None:
-            if self.clip is None:
-                raise RuntimeError("no CLIP embedder configured and no `enc` given")
-            enc = self.clip(video)
-        enc = enc.to(self.device).float().reshape(T, -1)
+        frames = frames.to(self.device, non_blocking=True)
+        if enc is None and self.clip is None:
+            raise RuntimeError("no CLIP embedder configured and no `enc` given")
         # the two random draws of the upstream pipeline (noise augmentation, initial latents); drawn on the
         # generator's device -- a CUDA generator keeps 15 M normals off the host (70 ms per clip on CPU)
         gdev = generator.device if generator is not None else self.device
         if aug_noise is None:
-            aug_noise = torch.randn(video.shape, generator=generator, device=gdev).to(self.device)
+            aug_noise = torch.randn((T, 3, H, W), generator=generator, device=gdev).to(self.device)
         if init_noise is None:
             init_noise = torch.randn((T, 4, h, w), generator=generator, device=gdev).to(self.device)
         e.prepare(T, h, w)
-        e.set_clip_context(enc)
-        cond = e.vae_encode(video, aug_noise.to(self.device), cfg.noise_aug_strength)
+        if enc is None:
+            cond, video = e.vae_encode_frames(frames, aug_noise, cfg.noise_aug_strength, want_video=True)
+            enc = self.clip(video)
+        else:
+            cond = e.vae_encode_frames(frames, aug_noise, cfg.noise_aug_strength)
+        e.set_clip_context(enc.to(self.device).float().reshape(T, -1))
         lat = e.denoise(cond, init_noise.reshape(T, 4, h, w), self.added_time_ids(), num_inference_steps)
-        img = e.vae_decode(lat, cfg.decode_chunk_size)
-        out = (img / 2.0 + 0.5).clamp_(0.0, 1.0).permute(0, 2, 3, 1).contiguous()
+        out = e.vae_decode_frames(lat, cfg.decode_chunk_size)
         if output_type == "pt":
             return out
         return out.cpu().numpy()
