@@ -46,6 +46,31 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// Two gates at once on the packed fp32 pipe (FFMA2 / FMUL2 / FADD2, sm_100): the GEGLU epilogue is
+// instruction-issue bound at K = 320 (ncu: 30 thread instructions per output element), and the packed
+// forms halve the polynomial's share.  Same formula as gelu_erf: returns 0.5 x (1 + erf(x / sqrt 2)).
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  // t = 1 / (1 + 0.3275911 |x| / sqrt 2)   (|.| rides on the scalar FFMA as an operand modifier)
+  float2 t;
+  t.x = rcp_approx(fmaf(0.23164189f, fabsf(x.x), 1.0f));
+  t.y = rcp_approx(fmaf(0.23164189f, fabsf(x.y), 1.0f));
+  // q = -(a1 t + a2 t^2 + ... + a5 t^5)  (coefficients negated so that erf = 1 + q e)
+  float2 q = __ffma2_rn(t, make_float2(-1.061405429f, -1.061405429f), make_float2(1.453152027f, 1.453152027f));
+  q = __ffma2_rn(t, q, make_float2(-1.421413741f, -1.421413741f));
+  q = __ffma2_rn(t, q, make_float2(0.284496736f, 0.284496736f));
+  q = __ffma2_rn(t, q, make_float2(-0.254829592f, -0.254829592f));
+  q = __fmul2_rn(q, t);
+  // e = exp(-x^2 / 2) = 2^(-0.5 log2(e) x^2)
+  const float2 w = __fmul2_rn(__fmul2_rn(x, x), make_float2(-0.72134752044448170f, -0.72134752044448170f));
+  float2 e;
+  e.x = ex2_approx(w.x);
+  e.y = ex2_approx(w.y);
+  const float2 erf_abs = __ffma2_rn(q, e, make_float2(1.0f, 1.0f));
+  // 0.5 x (1 + sign(x) erf|.|) = h + |h| erf|.|,  h = x / 2
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return make_float2(fmaf(fabsf(h.x), erf_abs.x, h.x), fmaf(fabsf(h.y), erf_abs.y, h.y));
+}
+
 __device__ __forceinline__ float2 unpack16x2(uint32_t u, int fmt) {
   return fmt ? Elem<__nv_bfloat16>::unpack2(u) : Elem<__half>::unpack2(u);
 }
@@ -186,6 +211,19 @@ __device__ __forceinline__ void stage_cols32(const float (&f)[32], uint32_t slab
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const uint32_t c16 = (uint32_t)(half * 4 + j);
+    const uint32_t addr = slab + (uint32_t)r * 128u + ((c16 ^ (uint32_t)(r & 7)) << 4);
+    const uint32_t w0 = pack16x2(f[8 * j + 0], f[8 * j + 1], fmt), w1 = pack16x2(f[8 * j + 2], f[8 * j + 3], fmt);
+    const uint32_t w2 = pack16x2(f[8 * j + 4], f[8 * j + 5], fmt), w3 = pack16x2(f[8 * j + 6], f[8 * j + 7], fmt);
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3)
+                 : "memory");
+  }
+}
+
+// 16 finished columns (quarter qt = 0..3 of the 64-column slab) of row r
+__device__ __forceinline__ void stage_cols16(const float (&f)[16], uint32_t slab, int r, int qt, int fmt) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const uint32_t c16 = (uint32_t)(qt * 2 + j);
     const uint32_t addr = slab + (uint32_t)r * 128u + ((c16 ^ (uint32_t)(r & 7)) << 4);
     const uint32_t w0 = pack16x2(f[8 * j + 0], f[8 * j + 1], fmt), w1 = pack16x2(f[8 * j + 2], f[8 * j + 3], fmt);
     const uint32_t w2 = pack16x2(f[8 * j + 4], f[8 * j + 5], fmt), w3 = pack16x2(f[8 * j + 6], f[8 * j + 7], fmt);
@@ -541,26 +579,38 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int c = sl * 64 + half * 32;
             if (c >= out_w) break;
             const bool last_ld = last_slab && (half == 1 || c + 32 >= out_w);
-            float f[32];
             if (a.geglu) {
-              uint32_t v[32], g[32];
-              tmem_ld_32x32(trow + c, v);
-              tmem_ld_32x32(trow + BNh + c, g);
+              // value and gate columns 16 at a time: both accumulators in flight (tcgen05.ld x16), packed fp32 math
+              uint32_t v[2][16], g[2][16];
+              tmem_ld_32x16(trow + c, v[0]);
+              tmem_ld_32x16(trow + BNh + c, g[0]);
+              tmem_ld_32x16(trow + c + 16, v[1]);
+              tmem_ld_32x16(trow + BNh + c + 16, g[1]);
               tmem_ld_wait();
               if (last_ld) { release(buf); released = true; }
-              const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              const float4* bv = reinterpret_cast<const float4*>(sbt + c);
-              const float4* bg = reinterpret_cast<const float4*>(sbt + BNh + c);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 x = have_sb ? bv[j] : zero4, y = have_sb ? bg[j] : zero4;
-                f[4 * j + 0] = (__uint_as_float(v[4 * j + 0]) + x.x) * gelu_erf(__uint_as_float(g[4 * j + 0]) + y.x);
-                f[4 * j + 1] = (__uint_as_float(v[4 * j + 1]) + x.y) * gelu_erf(__uint_as_float(g[4 * j + 1]) + y.y);
-                f[4 * j + 2] = (__uint_as_float(v[4 * j + 2]) + x.z) * gelu_erf(__uint_as_float(g[4 * j + 2]) + y.z);
-                f[4 * j + 3] = (__uint_as_float(v[4 * j + 3]) + x.w) * gelu_erf(__uint_as_float(g[4 * j + 3]) + y.w);
+              for (int hq = 0; hq < 2; ++hq) {
+                const float2* bv = reinterpret_cast<const float2*>(sbt + c + 16 * hq);
+                const float2* bg = reinterpret_cast<const float2*>(sbt + BNh + c + 16 * hq);
+                float fq[16];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  float2 val = make_float2(__uint_as_float(v[hq][2 * j]), __uint_as_float(v[hq][2 * j + 1]));
+                  float2 gate = make_float2(__uint_as_float(g[hq][2 * j]), __uint_as_float(g[hq][2 * j + 1]));
+                  if (have_sb) {
+                    val = __fadd2_rn(val, bv[j]);
+                    gate = __fadd2_rn(gate, bg[j]);
+                  }
+                  const float2 o = __fmul2_rn(val, gelu_erf2(gate));
+                  fq[2 * j] = o.x;
+                  fq[2 * j + 1] = o.y;
+                }
+                stage_cols16(fq, slab, r, half * 2 + hq, a.fmt);
               }
-              finish_cols<32>(f, a, pix, fb_off, out_c0 + c, nullptr, n_out - (out_c0 + c), row_ok);
-            } else {
+              continue;
+            }
+            float f[32];
+            {
               uint32_t v[32];
               tmem_ld_32x32(trow + c, v);     // columns past Ncur are stale but never reach memory (map clips)
               tmem_ld_wait();
@@ -757,6 +807,8 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   if (args.tma_store && (tmC == nullptr || (args.bn_tile & 63) || batch != 1 || args.out_fp32))
     return (int)cudaErrorInvalidValue;
   if (args.geglu && (args.bn_tile != 256 || (args.n_total & 255))) return (int)cudaErrorInvalidValue;
+  if (args.geglu && (args.res != nullptr || args.blend != nullptr || args.fbias != nullptr || args.scale != 1.0f))
+    return (int)cudaErrorInvalidValue;             // the GEGLU epilogue is bias + gate only
   const CUtensorMap& mc = tmC ? *tmC : tmA;
   args.batch = batch;
   args.n_tiles = (args.n_total + args.bn_tile - 1) / args.bn_tile;
@@ -766,7 +818,8 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   const int sms = tapgemm_num_sms();
   if (ctas == 1) {
     const int grid = (int)(units < sms ? units : sms);
-    return (int)launch_pdl(tapgemm_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes, stream, tmA, tmB, mc, args);
+    return (int)launch_pdl(tapgemm_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes,
+                           stream, tmA, tmB, mc, args);
   }
   const long long slots = sms / 2;
   cudaLaunchConfig_t cfg = {};
