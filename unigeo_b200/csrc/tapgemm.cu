@@ -268,6 +268,24 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int pm_tiles = (m_tiles + CTAS - 1) / CTAS;  // tiles along M per scheduling unit
   const int n_tiles = a.n_tiles;
   const int total_tiles = pm_tiles * n_tiles * a.batch;
+  // unit index -> (M tile, N tile, batch).  Default order: M fastest (one weight tile stays hot while the
+  // activations stream).  n_fastest: all N tiles of an M tile run at the same time on neighbouring CTAs, so an
+  // activation matrix larger than L2 is read from HBM once instead of once per N tile; the N tile is rotated by
+  // the M index so that ragged (e.g. 192 + 128) tiles alternate on every CTA.
+  auto decode = [&](int t, int& m_lin, int& n_tile, int& z) {
+    if (a.n_fastest) {
+      const int per_z = pm_tiles * n_tiles;
+      z = t / per_z;
+      const int u = t - z * per_z;
+      m_lin = u / n_tiles;
+      n_tile = (u - m_lin * n_tiles + m_lin) % n_tiles;
+    } else {
+      m_lin = t % pm_tiles;
+      const int rest = t / pm_tiles;
+      n_tile = rest % n_tiles;
+      z = rest / n_tiles;
+    }
+  };
   const int num_iters = a.num_taps * a.kchunks;
   const int unit0 = blockIdx.x / CTAS, unit_stride = gridDim.x / CTAS;
   // N extent of the tile starting at column n0: ragged last tile, rounded up to the UMMA granularity
@@ -316,10 +334,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                  (uint32_t)(a.b_mn_major ? BK : BN / CTAS) * (BK * 2)) * CTAS;
       int it_g = 0;   // ring position, continuous across tiles
       for (int t = unit0; t < total_tiles; t += unit_stride) {
-        int m_tile = (t % pm_tiles) * CTAS + rank;
-        const int rest = t / pm_tiles;
-        const int n0 = (rest % n_tiles) * BN;
-        const int z = rest / n_tiles;
+        int m_lin, n_tile_p, z;
+        decode(t, m_lin, n_tile_p, z);
+        int m_tile = m_lin * CTAS + rank;
+        const int n0 = n_tile_p * BN;
         const int z1 = z / a.zdiv, z0 = z - z1 * a.zdiv;
         const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
         const int ty = m_tile % a.tiles_y;
@@ -365,7 +383,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t bstep = a.b_mn_major ? 128u : 2u;
       int it_g = 0, tl = 0;
       for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
-        const int n0 = ((t / pm_tiles) % n_tiles) * BN;
+        int m_lin_u, n_tile_u, z_u;
+        decode(t, m_lin_u, n_tile_u, z_u);
+        const int n0 = n_tile_u * BN;
         const uint32_t idesc = make_idesc_f16(BM * CTAS, n_cur(n0), a.fmt, a.b_mn_major);
         const int buf = tl & 1;
         const uint32_t use = (uint32_t)(tl >> 1);
@@ -424,13 +444,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int slab_it = 0;
     int tl = 0;
     for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
-      int m_tile = (t % pm_tiles) * CTAS + rank;
+      int m_lin, n_tile, z;
+      decode(t, m_lin, n_tile, z);
+      int m_tile = m_lin * CTAS + rank;
       const int m_tile_lin = m_tile;
-      const int rest = t / pm_tiles;
-      const int n_tile = rest % n_tiles;
       const int n0 = n_tile * BN;
       const int Ncur = n_cur(n0);
-      const int z = rest / n_tiles;
       const int z1 = z / a.zdiv, z0 = z - z1 * a.zdiv;
       const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
       const int ty = m_tile % a.tiles_y;
@@ -812,6 +831,15 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   const CUtensorMap& mc = tmC ? *tmC : tmA;
   args.batch = batch;
   args.n_tiles = (args.n_total + args.bn_tile - 1) / args.bn_tile;
+  {
+    // plain GEMMs whose activation matrix does not survive in L2 (126 MB, shared with the output stream) until the
+    // next N pass.  Measured at cfg2: M76800 N320 K1280 100 -> 85 us, M19200 N640 K2560 87 -> 75 us; convolutions
+    // (9 taps re-read each tile from L2 anyway, weights 20+ MB) are slower this way and keep the M-fastest order.
+    static const char* force = getenv("UG_NFAST");
+    const double a_bytes = (double)args.W * args.H * args.N * args.kchunks * 64.0 * 2.0;
+    args.n_fastest = force ? atoi(force)
+                           : (args.n_tiles > 1 && batch == 1 && args.num_taps == 1 && a_bytes > 40e6) ? 1 : 0;
+  }
   const long long m_tiles = (long long)args.tiles_x * args.tiles_y * args.tiles_n;
   const long long units = ((m_tiles + ctas - 1) / ctas) * args.n_tiles * batch;
   if (units <= 0 || units > 0x7fffffffLL) return (int)cudaErrorInvalidValue;

@@ -47,6 +47,7 @@ struct TapGemmArgs {
   int tma_store;           // finished 64-column slabs leave through smem + TMA tile stores (coalesced);
                            // needs a 16-bit output, ldc % 8 == 0, batch 1 and the output tensor map
   int n_tiles, batch;      // filled by launch_tapgemm
+  int n_fastest;           // tile order (filled by launch_tapgemm): N tiles of one M tile run concurrently
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
   int out_fp32;
   int geglu;               // columns [0,128) of each 256-wide tile gate-multiplied by gelu([128,256))
