@@ -19,6 +19,11 @@ long long gn_partial_floats(int C, long long rows, long long rows_per_set, int G
 constexpr int kGnMaxSets = 1024;
 int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
                     int G, float eps, float* stats, unsigned int* counters, int fmt, cudaStream_t st);
+// statistics + apply in ONE launch (grid-wide flag between the phases; needs 3 * kGnMaxSets zeroed counters).
+// Returns cudaErrorNotSupported (801) when the grid cannot be co-resident: use launch_gn_stats + launch_gn_apply.
+int launch_gn_fused(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set, int G,
+                    float eps, float* stats, unsigned int* counters, const float* gamma, const float* beta, int silu,
+                    void* y, int fmt, cudaStream_t st);
 // folds the partials into (mean, rstd) per (set, group), stored behind the partials in `stats`
 int launch_gn_finalize(int C, long long rows, long long rows_per_set, int G, float eps, float* stats,
                        cudaStream_t st);

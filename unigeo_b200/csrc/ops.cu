@@ -421,16 +421,23 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
   float* stats = c.allocf(gn_partial_floats(C1 + C2, rows, rows_per_set, G));
   if (!c.dry) {
     if (!c.gn_counters) {
-      c.gn_counters = reinterpret_cast<unsigned int*>(c.dmalloc(kGnMaxSets * sizeof(unsigned int)));
-      UG_CUDA(cudaMemset(c.gn_counters, 0, kGnMaxSets * sizeof(unsigned int)));
+      c.gn_counters = reinterpret_cast<unsigned int*>(c.dmalloc(3 * kGnMaxSets * sizeof(unsigned int)));
+      UG_CUDA(cudaMemset(c.gn_counters, 0, 3 * kGnMaxSets * sizeof(unsigned int)));
     }
-    op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, eps, stats, c.gn_counters, c.fmt, c.stream),
-             prof_name(c, "gn_stats", "rows" + std::to_string(rows) + " C" + std::to_string(C1 + C2) + " sets" + std::to_string(sets)),
-             0.0, 2.0 * rows * (C1 + C2));
-    op_check(c, launch_gn_apply(x1, C1, x2, C2, rows, rows_per_set, G, stats, gamma, beta, eps, silu, y, c.fmt,
-                                c.stream),
-             prof_name(c, "gn_apply", "rows" + std::to_string(rows) + " C" + std::to_string(C1 + C2) + " sets" + std::to_string(sets)),
-             0.0, 4.0 * rows * (C1 + C2));
+    static const bool two_pass = getenv("UG_GN_TWO_PASS") != nullptr;
+    const std::string shape = "rows" + std::to_string(rows) + " C" + std::to_string(C1 + C2) + " sets" + std::to_string(sets);
+    int r = two_pass ? (int)cudaErrorNotSupported
+                     : launch_gn_fused(x1, C1, x2, C2, rows, rows_per_set, G, eps, stats, c.gn_counters, gamma, beta, silu,
+                                       y, c.fmt, c.stream);
+    if (r == (int)cudaErrorNotSupported) {      // grid cannot be co-resident: two launches
+      op_check(c, launch_gn_stats(x1, C1, x2, C2, rows, rows_per_set, G, eps, stats, c.gn_counters, c.fmt, c.stream),
+               prof_name(c, "gn_stats", shape), 0.0, 2.0 * rows * (C1 + C2));
+      op_check(c, launch_gn_apply(x1, C1, x2, C2, rows, rows_per_set, G, stats, gamma, beta, eps, silu, y, c.fmt,
+                                  c.stream),
+               prof_name(c, "gn_apply", shape), 0.0, 4.0 * rows * (C1 + C2));
+    } else {
+      op_check(c, r, prof_name(c, "gn_fused", shape), 0.0, 4.0 * rows * (C1 + C2));
+    }
   }
   c.ws.release(m);
 }
