@@ -171,6 +171,9 @@ def run_b200(a):
     # seeded random-init weights drawn directly on the device (values are irrelevant to the timing)
     eng.load_state_dict("unet", synthetic_state_dict(unet_param_shapes(cfg.unet), 1000, torch.float16, eng.device))
     eng.load_state_dict("vae", synthetic_state_dict(vae_param_shapes(cfg.vae), 2000, torch.float16, eng.device))
+    if not a.no_e2e:
+        from unigeo_b200.clip_embed import ClipEmbedder
+        ClipEmbedder(eng, device_weights=True)                     # ViT-H/14 image encoder for the e2e plugin call
     eng.finalize()
     eng.prepare(T, h, w)
     dev = eng.device
@@ -339,8 +342,8 @@ def run_e2e(a, eng, cfg, world, rank, dev):
     plug = object.__new__(DepthCrafter)                       # reuse the already-loaded engine (one copy of weights)
     plug.device, plug.cfg, plug.dtype, plug.engine = dev, cfg, a.dtype, eng
     plug.num_inference_steps, plug.seed, plug._stage = a.e2e_steps, 1234 + rank, None
-    clip = ClipEmbedder(cfg.clip_embed_dim, dev, torch.float16 if a.dtype == "fp16" else torch.bfloat16)
-    plug.pipeline = DepthCrafterPipelineB200(cfg, eng, clip)
+    plug.pipeline = DepthCrafterPipelineB200(cfg, eng, ClipEmbedder.__new__(ClipEmbedder))
+    plug.pipeline.clip.engine = eng                           # CLIP weights were loaded with the rest (run_b200)
     data = make_clip(a.frames, a.height, a.width, seed=1234 + rank)
     plug.forward(data)                                         # warm-up (CLIP autotune, workspace sizing)
     torch.cuda.synchronize()
@@ -358,7 +361,7 @@ def run_e2e(a, eng, cfg, world, rank, dev):
     d2h = out["pred_depths"].numel() * 4 + out["pred_normals"].numel() * 4
     return {"value": world * a.e2e_steps / dt, "unit": "steps/s", "h2d_bytes_per_step": h2d / a.e2e_steps,
             "d2h_bytes_per_step": d2h / a.e2e_steps, "clip_seconds": dt, "num_inference_steps": a.e2e_steps,
-            "call": "unigeo_b200.model.DepthCrafter.forward(data) (H2D images + prepare_input + CLIP + VAE encode + denoise + "
+            "call": "unigeo_b200.model.DepthCrafter.forward(data) (H2D images + prepare_input + CLIP ViT-H + VAE encode + denoise + "
                     "VAE decode + depth/normal post-processing + D2H)"}
 
 

@@ -83,6 +83,14 @@ typedef struct ug_unet2d_cfg {
   float beta_start, beta_end;
 } ug_unet2d_cfg;
 
+/* CLIP image encoder (ViT, transformers CLIPVisionModelWithProjection layout) of the DepthCrafter pipeline's
+ * encode_video step.  Optional: set before ug_ctx_finalize when "clip." weights are
+ * loaded.  ViT-H/14: hidden 1280, 32 layers, 16 heads, mlp 5120, patch 14, image 224, proj_dim 1024. */
+typedef struct ug_clip_cfg {
+  int32_t hidden, layers, heads, mlp, patch, image_size, proj_dim;
+  float ln_eps;
+} ug_clip_cfg;
+
 int ug_version(void);
 const char* ug_last_error(void);
 
@@ -173,6 +181,13 @@ int ug_vae_decode_frames(ug_ctx* ctx, const float* lat, int T, int h, int w, int
  * intrinsics fp32 [T][3][3] (device) -> depths fp32 [T][H][W], normals fp32 [T][H][W][3]. */
 int ug_depth_postprocess(ug_ctx* ctx, const float* frames, const float* intrinsics, int T, int H, int W,
                          float* depths, float* normals, void* stream);
+
+/* Replaces [UPSTREAM] encode_video (antialiased 224x224 resize, CLIP normalisation, ViT + projection):
+ * video fp32 [F][3][H][W] in [-1,1] (ug_vae_encode_frames' video_nchw) -> image embeddings fp32 [F][proj_dim],
+ * the encoder_hidden_states ug_set_clip_context takes.  Weight keys: "clip." + transformers state_dict names;
+ * patch_embedding.weight is loaded reshaped to [hidden][3*patch*patch], position_embedding.weight flattened. */
+int ug_ctx_set_clip_cfg(ug_ctx* ctx, const ug_clip_cfg* cfg);
+int ug_clip_embed(ug_ctx* ctx, const float* video, int F, int H, int W, float* enc, void* stream);
 
 /* Kernels launched on behalf of this context since the last reset (bench "gpu_launches"). */
 long long ug_ctx_launch_count(ug_ctx* ctx, int reset);

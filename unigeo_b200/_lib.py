@@ -58,6 +58,11 @@ class UNet2DCfg(C.Structure):
     ]
 
 
+class ClipCfg(C.Structure):
+    _fields_ = [("hidden", C.c_int32), ("layers", C.c_int32), ("heads", C.c_int32), ("mlp", C.c_int32),
+                ("patch", C.c_int32), ("image_size", C.c_int32), ("proj_dim", C.c_int32), ("ln_eps", C.c_float)]
+
+
 _P, _I, _L, _F = C.c_void_p, C.c_int, C.c_longlong, C.c_float
 
 _SIGNATURES = {
@@ -79,6 +84,8 @@ _SIGNATURES = {
     "ug_refine_frames_2d": ([_P, C.c_char_p, C.c_char_p, _P, _P, _I, _I, _I, _I, _I, _P, _P], C.c_int),
     "ug_vae2d_encode": ([_P, _P, _I, _I, _I, _F, _P, _P], C.c_int),
     "ug_vae2d_decode": ([_P, _P, _I, _I, _I, _P, _P, _P], C.c_int),
+    "ug_ctx_set_clip_cfg": ([_P, C.POINTER(ClipCfg)], C.c_int),
+    "ug_clip_embed": ([_P, _P, _I, _I, _I, _P, _P], C.c_int),
     "ug_prepare_frames": ([_P, _P, _I, _I, _I, _P, _P], C.c_int),
     "ug_vae_encode_frames": ([_P, _P, _P, _F, _I, _I, _I, _P, _P, _P], C.c_int),
     "ug_vae_decode_frames": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),

@@ -57,10 +57,25 @@ class VAEConfig:
 
 
 @dataclass(frozen=True)
+class ClipConfig:
+    """CLIP image encoder (transformers ``CLIPVisionConfig`` fields); default = ViT-H/14 as shipped in
+    stable-video-diffusion-img2vid-xt/image_encoder."""
+    hidden_size: int = 1280
+    num_hidden_layers: int = 32
+    num_attention_heads: int = 16
+    intermediate_size: int = 5120
+    patch_size: int = 14
+    image_size: int = 224
+    projection_dim: int = 1024
+    layer_norm_eps: float = 1e-5
+
+
+@dataclass(frozen=True)
 class PipelineConfig:
     unet: UNetSTConfig = field(default_factory=UNetSTConfig)
     vae: VAEConfig = field(default_factory=VAEConfig)
     clip_embed_dim: int = 1024
+    clip: ClipConfig = field(default_factory=ClipConfig)
     # scheduler (SURVEY.md App. A.2)
     sigma_min: float = 0.002
     sigma_max: float = 700.0
@@ -129,6 +144,8 @@ def tiny_config() -> PipelineConfig:
         ),
         vae=VAEConfig(block_out_channels=(32, 64, 128, 128)),
         clip_embed_dim=64,
+        clip=ClipConfig(hidden_size=64, num_hidden_layers=2, num_attention_heads=2, intermediate_size=128,
+                        patch_size=32, image_size=224, projection_dim=64),
     )
 
 

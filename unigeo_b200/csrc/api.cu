@@ -162,6 +162,7 @@ int ug_ctx_finalize(ug_ctx* u, void* stream) {
     unet_finalize(c, st);
     unet2d_finalize(c, st);
     vae_finalize(c, st);
+    clip_finalize(c, st);
     UG_CUDA(cudaStreamSynchronize(st));
     c.finalized = true;
   });
@@ -257,6 +258,27 @@ int ug_vae_encode(ug_ctx* u, const float* img, const float* noise, float noise_s
                                         img16, c.fmt, c.stream), "image in");
       vae_encode(c, "vae.", img16, N, H, W, 1.f, lat_mean);
     });
+  });
+}
+
+int ug_ctx_set_clip_cfg(ug_ctx* u, const ug_clip_cfg* cfg) {
+  return guard([&] {
+    UG_CHECK(u && cfg, UG_ERR_INVALID, "null argument");
+    UG_CHECK(cfg->layers >= 1 && cfg->heads >= 1 && cfg->hidden % cfg->heads == 0 && cfg->hidden % 8 == 0 &&
+                 cfg->mlp % 8 == 0 && cfg->patch >= 1 && cfg->image_size % cfg->patch == 0 && cfg->proj_dim >= 1,
+             UG_ERR_INVALID, "bad CLIP config");
+    u->c.cfg_clip = *cfg;
+    u->c.finalized = false;
+  });
+}
+
+int ug_clip_embed(ug_ctx* u, const float* video, int F, int H, int W, float* enc, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && video && enc, UG_ERR_INVALID, "null argument");
+    UG_CHECK(u->c.finalized, UG_ERR_STATE, "ug_ctx_finalize must precede ug_clip_embed");
+    UG_CHECK(F >= 1 && H >= 2 && W >= 2, UG_ERR_INVALID, "bad shape");
+    const std::string sig = "clip:" + std::to_string(F) + "x" + std::to_string(H) + "x" + std::to_string(W);
+    run_sized(u, sig, stream, [&](Ctx& c) { clip_embed(c, video, F, H, W, enc); });
   });
 }
 

@@ -77,6 +77,7 @@ struct Epi {                     // epilogue description for tapgemm-backed ops
   float alpha = 0.f;
   float scale = 1.f;
   int geglu = 0;
+  int act = 0;                   // 1: GELU(acc + bias) before residual
 };
 
 struct UNetModel;
@@ -96,6 +97,7 @@ struct Ctx {
   VaeModel* vae = nullptr;
   ug_unet2d_cfg cfg2d{};         // StableNormal path (ug_ctx_set_unet2d_cfg); num_blocks == 0: not configured
   Nets2D* nets2d = nullptr;
+  ug_clip_cfg cfg_clip{};        // CLIP image encoder (ug_ctx_set_clip_cfg); layers == 0: not configured
   bool finalized = false;
   unsigned int* gn_counters = nullptr;   // "last CTA" tickets of the fused GroupNorm finalize
   bool attn_materialized = false; // true: head_dim-64 attention through QK^T / softmax / PV GEMMs (A/B debug)
@@ -131,7 +133,10 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
 void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm, int Cout, int chunk,
                const Epi& e);
 // self-attention over N tokens per frame from a fused [F*N][3C] q|k|v buffer, head_dim dh -> out [F*N][C]
-void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, void* out);
+// n_valid < N: keys >= n_valid are padding (masked); scale <= 0: 1/sqrt(dh).  head_dim 64 runs the fused flash
+// kernel (needs n_valid == N); other multiples of 64 materialise the scores.
+void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, void* out, int n_valid = 0,
+                          float scale = 0.f);
 
 void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set,
            const float* gamma, const float* beta, float eps, int silu, void* y);

@@ -504,7 +504,7 @@ layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float*
 
 // ------------------------------------------------------------------ row softmax (block per row)
 template <typename T, int VPT>
-__global__ void softmax_rows_kernel(void* __restrict__ s, long long rows, int n, float scale_log2e) {
+__global__ void softmax_rows_kernel(void* __restrict__ s, long long rows, int n, int n_valid, float scale_log2e) {
   __shared__ float red[32];
   const long long row = blockIdx.x;
   const int nvec = n >> 3;
@@ -517,7 +517,10 @@ __global__ void softmax_rows_kernel(void* __restrict__ s, long long rows, int n,
     if (i < nvec) {
       unpack8<T>(p[i], f[k]);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { f[k][j] *= scale_log2e; m = fmaxf(m, f[k][j]); }
+      for (int j = 0; j < 8; ++j) {
+        f[k][j] = (i * 8 + j < n_valid) ? f[k][j] * scale_log2e : -INFINITY;   // padded keys get probability 0
+        m = fmaxf(m, f[k][j]);
+      }
     }
   }
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -1200,18 +1203,18 @@ int launch_layernorm(const void* x, long long rows, int C, const float* gamma, c
 #undef UG_LN
 }
 
-int launch_softmax_rows(void* s, long long rows, int n, float scale, int fmt, cudaStream_t st) {
-  if (n & 7) return (int)cudaErrorInvalidValue;
+int launch_softmax_rows(void* s, long long rows, int n, int n_valid, float scale, int fmt, cudaStream_t st) {
+  if ((n & 7) || n_valid < 1 || n_valid > n) return (int)cudaErrorInvalidValue;
   const float sl = scale * 1.4426950408889634f;
   const int nvec = n / 8;
   if (nvec <= 32) {
-    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 1><<<(unsigned)rows, 32, 0, st>>>(s, rows, n, sl)));
+    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 1><<<(unsigned)rows, 32, 0, st>>>(s, rows, n, n_valid, sl)));
   } else if (nvec <= 128) {
-    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 1><<<(unsigned)rows, 128, 0, st>>>(s, rows, n, sl)));
+    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 1><<<(unsigned)rows, 128, 0, st>>>(s, rows, n, n_valid, sl)));
   } else if (nvec <= 512) {
-    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 2><<<(unsigned)rows, 256, 0, st>>>(s, rows, n, sl)));
+    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 2><<<(unsigned)rows, 256, 0, st>>>(s, rows, n, n_valid, sl)));
   } else if (nvec <= 2048) {
-    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 8><<<(unsigned)rows, 256, 0, st>>>(s, rows, n, sl)));
+    UG_DISPATCH_FMT(fmt, (softmax_rows_kernel<T, 8><<<(unsigned)rows, 256, 0, st>>>(s, rows, n, n_valid, sl)));
   } else {
     return (int)cudaErrorInvalidValue;
   }

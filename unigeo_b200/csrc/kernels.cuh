@@ -36,8 +36,8 @@ int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long ro
 int launch_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
                      const float* add, int add_div, void* y, int fmt, cudaStream_t st);
 
-// ---- row softmax in place over [rows][n] 16-bit (scores pre-scaled) ------------------
-int launch_softmax_rows(void* s, long long rows, int n, float scale, int fmt, cudaStream_t st);
+// ---- row softmax in place over [rows][n] 16-bit; columns >= n_valid (padded keys) get probability 0 ----
+int launch_softmax_rows(void* s, long long rows, int n, int n_valid, float scale, int fmt, cudaStream_t st);
 
 // ---- temporal self-attention: sequences of T tokens per (pixel, head), head_dim 64 ----
 // qkv: [T][P][3C] (q | k | v), out: [T][P][C]; heads = C / 64.

@@ -82,6 +82,10 @@ void vae2d_decode(Ctx& c, const void* z16, int N, int h, int w, float* img_nchw,
 void vae_decode(Ctx& c, const void* z16, int T, int h, int w, int chunk, float* img_nchw,
                 float* frames_hwc = nullptr);
 
+// CLIP image encoder (clip.cu): padded q|k|v / out_proj weights; video fp32 [F][3][H][W] -> enc fp32 [F][proj_dim]
+void clip_finalize(Ctx& c, cudaStream_t st);
+void clip_embed(Ctx& c, const float* video, int F, int H, int W, float* enc);
+
 float sigmoidf_host(float x);
 
 }  // namespace ug

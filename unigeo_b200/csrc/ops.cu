@@ -89,6 +89,7 @@ void fill_epi(TapGemmArgs& a, const Epi& e, int fmt) {
   a.alpha = e.alpha;
   a.scale = e.scale;
   a.geglu = e.geglu;
+  a.act = e.act;
 }
 
 void base_args(TapGemmArgs& a) {
@@ -322,11 +323,12 @@ void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm,
 
 // v1 attention: S = Q K^T (tapgemm, batched over frame x head) -> row softmax -> O = P V
 // (tapgemm with the MN-major B path reading V in place).  Scores live in the workspace.
-void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, void* out) {
-  UG_CHECK(dh == 64 || dh == C, UG_ERR_INVALID, "attention: head_dim must be 64 or C");
-  UG_CHECK((N % 8) == 0 && (dh % 64) == 0, UG_ERR_INVALID, "attention: N % 8 and head_dim % 64");
+void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, void* out, int n_valid, float scale) {
+  UG_CHECK((N % 8) == 0 && (dh % 64) == 0 && (C % dh) == 0, UG_ERR_INVALID, "attention: N % 8, head_dim % 64, C % head_dim");
+  if (n_valid <= 0) n_valid = N;
+  if (scale <= 0.f) scale = 1.0f / sqrtf((float)dh);
   const int heads = C / dh;
-  if (dh == 64 && !c.attn_materialized) {
+  if (dh == 64 && n_valid == N && !c.attn_materialized) {
     // fused flash attention (tcgen05): no score tensor in HBM
     if (c.dry) return;
     TmapDesc d;
@@ -339,7 +341,7 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
     if (r != 0) throw UgError(UG_ERR_CUDA, "cuTensorMapEncodeTiled(qkv) failed: " + std::to_string(r));
     FmhaArgs fa;
     fa.N = N; fa.C = C; fa.heads = heads; fa.F = F;
-    fa.scale_log2 = 1.4426950408889634f / sqrtf((float)dh);
+    fa.scale_log2 = 1.4426950408889634f * scale;
     fa.out = out; fa.fmt = c.fmt;
     op_check(c, launch_fmha_d64(tm, fa, c.stream),
              prof_name(c, "fmha_d64", "F" + std::to_string(F) + " N" + std::to_string(N) + " heads" + std::to_string(heads)),
@@ -377,7 +379,7 @@ void op_spatial_attention(Ctx& c, const void* qkv, int F, int N, int C, int dh, 
       make_b_map(&mb, qkv, c.fmt, (unsigned long long)3 * C, (unsigned long long)F * N, rowb, a.bn_tile / a.ctas);
       launch(c, ma, mb, a, F * heads, "tapgemm.attn_qk", dh);
     }
-    op_check(c, launch_softmax_rows(S, (long long)F * heads * N, N, 1.0f / sqrtf((float)dh), c.fmt, c.stream),
+    op_check(c, launch_softmax_rows(S, (long long)F * heads * N, N, n_valid, scale, c.fmt, c.stream),
              "softmax_rows", 0.0, 4.0 * F * heads * (double)N * N);
     {  // O[z] = P[z] V[z]
       TapGemmArgs a;

@@ -117,6 +117,14 @@ __device__ __forceinline__ void finish_cols(float (&f)[NC], const TapGemmArgs& a
         if (full || j < ncols_valid) f[j] += __ldg(fb + j);
     }
   }
+  if (a.act == 1) {
+#pragma unroll
+    for (int j = 0; j < NC; j += 2) {
+      const float2 o = gelu_erf2(make_float2(f[j], f[j + 1]));
+      f[j] = o.x;                     // gelu_erf2 returns 0.5 x (1 + erf(x / sqrt 2)): the GELU itself
+      f[j + 1] = o.y;
+    }
+  }
   if (!AUX) return;      // residual / blend handled by the caller (prefetched)
   if (a.res != nullptr) {
     const long long off = pix * a.ldr + col0;
@@ -826,7 +834,8 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   if (args.tma_store && (tmC == nullptr || (args.bn_tile & 63) || batch != 1 || args.out_fp32))
     return (int)cudaErrorInvalidValue;
   if (args.geglu && (args.bn_tile != 256 || (args.n_total & 255))) return (int)cudaErrorInvalidValue;
-  if (args.geglu && (args.res != nullptr || args.blend != nullptr || args.fbias != nullptr || args.scale != 1.0f))
+  if (args.geglu && (args.res != nullptr || args.blend != nullptr || args.fbias != nullptr || args.scale != 1.0f ||
+                     args.act != 0))
     return (int)cudaErrorInvalidValue;             // the GEGLU epilogue is bias + gate only
   const CUtensorMap& mc = tmC ? *tmC : tmA;
   args.batch = batch;

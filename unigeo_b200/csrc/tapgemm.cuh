@@ -50,6 +50,7 @@ struct TapGemmArgs {
   int n_fastest;           // tile order (filled by launch_tapgemm): N tiles of one M tile run concurrently
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
   int out_fp32;
+  int act;                 // 1: exact (erf) GELU on (acc * scale + bias) before residual / blend (ViT MLPs)
   int geglu;               // columns [0,128) of each 256-wide tile gate-multiplied by gelu([128,256))
   void* out;
   long long ldc;

@@ -69,6 +69,7 @@ void add_weight(Ctx& c, const std::string& key, void* p, bool f32, int taps, int
 
 // ------------------------------------------------------------------ weight fusion
 void fuse_qkv(Ctx& c, const std::string& k, cudaStream_t st) {
+  if (c.has(k + ".to_qkv.weight")) return;       // ug_ctx_finalize may run again after more weights were loaded
   const Weight& q = c.W(k + ".to_q.weight");
   const Weight& kk = c.W(k + ".to_k.weight");
   const Weight& v = c.W(k + ".to_v.weight");
@@ -91,6 +92,7 @@ void fuse_qkv(Ctx& c, const std::string& k, cudaStream_t st) {
 }
 
 void fuse_geglu(Ctx& c, const std::string& k, cudaStream_t st) {
+  if (c.has(k + ".net.0.proj.geglu.weight")) return;
   const Weight& w = c.W(k + ".net.0.proj.weight");
   const int n = w.cout, K = w.cin, half = n / 2;
   UG_CHECK(half % 128 == 0, UG_ERR_WEIGHT, "fuse_geglu: inner dim must be a multiple of 128: " + k);
@@ -122,6 +124,7 @@ void unet_finalize(Ctx& c, cudaStream_t st) {
     fuse_geglu(c, k + ".temporal_transformer_blocks.0.ff_in", st);
     fuse_geglu(c, k + ".temporal_transformer_blocks.0.ff", st);
   }
+  if (c.has(U + "__temb_all.weight")) return;
   // stack every time_emb_proj (spatial + temporal resnets) into one GEMV; fold conv1.bias in
   const int E = c.cfg.unet_block_out[0] * 4;
   int total = 0;

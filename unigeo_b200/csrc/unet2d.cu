@@ -65,6 +65,7 @@ void add_weight2d(Ctx& c, const std::string& key, void* p, bool f32, int cout, i
 
 // attn2: to_k | to_v stacked -> one [2C][D] projection of the context
 void fuse_kv(Ctx& c, const std::string& k, cudaStream_t st) {
+  if (c.has(k + ".to_kv.weight")) return;
   const Weight& wk = c.W(k + ".to_k.weight");
   const Weight& wv = c.W(k + ".to_v.weight");
   UG_CHECK(wk.cin == wv.cin && wk.cout == wv.cout, UG_ERR_WEIGHT, "fuse_kv: to_k / to_v must agree: " + k);

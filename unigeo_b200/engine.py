@@ -45,6 +45,12 @@ class Engine:
         self._shape: Tuple[int, int, int] | None = None
         self._finalized = False
         self.sn_cfg = sn_cfg
+        cc = getattr(cfg, "clip", None)
+        if cc is not None:           # CLIP image encoder dims (weights optional; used by clip_embed)
+            self._cfg_clip = _lib.ClipCfg(cc.hidden_size, cc.num_hidden_layers, cc.num_attention_heads,
+                                          cc.intermediate_size, cc.patch_size, cc.image_size, cc.projection_dim,
+                                          cc.layer_norm_eps)
+            _lib.check(self.lib.ug_ctx_set_clip_cfg(self._ctx, C.byref(self._cfg_clip)))
         if sn_cfg is not None:       # StableNormal path: 2-D UNet / ControlNet dims (the 2-D VAE uses cfg.vae)
             if sn_cfg.unet2d.norm_groups != cfg.unet.norm_groups or sn_cfg.vae2d != cfg.vae:
                 raise ValueError("the 2-D path shares GroupNorm groups and VAE dims with the pipeline config")
@@ -58,6 +64,11 @@ class Engine:
             for key, t in sd.items():
                 if t.dtype not in _TORCH_TO_UG:
                     t = t.float()
+                if prefix == "clip":             # see include/unigeo_b200.h: ug_clip_embed
+                    if key.endswith("patch_embedding.weight"):
+                        t = t.reshape(t.shape[0], -1)
+                    elif key.endswith("position_embedding.weight"):
+                        t = t.reshape(-1)
                 t = t.to(self.device).contiguous()
                 shape = (C.c_int64 * t.dim())(*t.shape)
                 _lib.check(self.lib.ug_ctx_load_weight(self._ctx, f"{prefix}.{key}".encode(), t.data_ptr(),
@@ -144,6 +155,17 @@ class Engine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.ug_vae_decode_temporal(self._ctx, lat.data_ptr(), T, h, w, int(chunk),
                                                        out.data_ptr(), _stream()))
+        return out
+
+    def clip_embed(self, video: torch.Tensor) -> torch.Tensor:
+        """video [F,3,H,W] in [-1,1] -> CLIP image embeddings [F, projection_dim] ("clip" weights)."""
+        if not self._finalized:
+            self.finalize()
+        v = _f32(video, self.device)
+        F_, _, H, W = v.shape
+        out = torch.empty((F_, self.cfg.clip.projection_dim), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_clip_embed(self._ctx, v.data_ptr(), F_, H, W, out.data_ptr(), _stream()))
         return out
 
     def prepare_frames(self, images: torch.Tensor) -> torch.Tensor:

@@ -51,12 +51,11 @@ class DepthCrafter:
             wdt = torch.float16 if kwargs.get("device_weights") else torch.float32
             self.engine.load_state_dict("unet", synthetic_state_dict(unet_param_shapes(self.cfg.unet), 1000 + s, wdt, wdev))
             self.engine.load_state_dict("vae", synthetic_state_dict(vae_param_shapes(self.cfg.vae), 2000 + s, wdt, wdev))
-        self.engine.finalize()
         clip = None
-        if kwargs.get("clip", "random") != "none":
-            clip = ClipEmbedder(self.cfg.clip_embed_dim, self.device,
-                                torch.float16 if self.dtype == "fp16" else torch.bfloat16,
-                                pretrained=clip_dir if clip_dir and os.path.isdir(clip_dir) else None)
+        if kwargs.get("clip", "random") != "none":       # CLIP image encoder weights ride in the same context
+            clip = ClipEmbedder(self.engine, pretrained=clip_dir if clip_dir and os.path.isdir(clip_dir) else None,
+                                device_weights=bool(kwargs.get("device_weights")))
+        self.engine.finalize()
         self.pipeline = DepthCrafterPipelineB200(self.cfg, self.engine, clip)
         print(f"Using device: {self.device}")
 

@@ -15,7 +15,7 @@ from typing import Dict, Tuple
 
 import torch
 
-from .config import UNet2DConfig, UNetSTConfig, VAEConfig
+from .config import ClipConfig, UNet2DConfig, UNetSTConfig, VAEConfig
 
 Shapes = "OrderedDict[str, Tuple[int, ...]]"
 
@@ -297,10 +297,35 @@ def vae2d_param_shapes(cfg: VAEConfig) -> Shapes:
     return d
 
 
+# --------------------------------------------------------------------------- CLIP image encoder
+def clip_param_shapes(cfg: ClipConfig) -> Shapes:
+    """Ordered {transformers key: shape} of ``CLIPVisionModelWithProjection`` (state_dict names, including
+    upstream's ``pre_layrnorm`` spelling)."""
+    d: Shapes = OrderedDict()
+    c, p = cfg.hidden_size, cfg.patch_size
+    n_pos = (cfg.image_size // p) ** 2 + 1
+    d["vision_model.embeddings.class_embedding"] = (c,)
+    d["vision_model.embeddings.patch_embedding.weight"] = (c, 3, p, p)
+    d["vision_model.embeddings.position_embedding.weight"] = (n_pos, c)
+    _norm(d, "vision_model.pre_layrnorm", c)
+    for i in range(cfg.num_hidden_layers):
+        b = f"vision_model.encoder.layers.{i}"
+        for k in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            _lin(d, f"{b}.self_attn.{k}", c, c)
+        _norm(d, f"{b}.layer_norm1", c)
+        _lin(d, f"{b}.mlp.fc1", c, cfg.intermediate_size)
+        _lin(d, f"{b}.mlp.fc2", cfg.intermediate_size, c)
+        _norm(d, f"{b}.layer_norm2", c)
+    _norm(d, "vision_model.post_layernorm", c)
+    _lin(d, "visual_projection", c, cfg.projection_dim, bias=False)
+    return d
+
+
 # --------------------------------------------------------------------------- synthetic
 def _is_norm_key(key: str) -> bool:
     leaf = key.rsplit(".", 2)[-2]
-    return leaf.startswith("norm") or leaf in ("group_norm", "conv_norm_out")
+    return (leaf.startswith("norm") or leaf.startswith("layer_norm")
+            or leaf in ("group_norm", "conv_norm_out", "pre_layrnorm", "post_layernorm"))
 
 
 def synthetic_state_dict(shapes: Shapes, seed: int, dtype=torch.float32, device="cpu") -> Dict[str, torch.Tensor]:
