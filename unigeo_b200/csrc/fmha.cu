@@ -21,6 +21,7 @@
 #include "ptx.cuh"
 
 #include <cstdio>
+#include <type_traits>
 #include <cstdlib>
 
 namespace ug {
@@ -40,6 +41,7 @@ constexpr int kSmem = kOffBar + 256;
 constexpr int kThreads = 320;
 constexpr uint32_t kColS = 0, kColO = 256;
 
+template <int FMT>
 __global__ void __launch_bounds__(kThreads, 1)
 fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ FmhaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -180,22 +182,30 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
     // P tile (K-major SWIZZLE_128B: row r, 16-byte chunk c16 of half hh at ((c16 ^ (r & 7)) * 16))
     // The TMEM load of chunk c+1 is in flight while chunk c goes through the MUFU (both cost ~256 clk per
     // chunk and SM; serialised they were the whole kernel time).
-    auto p_chunk = [&](const uint32_t (&v)[32], int c, uint32_t sP, float mref, int valid, float& rowsum,
-                       float& pmax) {
+    // MASK = the block has fewer than 128 real keys (last block of a ragged sequence): a compile-time branch, so
+    // that full blocks carry no per-element compare / select
+    auto p_chunk = [&](auto mask_tag, const uint32_t (&v)[32], int c, uint32_t sP, float mref, int valid,
+                       float& rowsum, float& pmax) {
+      constexpr bool MASK = decltype(mask_tag)::value;
       uint32_t pk[16];
+      // packed fp32 pipe (FFMA2 / FADD2): the softmax warps are issue bound (ncu: 52 % issue slots with 2.5 warps
+      // per scheduler), so the scale-and-shift and the row sum take half an instruction per element
+      const float2 sc2 = make_float2(sc, sc), nm2 = make_float2(-mref, -mref);
+      float2 rs2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, -mref));
-        float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, -mref));
-        if (valid != 128) {
-          if (c * 32 + i >= valid) p0 = 0.f;
-          if (c * 32 + i + 1 >= valid) p1 = 0.f;
+        const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
+        float2 pp = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+        if constexpr (MASK) {
+          if (c * 32 + i >= valid) pp.x = 0.f;
+          if (c * 32 + i + 1 >= valid) pp.y = 0.f;
         }
-        rowsum += p0 + p1;
-        pk[i >> 1] = a.fmt ? Elem<__nv_bfloat16>::pack2(p0, p1) : Elem<__half>::pack2(p0, p1);
+        rs2 = __fadd2_rn(rs2, pp);
+        pk[i >> 1] = FMT ? Elem<__nv_bfloat16>::pack2(pp.x, pp.y) : Elem<__half>::pack2(pp.x, pp.y);
       }
+      rowsum += rs2.x + rs2.y;
       // threshold test on the packed pairs: one packed max per two elements (p >= 0, inf stays inf)
-      if (a.fmt) {
+      if (FMT) {
         __nv_bfloat162 mx2 = *reinterpret_cast<__nv_bfloat162*>(&pk[0]);
 #pragma unroll
         for (int i = 1; i < 16; ++i) mx2 = __hmax2(mx2, *reinterpret_cast<__nv_bfloat162*>(&pk[i]));
@@ -216,22 +226,26 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
                      : "memory");
       }
     };
-    auto compute_p = [&](uint32_t sP, float mref, int valid, float& rowsum, float& pmax) {
+    auto compute_p_t = [&](auto mask_tag, uint32_t sP, float mref, int valid, float& rowsum, float& pmax) {
       rowsum = 0.f;
       pmax = 0.f;
       uint32_t va[32], vb[32];
       tmem_ld_32x32(lane_addr + colS, va);
       tmem_ld_wait();
       tmem_ld_32x32(lane_addr + colS + 32, vb);
-      p_chunk(va, 0, sP, mref, valid, rowsum, pmax);
+      p_chunk(mask_tag, va, 0, sP, mref, valid, rowsum, pmax);
       tmem_ld_wait();
       tmem_ld_32x32(lane_addr + colS + 64, va);
-      p_chunk(vb, 1, sP, mref, valid, rowsum, pmax);
+      p_chunk(mask_tag, vb, 1, sP, mref, valid, rowsum, pmax);
       tmem_ld_wait();
       tmem_ld_32x32(lane_addr + colS + 96, vb);
-      p_chunk(va, 2, sP, mref, valid, rowsum, pmax);
+      p_chunk(mask_tag, va, 2, sP, mref, valid, rowsum, pmax);
       tmem_ld_wait();
-      p_chunk(vb, 3, sP, mref, valid, rowsum, pmax);
+      p_chunk(mask_tag, vb, 3, sP, mref, valid, rowsum, pmax);
+    };
+    auto compute_p = [&](uint32_t sP, float mref, int valid, float& rowsum, float& pmax) {
+      if (valid == 128) compute_p_t(std::false_type{}, sP, mref, valid, rowsum, pmax);
+      else compute_p_t(std::true_type{}, sP, mref, valid, rowsum, pmax);
     };
     for (int j = 0; j < nb; ++j) {
       mbar_wait(&s_full[x], (uint32_t)j & 1u);
@@ -310,7 +324,7 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             const float x0 = __uint_as_float(o[g * 8 + e * 2]) * inv, x1 = __uint_as_float(o[g * 8 + e * 2 + 1]) * inv;
-            w[e] = a.fmt ? Elem<__nv_bfloat16>::pack2(x0, x1) : Elem<__half>::pack2(x0, x1);
+            w[e] = FMT ? Elem<__nv_bfloat16>::pack2(x0, x1) : Elem<__half>::pack2(x0, x1);
           }
           u.x = w[0]; u.y = w[1]; u.z = w[2]; u.w = w[3];
           dst[c * 4 + g] = u;
@@ -331,13 +345,15 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
 int launch_fmha_d64(const CUtensorMap& tm, const FmhaArgs& args, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fmha_d64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    cudaError_t e = cudaFuncSetAttribute(fmha_d64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(fmha_d64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   if (args.C != args.heads * 64 || (args.C & 7)) return (int)cudaErrorInvalidValue;
   dim3 grid((args.N + 255) / 256, args.heads, args.F);
-  return (int)launch_pdl(fmha_d64_kernel, grid, dim3(kThreads), kSmem, stream, tm, args);
+  return (int)launch_pdl(args.fmt ? fmha_d64_kernel<1> : fmha_d64_kernel<0>, grid, dim3(kThreads), kSmem, stream, tm, args);
 }
 
 }  // namespace ug
