@@ -107,14 +107,16 @@ void base_args(TapGemmArgs& a) {
 
 // A: rank-5 map (unused dims = 1).  dims[0] = channels.
 void make_a_map(CUtensorMap* m, const void* p, int fmt, const unsigned long long dims[5],
-                const unsigned long long strides_bytes[4], int box1, int box2, int box3, int box4) {
+                const unsigned long long strides_bytes[4], int box1, int box2, int box3, int box4,
+                bool chunk32 = false) {
   TmapDesc d;
   d.ptr = p;
   d.elem_fmt = fmt;
   d.rank = 5;
   for (int i = 0; i < 5; ++i) d.dims[i] = dims[i];
   for (int i = 0; i < 4; ++i) d.strides[i] = strides_bytes[i];
-  d.box[0] = 64;
+  d.box[0] = chunk32 ? 32 : 64;            // 32-column SWIZZLE_64B chunks: the residual-by-TMA epilogue
+  d.swizzle64 = chunk32 ? 1 : 0;
   d.box[1] = box1; d.box[2] = box2; d.box[3] = box3; d.box[4] = box4;
   int r = encode_tmap(m, d);
   if (r != 0) throw UgError(UG_ERR_CUDA, "cuTensorMapEncodeTiled(A) failed: " + std::to_string(r));
@@ -139,13 +141,20 @@ inline bool can_tma_store(const Epi& e) {
   return !off && !e.out_fp32 && (e.ldc % 8) == 0 && (reinterpret_cast<uintptr_t>(e.out) % 16) == 0;
 }
 
+// residual tiles by TMA (in-place 32-column chunks): 16-bit residual with 16-byte aligned rows, N % 32 == 0
+inline bool can_tma_res(const Epi& e, int n_out) {
+  static const bool off = getenv("UG_NO_TMA_RES") != nullptr;
+  return !off && can_tma_store(e) && e.res != nullptr && !e.geglu && (n_out % 32) == 0 && (e.ldr % 8) == 0 &&
+         (reinterpret_cast<uintptr_t>(e.res) % 16) == 0;
+}
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline int imin(int a, int b) { return a < b ? a : b; }
 
 // algorithmic work of one tapgemm launch: 2*M*N*K flops over the REAL (unpadded) extents;
 // bytes = A read once + output written once (16-bit), weights ignored (SURVEY.md §8 convention)
 void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmArgs& a, int batch,
-            const char* what, long long k_real, const CUtensorMap* mc = nullptr) {
+            const char* what, long long k_real, const CUtensorMap* mc = nullptr, const CUtensorMap* mr = nullptr) {
   const double M = (double)a.W * a.H * a.N * batch;
   const double flops = 2.0 * M * a.n_total * (double)k_real * a.num_taps;
   const double bytes = M * ((double)k_real + (a.geglu ? a.n_total / 2 : a.n_total)) * 2.0;
@@ -154,10 +163,10 @@ void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmA
     const std::string full = std::string(what) + " M" + std::to_string((long long)M) + " N" + std::to_string(a.n_total) +
                              " K" + std::to_string(k_real * a.num_taps) + " bn" + std::to_string(a.bn_tile) + "x" +
                              std::to_string(a.ctas) + (a.res ? " +res" : "") + (a.blend ? " +blend" : "") +
-                             (a.fbias ? " +fbias" : "") + (a.tma_store ? "" : " direct");
+                             (a.fbias ? " +fbias" : "") + (a.tma_store ? "" : " direct") + (a.res_tma ? " rtma" : "");
     name = c.prof_names.insert(full).first->c_str();
   }
-  op_check(c, launch_tapgemm(ma, mb, mc, a, batch, c.stream), name, flops, bytes);
+  op_check(c, launch_tapgemm(ma, mb, mc, a, batch, c.stream, mr), name, flops, bytes);
 }
 
 }  // namespace
@@ -176,9 +185,10 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   fill_epi(a, e, c.fmt);
   a.fbias_uniform = (e.fbias != nullptr && (a.fbias_div % 128) == 0) ? 1 : 0;   // tiles = 128 consecutive tokens
   a.tma_store = can_tma_store(e);
+  a.res_tma = can_tma_res(e, N) ? 1 : 0;
   a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
   const int bn = a.bn_tile / a.ctas;
-  CUtensorMap ma, mb, mc;
+  CUtensorMap ma, mb, mc, mr;
   unsigned long long dims[5] = {(unsigned long long)K, (unsigned long long)M, 1, 1, 1};
   unsigned long long st[4] = {(unsigned long long)ldx * 2, (unsigned long long)ldx * 2 * M,
                               (unsigned long long)ldx * 2 * M, (unsigned long long)ldx * 2 * M};
@@ -188,9 +198,15 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
     const unsigned long long rb = (unsigned long long)e.ldc * 2;
     unsigned long long od[5] = {(unsigned long long)(e.geglu ? N / 2 : N), (unsigned long long)M, 1, 1, 1};
     unsigned long long os[4] = {rb, rb * M, rb * M, rb * M};
-    make_a_map(&mc, e.out, c.fmt, od, os, 128, 1, 1, 1);
+    make_a_map(&mc, e.out, c.fmt, od, os, 128, 1, 1, 1, a.res_tma);
+    if (a.res_tma) {
+      const unsigned long long rr = (unsigned long long)e.ldr * 2;
+      unsigned long long rs[4] = {rr, rr * M, rr * M, rr * M};
+      make_a_map(&mr, e.res, c.fmt, od, rs, 128, 1, 1, 1, true);
+    }
   }
-  launch(c, ma, mb, a, 1, e.geglu ? "tapgemm.linear_geglu" : "tapgemm.linear", K, a.tma_store ? &mc : nullptr);
+  launch(c, ma, mb, a, 1, e.geglu ? "tapgemm.linear_geglu" : "tapgemm.linear", K, a.tma_store ? &mc : nullptr,
+         a.res_tma ? &mr : nullptr);
 }
 
 void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* Wm, int Cout, int stride,
@@ -226,15 +242,21 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
   a.n_total = Cout;
   fill_epi(a, e, c.fmt);
   a.tma_store = can_tma_store(e);
+  a.res_tma = can_tma_res(e, Cout) ? 1 : 0;
   a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
   const int bn = a.bn_tile / a.ctas;
-  CUtensorMap ma, mb, mc;
+  CUtensorMap ma, mb, mc, mr;
   if (a.tma_store) {
     const unsigned long long rb = (unsigned long long)e.ldc * 2;
     unsigned long long od[5] = {(unsigned long long)Cout, (unsigned long long)Wo, (unsigned long long)Ho,
                                 (unsigned long long)Nf, 1};
     unsigned long long os[4] = {rb, rb * Wo, rb * Wo * Ho, rb * Wo * Ho * Nf};
-    make_a_map(&mc, e.out, c.fmt, od, os, a.bw, a.bh, a.bn, 1);
+    make_a_map(&mc, e.out, c.fmt, od, os, a.bw, a.bh, a.bn, 1, a.res_tma);
+    if (a.res_tma) {
+      const unsigned long long rr = (unsigned long long)e.ldr * 2;
+      unsigned long long rs[4] = {rr, rr * Wo, rr * Wo * Ho, rr * Wo * Ho * Nf};
+      make_a_map(&mr, e.res, c.fmt, od, rs, a.bw, a.bh, a.bn, 1, true);
+    }
   }
   const unsigned long long rowb = (unsigned long long)C * 2;
   if (stride == 1) {
@@ -270,7 +292,7 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
     make_a_map(&ma, x, c.fmt, dims, st, a.bw, 1, a.bh, a.bn);
   }
   make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)9 * Cout, rowb, bn);
-  launch(c, ma, mb, a, 1, "tapgemm.conv3x3", C, a.tma_store ? &mc : nullptr);
+  launch(c, ma, mb, a, 1, "tapgemm.conv3x3", C, a.tma_store ? &mc : nullptr, a.res_tma ? &mr : nullptr);
 }
 
 void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm, int Cout, int chunk,
@@ -304,20 +326,26 @@ void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm,
     if (e.fbias) ec.fbias = e.fbias + (tok0 / ec.fbias_div) * e.fbias_ld;
     fill_epi(a, ec, c.fmt);
     a.tma_store = can_tma_store(ec);
+    a.res_tma = can_tma_res(ec, Cout) ? 1 : 0;
     a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
     const int bn = a.bn_tile / a.ctas;
-    CUtensorMap ma, mb, mc;
+    CUtensorMap ma, mb, mc, mr;
     if (a.tma_store) {
       const unsigned long long rb = (unsigned long long)ec.ldc * 2;
       unsigned long long od[5] = {(unsigned long long)Cout, (unsigned long long)P, (unsigned long long)Tc, 1, 1};
       unsigned long long os[4] = {rb, rb * P, rb * P * Tc, rb * P * Tc};
-      make_a_map(&mc, ec.out, c.fmt, od, os, a.bw, a.bh, 1, 1);
+      make_a_map(&mc, ec.out, c.fmt, od, os, a.bw, a.bh, 1, 1, a.res_tma);
+      if (a.res_tma) {
+        const unsigned long long rr = (unsigned long long)ec.ldr * 2;
+        unsigned long long rs[4] = {rr, rr * P, rr * P * Tc, rr * P * Tc};
+        make_a_map(&mr, ec.res, c.fmt, od, rs, a.bw, a.bh, 1, 1, true);
+      }
     }
     unsigned long long dims[5] = {(unsigned long long)C, (unsigned long long)P, (unsigned long long)Tc, 1, 1};
     unsigned long long st[4] = {rowb, rowb * P, rowb * P * Tc, rowb * P * Tc};
     make_a_map(&ma, reinterpret_cast<const char*>(x) + tok0 * rowb, c.fmt, dims, st, a.bw, a.bh, 1, 1);
     make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)3 * Cout, rowb, bn);
-    launch(c, ma, mb, a, 1, "tapgemm.tconv3", C, a.tma_store ? &mc : nullptr);
+    launch(c, ma, mb, a, 1, "tapgemm.tconv3", C, a.tma_store ? &mc : nullptr, a.res_tma ? &mr : nullptr);
   }
 }
 

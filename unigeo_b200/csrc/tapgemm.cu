@@ -254,7 +254,8 @@ __device__ __forceinline__ void stage_cols16(const float (&f)[16], uint32_t slab
 template <int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ TapGemmArgs a) {
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ TapGemmArgs a) {
   constexpr int kSt = CTAS == 2 ? kStages2 : kStages;
   constexpr int kStB = CTAS == 2 ? kStageBytes2 : kStageBytes;
   constexpr int G16 = 16 * CTAS;                     // granularity of the N extent of one UMMA
@@ -265,7 +266,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* empty_bar = full_bar + kSt;
   uint64_t* tmem_full_bar = empty_bar + kSt;         // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = tmem_empty_bar + 2;            // [2 column groups][4 chunk buffers] residual chunk landed
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 8);
   float* bias_s = reinterpret_cast<float*>(slabs + 4 * kSlabBytes + 256);   // [2][256] per-tile bias vectors
 
   const int warp = threadIdx.x >> 5;
@@ -307,6 +309,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (a.tma_store) tma_prefetch_desc(&tmC);
+    if (a.res_tma) tma_prefetch_desc(&tmR);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -318,6 +321,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_init(&tmem_full_bar[b], 1);
         mbar_init(&tmem_empty_bar[b], kEpiWarps * CTAS);
       }
+      for (int b = 0; b < 8; ++b) mbar_init(&res_bar[b], 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -450,6 +454,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool issuer = (warp == 2 + 4 * hsel) && lane == 0;   // issues this group's TMA stores
     const uint32_t slab_base = smem_u32(slabs + hsel * 2 * kSlabBytes);
     int slab_it = 0;
+    uint32_t ring_it = 0;                   // chunk ring position of this column group (res_tma path)
     int tl = 0;
     for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
       int m_lin, n_tile, z;
@@ -484,18 +489,118 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 256u;
       const int BNh = BN >> 1;              // GEGLU: [BNh value | BNh gate] accumulator columns
-      const bool prefetching = a.tma_store && !a.geglu && (a.res != nullptr || a.blend != nullptr);
+      const bool prefetching = a.res_tma || (a.tma_store && !a.geglu && (a.res != nullptr || a.blend != nullptr));
       if (!prefetching) {                   // (the prefetching path waits after issuing its first loads)
         mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
         tc_fence_after();
       }
 
-      if (a.tma_store && !a.geglu && (a.res != nullptr || a.blend != nullptr)) {
+      if (a.res_tma) {
+        // ---- residual by TMA, in place: the store staging memory of this column group is a ring of four
+        // [128 rows x 32 columns] chunk buffers (SWIZZLE_64B).  A residual chunk lands in its buffer two chunks
+        // ahead of use (the first two of a tile while the accumulator is still being produced), each thread adds
+        // its accumulator row into its own 64 bytes, and the same buffer leaves through a TMA tile store.
+        // Replaces 4 x LDG.128 per row and chunk, whose 32 distinct lines per request made the L1 tag stage the
+        // bottleneck of every residual-carrying GEMM (ncu: 30 sectors per request, +20 us per launch at L0).
+        const int out_w = Ncur, out_c0 = n0;
+        const float al = a.alpha, be = 1.0f - a.alpha;
+        const bool same_aux = a.blend != nullptr && a.blend == a.res && a.ldr == a.ldb;
+        const bool blend_regs = a.blend != nullptr && !same_aux;
+        auto chunk_col = [&](int qq) { return (hsel + 2 * (qq >> 1)) * 64 + (qq & 1) * 32; };
+        int nch = 0;
+        while (nch < 8 && chunk_col(nch) < out_w) ++nch;
+        uint8_t* ring = slabs + hsel * 2 * kSlabBytes;
+        uint64_t* rbar = res_bar + hsel * 4;
+        const uint32_t chunk_bytes = (uint32_t)(a.bw * a.bh * a.bn) * 64u;
+        auto issue_load = [&](int qq) {
+          const int b = (int)((ring_it + (uint32_t)qq) & 3u);
+          mbar_arrive_expect_tx(&rbar[b], chunk_bytes);
+          tma_load_5d(ring + b * 8192, &tmR, &rbar[b], out_c0 + chunk_col(qq), x0, y0, nn0, 0);
+        };
+        if (issuer && nch > 0) {
+          bulk_wait_group_read<1>();                           // the stores that last read these buffers are done
+          issue_load(0);
+          if (nch > 1) issue_load(1);
+        }
+        mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
+        tc_fence_after();
+        bool released = false;
+#pragma unroll 1
+        for (int qq = 0; qq < nch; ++qq) {
+          const uint32_t it = ring_it + (uint32_t)qq;
+          const int b = (int)(it & 3u);
+          const int c = chunk_col(qq);
+          if (issuer && qq + 2 < nch) {
+            bulk_wait_group_read<1>();                         // buffer (it + 2) & 3 was stored two chunks ago
+            issue_load(qq + 2);
+          }
+          uint4 bq4[4];
+          if (blend_regs && row_ok) {
+            const uint4* pb = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.blend) +
+                                                            pix * a.ldb + out_c0 + c);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(bq4[j].x), "=r"(bq4[j].y), "=r"(bq4[j].z), "=r"(bq4[j].w) : "l"(pb + j));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bq4[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          uint32_t v[32];
+          tmem_ld_32x32(trow + c, v);
+          tmem_ld_wait();
+          if (qq == nch - 1) { release(buf); released = true; }
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (a.scale != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= a.scale;
+          }
+          finish_cols<32, false>(f, a, pix, fb_off, out_c0 + c, have_sb ? sbt + c : nullptr, a.n_total - (out_c0 + c), row_ok);
+          mbar_wait(&rbar[b], (it >> 2) & 1u);
+          const uint32_t rowaddr = smem_u32(ring + b * 8192) + (uint32_t)r * 64u;
+          const uint32_t sw = (uint32_t)((r >> 1) & 3);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t addr = rowaddr + ((((uint32_t)j) ^ sw) << 4);
+            uint4 u;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));
+            const float2 t0 = unpack16x2(u.x, a.fmt), t1 = unpack16x2(u.y, a.fmt), t2 = unpack16x2(u.z, a.fmt),
+                         t3 = unpack16x2(u.w, a.fmt);
+            f[8 * j + 0] += t0.x; f[8 * j + 1] += t0.y; f[8 * j + 2] += t1.x; f[8 * j + 3] += t1.y;
+            f[8 * j + 4] += t2.x; f[8 * j + 5] += t2.y; f[8 * j + 6] += t3.x; f[8 * j + 7] += t3.y;
+            if (a.blend != nullptr) {
+              const uint4 bw = same_aux ? u : bq4[j];
+              const float2 s0 = unpack16x2(bw.x, a.fmt), s1 = unpack16x2(bw.y, a.fmt), s2 = unpack16x2(bw.z, a.fmt),
+                           s3 = unpack16x2(bw.w, a.fmt);
+              f[8 * j + 0] = al * s0.x + be * f[8 * j + 0]; f[8 * j + 1] = al * s0.y + be * f[8 * j + 1];
+              f[8 * j + 2] = al * s1.x + be * f[8 * j + 2]; f[8 * j + 3] = al * s1.y + be * f[8 * j + 3];
+              f[8 * j + 4] = al * s2.x + be * f[8 * j + 4]; f[8 * j + 5] = al * s2.y + be * f[8 * j + 5];
+              f[8 * j + 6] = al * s3.x + be * f[8 * j + 6]; f[8 * j + 7] = al * s3.y + be * f[8 * j + 7];
+            }
+            const uint32_t w0 = pack16x2(f[8 * j + 0], f[8 * j + 1], a.fmt), w1 = pack16x2(f[8 * j + 2], f[8 * j + 3], a.fmt);
+            const uint32_t w2 = pack16x2(f[8 * j + 4], f[8 * j + 5], a.fmt), w3 = pack16x2(f[8 * j + 6], f[8 * j + 7], a.fmt);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + hsel, 128);
+          if (issuer) {
+            tma_store_5d(&tmC, reinterpret_cast<const void*>(ring + b * 8192), out_c0 + c, x0, y0, nn0, 0);
+            bulk_commit_group();
+          }
+        }
+        ring_it += (uint32_t)nch;
+        if (!released) release(buf);
+      } else if (a.tma_store && !a.geglu && (a.res != nullptr || a.blend != nullptr)) {
         // ---- coalesced stores + software-pipelined residual / blend loads: the 64 bytes a row needs for
         // chunk k+1 are requested before chunk k is computed (and, for the first chunk, before the
         // accumulator is even ready), so their L2/HBM latency hides under the MMA wait and the math.
         const int out_w = Ncur, out_c0 = n0, n_out = a.n_total;
         const float al = a.alpha, be = 1.0f - a.alpha;
+        // SpatioTemporalResBlock passes x_spatial as BOTH the temporal resnet's residual and the AlphaBlender's
+        // spatial input: one load serves both (out = (al + be) * x + be * (acc + bias))
+        const bool same_aux = a.res != nullptr && a.res == a.blend && a.ldr == a.ldb;
         uint4 rq[2][4], bq[2][4];
         auto prefetch = [&](int which, int c) {
           const bool ok = row_ok && (c < out_w) && (out_c0 + c + 32 <= n_out);
@@ -511,7 +616,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                              : "=r"(rq[which][j].x), "=r"(rq[which][j].y), "=r"(rq[which][j].z), "=r"(rq[which][j].w)
                              : "l"(pr + j));
             }
-            if (a.blend != nullptr) {
+            if (a.blend != nullptr && !same_aux) {
               const uint4* pb = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.blend) +
                                                               pix * a.ldb + out_c0 + c);
 #pragma unroll
@@ -536,8 +641,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (a.blend != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float2 t0 = unpack16x2(bq[which][j].x, a.fmt), t1 = unpack16x2(bq[which][j].y, a.fmt),
-                           t2 = unpack16x2(bq[which][j].z, a.fmt), t3 = unpack16x2(bq[which][j].w, a.fmt);
+              const uint4 bw = same_aux ? rq[which][j] : bq[which][j];
+              const float2 t0 = unpack16x2(bw.x, a.fmt), t1 = unpack16x2(bw.y, a.fmt),
+                           t2 = unpack16x2(bw.z, a.fmt), t3 = unpack16x2(bw.w, a.fmt);
               f[8 * j + 0] = al * t0.x + be * f[8 * j + 0]; f[8 * j + 1] = al * t0.y + be * f[8 * j + 1];
               f[8 * j + 2] = al * t1.x + be * f[8 * j + 2]; f[8 * j + 3] = al * t1.y + be * f[8 * j + 3];
               f[8 * j + 4] = al * t2.x + be * f[8 * j + 4]; f[8 * j + 5] = al * t2.y + be * f[8 * j + 5];
@@ -761,7 +867,8 @@ int encode_tmap(CUtensorMap* out, const TmapDesc& d) {
   for (int i = 0; i + 1 < d.rank; ++i) strides[i] = d.strides[i];
   CUresult r = fn(out, d.elem_fmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
                   (cuuint32_t)d.rank, const_cast<void*>(d.ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, d.swizzle64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return (int)r;
 }
@@ -818,7 +925,7 @@ int tapgemm_pick_bn(const TapGemmArgs& a, int batch) {
 }
 
 int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC,
-                   const TapGemmArgs& args_in, int batch, cudaStream_t stream) {
+                   const TapGemmArgs& args_in, int batch, cudaStream_t stream, const CUtensorMap* tmR) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
@@ -837,7 +944,10 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   if (args.geglu && (args.res != nullptr || args.blend != nullptr || args.fbias != nullptr || args.scale != 1.0f ||
                      args.act != 0))
     return (int)cudaErrorInvalidValue;             // the GEGLU epilogue is bias + gate only
+  if (args.res_tma && (tmR == nullptr || !args.tma_store || args.res == nullptr || args.geglu || (args.n_total & 31)))
+    return (int)cudaErrorInvalidValue;
   const CUtensorMap& mc = tmC ? *tmC : tmA;
+  const CUtensorMap& mr = tmR ? *tmR : tmA;
   args.batch = batch;
   args.n_tiles = (args.n_total + args.bn_tile - 1) / args.bn_tile;
   {
@@ -856,7 +966,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   if (ctas == 1) {
     const int grid = (int)(units < sms ? units : sms);
     return (int)launch_pdl(tapgemm_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes,
-                           stream, tmA, tmB, mc, args);
+                           stream, tmA, tmB, mc, mr, args);
   }
   const long long slots = sms / 2;
   cudaLaunchConfig_t cfg = {};
@@ -874,7 +984,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 1 : 2;
-  return (int)cudaLaunchKernelEx(&cfg, tapgemm_kernel<2>, tmA, tmB, mc, args);
+  return (int)cudaLaunchKernelEx(&cfg, tapgemm_kernel<2>, tmA, tmB, mc, mr, args);
 }
 
 }  // namespace ug

@@ -46,6 +46,8 @@ struct TapGemmArgs {
   int ctas;                // 1: 128 x BN tile per CTA; 2: 256 x BN tile per CTA pair (cta_group::2)
   int tma_store;           // finished 64-column slabs leave through smem + TMA tile stores (coalesced);
                            // needs a 16-bit output, ldc % 8 == 0, batch 1 and the output tensor map
+  int res_tma;             // residual tiles arrive by TMA (32-column chunks, in place in the store staging ring):
+                           // tmC / tmR are 32-column SWIZZLE_64B maps of the output / residual tensor
   int n_tiles, batch;      // filled by launch_tapgemm
   int n_fastest;           // tile order (filled by launch_tapgemm): N tiles of one M tile run concurrently
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
@@ -76,6 +78,7 @@ struct TmapDesc {
   unsigned long long dims[5];
   unsigned long long strides[4];   // bytes, dims 1..rank-1
   unsigned int box[5];
+  int swizzle64 = 0;            // 0: SWIZZLE_128B (64-element inner box), 1: SWIZZLE_64B (32-element inner box)
 };
 
 // Encodes a SWIZZLE_128B tiled tensor map; returns cudaSuccess-like 0 or non-zero.
@@ -84,7 +87,7 @@ int encode_tmap(CUtensorMap* out, const TmapDesc& d);
 // Launch (persistent, one CTA per SM); args.bn_tile must be set (tapgemm_pick_bn) and must equal the
 // row extent of the B tensor map's box.  Returns cudaError_t as int.
 int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC,
-                   const TapGemmArgs& args, int batch, cudaStream_t stream);
+                   const TapGemmArgs& args, int batch, cudaStream_t stream, const CUtensorMap* tmR = nullptr);
 
 // needs tiles_*, n_total, geglu, b_mn_major filled in; returns bn_tile and the CTA count per tile.
 // The B tensor map's box must have bn_tile / ctas rows.
