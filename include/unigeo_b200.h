@@ -193,6 +193,9 @@ int ug_clip_embed(ug_ctx* ctx, const float* video, int F, int H, int W, float* e
 long long ug_ctx_launch_count(ug_ctx* ctx, int reset);
 /* Bytes of workspace currently reserved. */
 long long ug_ctx_workspace_bytes(ug_ctx* ctx);
+/* CUDA graphs currently instantiated: ug_denoise_clip / ug_refine_frames_2d run their step loop eagerly on the first
+ * call with a given signature, capture it on the second and replay it afterwards (UG_NO_GRAPH=1 keeps them eager). */
+long long ug_ctx_graph_count(ug_ctx* ctx);
 /* Per-launch profiling for bench.py's roofline: while enabled, one CUDA event is recorded on the
  * call's stream after every kernel launch; ug_ctx_profile_read synchronises and aggregates by kernel
  * name (returns the number of rows written, or a negative ug_status).  Off by default. */

@@ -156,3 +156,22 @@ def test_clip_preprocess_matches_upstream_resize(cuda):
     e.load_state_dict("clip", sd)
     got = e.clip_embed(video)
     assert rel_l2(got, ref) <= UNET_TOL["fp16"], rel_l2(got, ref)
+
+
+def test_denoise_graph_replay_is_bit_identical(bundle):
+    """ug_denoise_clip: eager first call, CUDA-graph capture on the second, replay on the third -- bit-identical,
+    including after a new clip context (same device buffers, new contents)."""
+    cfg, usd, vsd, d = bundle
+    e = make_engine(cfg, usd, vsd, "fp16")
+    e.prepare(T, H // 8, W // 8)
+    e.set_clip_context(d["enc"][0])
+    ids = [7.0, 127.0, 0.02]
+    outs = [e.denoise(d["lat"], d["init"][0], ids, 2).clone() for _ in range(3)]
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    e.set_clip_context(d["enc"][0] * 0.5)
+    replay = e.denoise(d["lat"], d["init"][0], ids, 2)
+    e2 = make_engine(cfg, usd, vsd, "fp16")
+    e2.prepare(T, H // 8, W // 8)
+    e2.set_clip_context(d["enc"][0] * 0.5)
+    assert torch.equal(replay, e2.denoise(d["lat"], d["init"][0], ids, 2))

@@ -191,3 +191,29 @@ def test_missing_text_context_is_an_error(bundle):
         e.unet2d_forward("unet2d", d["x"], 10.0)
     with pytest.raises(UgError, match="no 2-D network"):
         e.unet2d_forward("nope", d["x"], 10.0)
+
+
+def test_refine_loop_graph_replay_is_bit_identical(bundle):
+    """The refinement loop is captured into a CUDA graph on its second call with the same signature and replayed
+    afterwards: eager (call 1), capture + launch (call 2) and replay (call 3) must agree bit for bit, also when
+    the inputs change between replays (external pointers stay outside the graph)."""
+    cfg, sn, usd, csd, vsd, d = bundle
+    e = make_engine(cfg, sn, usd, csd, vsd, "fp16")
+    e.set_text_context("unet2d", d["ctx"])
+    e.set_text_context("controlnet", d["ctx"])
+    n0 = e.launch_count()
+    a = e.refine_2d("unet2d", "controlnet", d["il"], d["x"], 2)
+    n1 = e.launch_count()
+    b = e.refine_2d("unet2d", "controlnet", d["il"], d["x"], 2)
+    c = e.refine_2d("unet2d", "controlnet", d["il"].clone(), d["x"].clone(), 2)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    import os
+    assert e.graph_count() == (0 if os.environ.get("UG_NO_GRAPH") else 1)
+    other = e.refine_2d("unet2d", "controlnet", d["il"] * 0.5, d["x"] + 1.0, 2)      # replay on new inputs
+    e2 = make_engine(cfg, sn, usd, csd, vsd, "fp16")
+    e2.set_text_context("unet2d", d["ctx"])
+    e2.set_text_context("controlnet", d["ctx"])
+    ref = e2.refine_2d("unet2d", "controlnet", d["il"] * 0.5, d["x"] + 1.0, 2)       # eager in a fresh context
+    assert torch.equal(other, ref)
+    assert e.launch_count() - n0 == 4 * (n1 - n0)           # replays are counted like the launches they contain

@@ -92,6 +92,7 @@ _SIGNATURES = {
     "ug_depth_postprocess": ([_P, _P, _P, _I, _I, _I, _P, _P, _P], C.c_int),
     "ug_ctx_launch_count": ([_P, _I], C.c_longlong),
     "ug_ctx_workspace_bytes": ([_P], C.c_longlong),
+    "ug_ctx_graph_count": ([_P], C.c_longlong),
     "ug_ctx_profile": ([_P, _I], C.c_int),
     "ug_ctx_profile_read": ([_P, _I, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                              C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),

@@ -7,9 +7,22 @@
 
 using namespace ug;
 
+// A launch-bound inner loop (denoising / refinement steps) captured once and replayed: hundreds of launches
+// per step, each with host-side tensor-map encoding, become one cudaGraphLaunch.
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  unsigned long long epoch = 0;    // Ctx::ptr_epoch the graph was captured under
+  long long launches = 0;          // kernels in the graph (bench "gpu_launches" accounting)
+  int calls = 0;                   // first call runs eagerly (one-time attribute / counter setup), second captures
+  bool disabled = false;           // capture or instantiation failed once: stay eager
+};
+
 struct ug_ctx {
   Ctx c;
   std::unordered_map<std::string, size_t> ws_need;   // call signature -> workspace bytes
+  std::unordered_map<std::string, GraphEntry> graphs;
+  cudaStream_t gstream = nullptr;                    // capture needs a non-default stream (torch's default is 0)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 namespace {
@@ -47,6 +60,67 @@ void run_sized(ug_ctx* u, const std::string& sig, void* stream, const std::funct
   c.stream = reinterpret_cast<cudaStream_t>(stream);
   if (c.profile) c.prof_mark("(start)", 0.0, 0.0);
   body(c);
+}
+
+// Runs `body` (which must only enqueue kernels on c.stream, at fixed workspace addresses) through a cached CUDA
+// graph keyed by `key`.  The graph lives on the context's own stream, fenced against the caller's stream with
+// events, so it also works when the caller uses the legacy default stream.  UG_NO_GRAPH=1 disables.
+void run_graphed(ug_ctx* u, const std::string& key, const std::function<void(Ctx&)>& body) {
+  static const bool off = getenv("UG_NO_GRAPH") != nullptr;
+  Ctx& c = u->c;
+  GraphEntry& g = u->graphs[key];
+  if (off || c.profile || g.disabled) { body(c); return; }
+  if (g.exec && g.epoch != c.ptr_epoch) {
+    cudaGraphExecDestroy(g.exec);
+    g.exec = nullptr;
+    g.calls = 0;
+  }
+  if (!g.exec && g.calls++ < 1) { body(c); return; }
+  cudaStream_t user = c.stream;
+  if (!u->gstream) {
+    UG_CUDA(cudaStreamCreateWithFlags(&u->gstream, cudaStreamNonBlocking));
+    UG_CUDA(cudaEventCreateWithFlags(&u->ev_in, cudaEventDisableTiming));
+    UG_CUDA(cudaEventCreateWithFlags(&u->ev_out, cudaEventDisableTiming));
+  }
+  if (!g.exec) {
+    const long long l0 = c.launches;
+    const unsigned long long e0 = c.ptr_epoch;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(u->gstream, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      c.stream = u->gstream;
+      try {
+        body(c);
+      } catch (...) {
+        c.stream = user;
+        cudaStreamEndCapture(u->gstream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        throw;
+      }
+      c.stream = user;
+      ok = cudaStreamEndCapture(u->gstream, &graph) == cudaSuccess && graph != nullptr && c.ptr_epoch == e0;
+      if (ok) ok = cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+    }
+    if (!ok) {                       // e.g. a driver that cannot capture these launches: stay eager for this key
+      cudaGetLastError();
+      g.exec = nullptr;
+      g.disabled = true;
+      c.launches = l0;
+      body(c);
+      return;
+    }
+    g.epoch = c.ptr_epoch;
+    g.launches = c.launches - l0;
+    c.launches = l0;
+  }
+  UG_CUDA(cudaEventRecord(u->ev_in, user));
+  UG_CUDA(cudaStreamWaitEvent(u->gstream, u->ev_in, 0));
+  UG_CUDA(cudaGraphLaunch(g.exec, u->gstream));
+  UG_CUDA(cudaEventRecord(u->ev_out, u->gstream));
+  UG_CUDA(cudaStreamWaitEvent(user, u->ev_out, 0));
+  c.launches += g.launches;
 }
 
 std::vector<double> karras_sigmas(const ug_model_cfg& g, int steps) {
@@ -103,6 +177,11 @@ int ug_ctx_destroy(ug_ctx* u) {
     if (!u) return;
     cudaSetDevice(u->c.device);
     cudaDeviceSynchronize();
+    for (auto& kv : u->graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    if (u->gstream) cudaStreamDestroy(u->gstream);
+    if (u->ev_in) cudaEventDestroy(u->ev_in);
+    if (u->ev_out) cudaEventDestroy(u->ev_out);
     for (void* p : u->c.owned) cudaFree(p);
     if (u->c.ws.base) cudaFree(u->c.ws.base);
     delete u->c.unet;
@@ -150,6 +229,7 @@ int ug_ctx_load_weight(ug_ctx* u, const char* key, const void* dev_ptr, int dtyp
     }
     c.weights[key] = w;
     c.finalized = false;
+    ++c.ptr_epoch;
   });
 }
 
@@ -231,13 +311,22 @@ int ug_denoise_clip(ug_ctx* u, const float* cond_lat, const float* init_noise, c
         const float s0 = (float)std::sqrt(sig[0] * sig[0] + 1.0);   // init_noise_sigma ("leading" spacing)
         op_check(c, launch_f32_nchw_to_nhwc(init_noise, c.T, hw, 4, s0, lat, c.stream), "init latents");
       }
-      const int n_iter = c.dry ? 1 : steps;
-      for (int i = 0; i < n_iter; ++i) {
-        c.ws.release(mk);
-        const float sg = (float)sig[i], sn = (float)sig[i + 1];
-        if (!c.dry) op_check(c, launch_build_unet_input(lat, cond16, sg, tok, x16, c.fmt, c.stream), "unet input");
-        unet_forward(c, x16, (float)(0.25 * std::log(sig[i])), ids, v);
-        if (!c.dry) op_check(c, launch_euler_step(lat, v, sg, sn, tok * 4, c.stream), "euler step");
+      auto loop = [&](Ctx& cc) {
+        const int n_iter = cc.dry ? 1 : steps;
+        for (int i = 0; i < n_iter; ++i) {
+          cc.ws.release(mk);
+          const float sg = (float)sig[i], sn = (float)sig[i + 1];
+          if (!cc.dry) op_check(cc, launch_build_unet_input(lat, cond16, sg, tok, x16, cc.fmt, cc.stream), "unet input");
+          unet_forward(cc, x16, (float)(0.25 * std::log(sig[i])), ids, v);
+          if (!cc.dry) op_check(cc, launch_euler_step(lat, v, sg, sn, tok * 4, cc.stream), "euler step");
+        }
+      };
+      if (c.dry) {
+        loop(c);
+      } else {
+        char key[160];
+        snprintf(key, sizeof(key), "denoise:%dx%dx%d:%d:%a:%a:%a", c.T, c.h, c.w, steps, ids[0], ids[1], ids[2]);
+        run_graphed(u, key, loop);
       }
       if (!c.dry) op_check(c, launch_f32_nhwc_to_nchw(lat, c.T, hw, 4, 1.f, lat_out, c.stream), "latents out");
     });
@@ -454,18 +543,22 @@ int ug_refine_frames_2d(ug_ctx* u, const char* unet_prefix, const char* controln
       void* c16 = controlnet_prefix ? latents_to_tokens(c, image_latent, F, h, w, 4) : nullptr;
       if (!c.dry) op_check(c, launch_f32_nchw_to_nhwc(latents_in, F, hw, 4, 1.f, lat, c.stream), "latents in");
       const size_t mk = c.ws.mark();
-      const int n_iter = c.dry ? 1 : steps;
-      for (int i = 0; i < n_iter; ++i) {
-        c.ws.release(mk);
-        const int t = ts[i], tp = i + 1 < steps ? ts[i + 1] : -1;
-        UG_CHECK(t >= 0 && t < NT, UG_ERR_INVALID, "timestep out of range");
-        if (!c.dry) op_check(c, launch_f32_to_tokens(lat, 4, 8, tok, x16, c.fmt, c.stream), "unet input");
-        unet2d_forward(c, P, x16, F, h, w, (float)t, controlnet_prefix ? &Q : nullptr, c16, x0);
-        const double a_t = ac[t], a_p = tp >= 0 ? ac[tp] : 1.0;
-        const double cx = std::sqrt((1.0 - a_p) / (1.0 - a_t));
-        const double cx0 = std::sqrt(a_p) - std::sqrt(a_t) * cx;
-        if (!c.dry) op_check(c, launch_axpby(lat, x0, (float)cx0, (float)cx, tok * 4, c.stream), "ddim step");
-      }
+      auto loop = [&](Ctx& cc) {
+        const int n_iter = cc.dry ? 1 : steps;
+        for (int i = 0; i < n_iter; ++i) {
+          cc.ws.release(mk);
+          const int t = ts[i], tp = i + 1 < steps ? ts[i + 1] : -1;
+          UG_CHECK(t >= 0 && t < NT, UG_ERR_INVALID, "timestep out of range");
+          if (!cc.dry) op_check(cc, launch_f32_to_tokens(lat, 4, 8, tok, x16, cc.fmt, cc.stream), "unet input");
+          unet2d_forward(cc, P, x16, F, h, w, (float)t, controlnet_prefix ? &Q : nullptr, c16, x0);
+          const double a_t = ac[t], a_p = tp >= 0 ? ac[tp] : 1.0;
+          const double cx = std::sqrt((1.0 - a_p) / (1.0 - a_t));
+          const double cx0 = std::sqrt(a_p) - std::sqrt(a_t) * cx;
+          if (!cc.dry) op_check(cc, launch_axpby(lat, x0, (float)cx0, (float)cx, tok * 4, cc.stream), "ddim step");
+        }
+      };
+      if (c.dry) loop(c);
+      else run_graphed(u, sig + ":" + std::to_string(steps) + ":" + std::to_string(t_start), loop);
       if (!c.dry) op_check(c, launch_f32_nhwc_to_nchw(lat, F, hw, 4, 1.f, latents_out, c.stream), "latents out");
     });
   });
@@ -511,6 +604,12 @@ long long ug_ctx_launch_count(ug_ctx* u, int reset) {
   return n;
 }
 long long ug_ctx_workspace_bytes(ug_ctx* u) { return u ? (long long)u->c.ws.cap : -1; }
+long long ug_ctx_graph_count(ug_ctx* u) {
+  if (!u) return -1;
+  long long n = 0;
+  for (const auto& kv : u->graphs) n += kv.second.exec != nullptr;
+  return n;
+}
 
 int ug_ctx_profile(ug_ctx* u, int enable) {
   return guard([&] {

@@ -104,6 +104,8 @@ struct Ctx {
   // prepared clip shape
   int T = 0, h = 0, w = 0;
   std::vector<void*> owned;      // cudaMalloc'd blocks to free at destroy
+  unsigned long long ptr_epoch = 0;      // bumped whenever library-owned device addresses may have changed
+                                         // (allocation, workspace growth, weights): invalidates captured graphs
   // ---- per-launch profiling (ug_ctx_profile): one event after every launch; a launch's time
   // is the gap to the previous event on the (single) stream
   struct ProfRec { const char* name; double flops, bytes; cudaEvent_t ev; };

@@ -13,6 +13,7 @@ void* Ctx::dmalloc(size_t bytes) {
   void* p = nullptr;
   UG_CUDA(cudaMalloc(&p, bytes < 256 ? 256 : bytes));
   owned.push_back(p);
+  ++ptr_epoch;
   return p;
 }
 const Weight& Ctx::W(const std::string& key) const {
@@ -42,6 +43,7 @@ void Ctx::ensure_workspace(size_t bytes) {
   UG_CUDA(cudaMalloc(&p, bytes));
   ws.base = reinterpret_cast<char*>(p);
   ws.cap = bytes;
+  ++ptr_epoch;
 }
 
 void Ctx::prof_mark(const char* name, double flops, double bytes) {

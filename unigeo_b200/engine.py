@@ -312,6 +312,10 @@ class Engine:
             rows.append(dict(name=nm, launches=int(cnt[i]), ms=float(ms[i]), flops=float(fl[i]), bytes=float(by[i])))
         return rows
 
+    def graph_count(self) -> int:
+        """CUDA graphs instantiated for the step loops (0 until a loop signature has been called twice)."""
+        return int(self.lib.ug_ctx_graph_count(self._ctx))
+
     def workspace_bytes(self) -> int:
         return int(self.lib.ug_ctx_workspace_bytes(self._ctx))
 
