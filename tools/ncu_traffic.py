@@ -14,7 +14,7 @@ for r in csv.DictReader(lines):
 fam = {}
 for r in rows:
     name = r["Kernel Name"]
-    key = next((k for k in ("tapgemm", "fmha", "gn_stats", "gn_apply", "layernorm", "temporal_attn", "concat",
+    key = next((k for k in ("tapgemm", "fmha", "gn_fused", "gn_stats", "gn_apply", "layernorm", "temporal_attn", "concat",
                             "upsample2x") if k in name), None)
     if key is None:
         continue

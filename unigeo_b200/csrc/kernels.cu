@@ -24,6 +24,23 @@ template <typename T> __device__ __forceinline__ uint4 pack8(const float (&f)[8]
   return u;
 }
 __device__ __forceinline__ float silu_f(float x) { return x * rcp_approx(1.0f + __expf(-x)); }
+// pairs on the packed fp32 pipe (FFMA2 / FMUL2 / FADD2, sm_100): the normalisation kernels are instruction-issue
+// bound before they are HBM bound (ncu: 47-54 % issue slots at 15-20 % DRAM), so halving the FP instruction count
+// is worth more than any further load tuning
+template <typename T> __device__ __forceinline__ void unpack4x2(const uint4& u, float2 (&p)[4]) {
+  p[0] = Elem<T>::unpack2(u.x); p[1] = Elem<T>::unpack2(u.y); p[2] = Elem<T>::unpack2(u.z); p[3] = Elem<T>::unpack2(u.w);
+}
+template <typename T> __device__ __forceinline__ uint4 pack4x2(const float2 (&p)[4]) {
+  uint4 u;
+  u.x = Elem<T>::pack2(p[0].x, p[0].y); u.y = Elem<T>::pack2(p[1].x, p[1].y);
+  u.z = Elem<T>::pack2(p[2].x, p[2].y); u.w = Elem<T>::pack2(p[3].x, p[3].y);
+  return u;
+}
+__device__ __forceinline__ float2 silu2(float2 v) {        // v / (1 + 2^(-v log2 e))
+  const float2 t = __fmul2_rn(v, make_float2(-1.4426950408889634f, -1.4426950408889634f));
+  const float2 d = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), make_float2(1.0f, 1.0f));
+  return __fmul2_rn(v, make_float2(rcp_approx(d.x), rcp_approx(d.y)));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -179,9 +196,9 @@ gn_fused_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x
   // ---- phase 1: partial (sum, sumsq) per group of this chunk
   {
     float* s_part = s_dyn;               // [rpb][C] sums, then [rpb][C] sumsq
-    float a[8], q[8];
+    float2 a[4], q[4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a[j] = 0.f; q[j] = 0.f; }
+    for (int j = 0; j < 4; ++j) { a[j] = make_float2(0.f, 0.f); q[j] = make_float2(0.f, 0.f); }
     if (rr < rpb) {
       for (long long r = r_begin + rr; r < r_end; r += 8 * rpb) {
         uint4 u[8];
@@ -192,16 +209,16 @@ gn_fused_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          float f[8];
-          unpack8<T>(u[k], f);
+          float2 f[4];
+          unpack4x2<T>(u[k], f);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) { a[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+          for (int j = 0; j < 4; ++j) { a[j] = __fadd2_rn(a[j], f[j]); q[j] = __ffma2_rn(f[j], f[j], q[j]); }
         }
       }
-      float* ps = s_part + (size_t)rr * C + c8 * 8;
-      float* pq = s_part + (size_t)(rpb + rr) * C + c8 * 8;
+      float2* ps = reinterpret_cast<float2*>(s_part + (size_t)rr * C + c8 * 8);
+      float2* pq = reinterpret_cast<float2*>(s_part + (size_t)(rpb + rr) * C + c8 * 8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { ps[j] = a[j]; pq[j] = q[j]; }
+      for (int j = 0; j < 4; ++j) { ps[j] = a[j]; pq[j] = q[j]; }
     }
     __syncthreads();
     if (threadIdx.x < G) {
@@ -294,28 +311,31 @@ gn_fused_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x
     }
     __syncthreads();
     if (rr < rpb) {
-      float sa[8], sb[8];
+      float2 sa[4], sb[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { sa[j] = s_a[c8 * 8 + j]; sb[j] = s_b[c8 * 8 + j]; }
+      for (int j = 0; j < 4; ++j) {
+        sa[j] = reinterpret_cast<const float2*>(s_a + c8 * 8)[j];
+        sb[j] = reinterpret_cast<const float2*>(s_b + c8 * 8)[j];
+      }
       uint4* yo = reinterpret_cast<uint4*>(y);
-      for (long long r = r_begin + rr; r < r_end; r += 6 * rpb) {
-        uint4 u[6];
+      for (long long r = r_begin + rr; r < r_end; r += 4 * rpb) {
+        uint4 u[4];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < 4; ++k) {
           const long long rk = r + (long long)k * rpb;
           u[k] = rk < r_end ? __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
-        for (int k = 0; k < 6; ++k) {
+        for (int k = 0; k < 4; ++k) {
           const long long rk = r + (long long)k * rpb;
-          float f0[8];
-          unpack8<T>(u[k], f0);
+          float2 f0[4];
+          unpack4x2<T>(u[k], f0);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float v0 = fmaf(f0[j], sa[j], sb[j]);
-            f0[j] = silu ? silu_f(v0) : v0;
+          for (int j = 0; j < 4; ++j) {
+            const float2 v0 = __ffma2_rn(f0[j], sa[j], sb[j]);
+            f0[j] = silu ? silu2(v0) : v0;
           }
-          if (rk < r_end) yo[(set * rows_per_set + rk) * nvec + c8] = pack8<T>(f0);
+          if (rk < r_end) yo[(set * rows_per_set + rk) * nvec + c8] = pack4x2<T>(f0);
         }
       }
     }
@@ -452,33 +472,36 @@ layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float*
     raw[k] = make_uint4(0u, 0u, 0u, 0u);
     if (rok && i < nvec) raw[k] = __ldg(xb + i);
   }
-  float f[VPL][8];
+  float2 f[VPL][4];
   const float* addr = (add && rok) ? add + (row / add_div) * C : nullptr;
-  float s = 0.f;
+  float2 s2 = make_float2(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     const int i = sub + LPR * k;
-    unpack8<T>(raw[k], f[k]);
+    unpack4x2<T>(raw[k], f[k]);
     if (addr && i < nvec) {
       const float4 a0 = __ldg(reinterpret_cast<const float4*>(addr + i * 8));
       const float4 a1 = __ldg(reinterpret_cast<const float4*>(addr + i * 8) + 1);
-      f[k][0] += a0.x; f[k][1] += a0.y; f[k][2] += a0.z; f[k][3] += a0.w;
-      f[k][4] += a1.x; f[k][5] += a1.y; f[k][6] += a1.z; f[k][7] += a1.w;
+      f[k][0] = __fadd2_rn(f[k][0], make_float2(a0.x, a0.y)); f[k][1] = __fadd2_rn(f[k][1], make_float2(a0.z, a0.w));
+      f[k][2] = __fadd2_rn(f[k][2], make_float2(a1.x, a1.y)); f[k][3] = __fadd2_rn(f[k][3], make_float2(a1.z, a1.w));
     }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s += f[k][j];         // padding vectors are zero
+    for (int j = 0; j < 4; ++j) s2 = __fadd2_rn(s2, f[k][j]);      // padding vectors are zero
   }
+  float s = s2.x + s2.y;
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   const float mean = s / (float)C;
-  float v = 0.f;
+  float2 v2 = make_float2(0.f, 0.f);
+  const float2 nm2 = make_float2(-mean, -mean);
 #pragma unroll
   for (int k = 0; k < VPL; ++k) {
     if (sub + LPR * k < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { f[k][j] -= mean; v = fmaf(f[k][j], f[k][j], v); }
+      for (int j = 0; j < 4; ++j) { f[k][j] = __fadd2_rn(f[k][j], nm2); v2 = __ffma2_rn(f[k][j], f[k][j], v2); }
     }
   }
+  float v = v2.x + v2.y;
 #pragma unroll
   for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const float rstd = rsqrtf(v / (float)C + eps);
@@ -492,12 +515,13 @@ layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float*
       const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + i * 8) + 1);
       const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + i * 8));
       const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + i * 8) + 1);
-      float o[8];
-      o[0] = fmaf(f[k][0] * rstd, g0.x, b0.x); o[1] = fmaf(f[k][1] * rstd, g0.y, b0.y);
-      o[2] = fmaf(f[k][2] * rstd, g0.z, b0.z); o[3] = fmaf(f[k][3] * rstd, g0.w, b0.w);
-      o[4] = fmaf(f[k][4] * rstd, g1.x, b1.x); o[5] = fmaf(f[k][5] * rstd, g1.y, b1.y);
-      o[6] = fmaf(f[k][6] * rstd, g1.z, b1.z); o[7] = fmaf(f[k][7] * rstd, g1.w, b1.w);
-      yb[i] = pack8<T>(o);
+      const float2 r2 = make_float2(rstd, rstd);
+      float2 o[4];
+      o[0] = __ffma2_rn(__fmul2_rn(f[k][0], r2), make_float2(g0.x, g0.y), make_float2(b0.x, b0.y));
+      o[1] = __ffma2_rn(__fmul2_rn(f[k][1], r2), make_float2(g0.z, g0.w), make_float2(b0.z, b0.w));
+      o[2] = __ffma2_rn(__fmul2_rn(f[k][2], r2), make_float2(g1.x, g1.y), make_float2(b1.x, b1.y));
+      o[3] = __ffma2_rn(__fmul2_rn(f[k][3], r2), make_float2(g1.z, g1.w), make_float2(b1.z, b1.w));
+      yb[i] = pack4x2<T>(o);
     }
   }
 }
