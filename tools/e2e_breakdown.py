@@ -9,7 +9,8 @@ import unigeo_b200.postprocess as PP
 T, H, W = 25, 384, 512
 plug = DepthCrafter(config="full", dtype="fp16", weights="synthetic", num_inference_steps=25, seed=1, device_weights=True)
 data = make_clip(T, H, W, seed=1)
-plug.forward(data)
+for _ in range(2):                 # workspace sizing, then the CUDA-graph capture of the denoising loop
+    plug.forward(data)
 torch.cuda.synchronize()
 eng = plug.engine
 marks = {}
