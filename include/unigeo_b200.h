@@ -189,6 +189,14 @@ int ug_depth_postprocess(ug_ctx* ctx, const float* frames, const float* intrinsi
 int ug_ctx_set_clip_cfg(ug_ctx* ctx, const ug_clip_cfg* cfg);
 int ug_clip_embed(ug_ctx* ctx, const float* video, int F, int H, int W, float* enc, void* stream);
 
+/* Host-only schedule tables (no device needed), exactly what the two step loops iterate over.
+ * ug_karras_schedule: [UPSTREAM] EulerDiscreteScheduler.set_timesteps (Karras sigmas, "leading"): sigmas[steps+1]
+ * (last 0), UNet timesteps[steps] = 0.25 ln sigma (nullable), init_noise_sigma (nullable).
+ * ug_ddim_schedule: trailing-spaced DDIM timesteps[steps] and the per-step update x <- c_x0 x0 + c_x x
+ * (prediction_type "sample", eta 0; both nullable). */
+int ug_karras_schedule(const ug_model_cfg* cfg, int steps, double* sigmas, double* timesteps, double* init_noise_sigma);
+int ug_ddim_schedule(const ug_unet2d_cfg* cfg, int steps, int t_start, int* timesteps, double* c_x0, double* c_x);
+
 /* Kernels launched on behalf of this context since the last reset (bench "gpu_launches"). */
 long long ug_ctx_launch_count(ug_ctx* ctx, int reset);
 /* Bytes of workspace currently reserved. */

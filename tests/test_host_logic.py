@@ -53,6 +53,40 @@ def test_scheduler_matches_oracle_and_closed_form():
     assert torch.allclose(O.euler_step(v, x, s, 0.0), x0, atol=1e-6)
 
 
+def test_library_schedules_match_oracle_without_gpu():
+    """The C++ step loops' own schedule tables (host-only ABI entry points) against the oracle: Karras sigmas /
+    continuous timesteps of ug_denoise_clip, trailing DDIM timesteps and update coefficients of ug_refine_frames_2d."""
+    import ctypes as C
+    from oracle import scheduler as O
+    from oracle.stablenormal import alphas_cumprod, ddim_timesteps
+    from unigeo_b200 import _lib
+    from unigeo_b200.config import stablenormal_config, tiny_config
+    lib = _lib.load()
+    cfg = _lib.cfg_struct(tiny_config(), _lib.UG_F16)
+    for n in (1, 5, 25):
+        sig, ts, s0 = (C.c_double * (n + 1))(), (C.c_double * n)(), C.c_double()
+        _lib.check(lib.ug_karras_schedule(C.byref(cfg), n, sig, ts, C.byref(s0)))
+        ref = O.karras_sigmas(n)
+        # ug_model_cfg carries sigma_min / sigma_max / rho as float32: 6e-8 relative is the representation error
+        assert all(abs(a - b) <= 1e-6 * max(1e-3, abs(b)) for a, b in zip(sig, ref)) and sig[n] == 0.0
+        assert all(abs(a - b) <= 1e-6 for a, b in zip(ts, O.timesteps_from_sigmas(ref)))
+        assert abs(s0.value - O.init_noise_sigma(ref)) <= 1e-6 * s0.value
+    sn = stablenormal_config("full")
+    c2 = _lib.unet2d_cfg_struct(sn)
+    ac = alphas_cumprod(sn.num_train_timesteps, sn.beta_start, sn.beta_end)
+    for n, t0 in ((10, -1), (4, 299), (1, -1)):
+        ts, c0, cx = (C.c_int * n)(), (C.c_double * n)(), (C.c_double * n)()
+        _lib.check(lib.ug_ddim_schedule(C.byref(c2), n, t0, ts, c0, cx))
+        ref = ddim_timesteps(n, sn.num_train_timesteps, None if t0 < 0 else t0)
+        assert list(ts) == ref
+        for i, t in enumerate(ref):
+            a_t = float(ac[t])
+            a_p = float(ac[ref[i + 1]]) if i + 1 < n else 1.0
+            k = math.sqrt((1 - a_p) / (1 - a_t))
+            assert abs(cx[i] - k) <= 1e-6 and abs(c0[i] - (math.sqrt(a_p) - math.sqrt(a_t) * k)) <= 1e-6
+    assert lib.ug_ddim_schedule(C.byref(c2), 0, -1, (C.c_int * 1)(), None, None) == -1     # UG_ERR_INVALID, no throw
+
+
 def test_geglu_interleave_layout():
     from unigeo_b200.ops import geglu_interleave
     H, K = 256, 8

@@ -134,6 +134,26 @@ std::vector<double> karras_sigmas(const ug_model_cfg& g, int steps) {
   return s;
 }
 
+// scaled-linear betas -> cumulative alpha products (double, like the host-side scheduler upstream)
+std::vector<double> ddim_alphas_cumprod(int NT, double beta_start, double beta_end) {
+  std::vector<double> ac(NT);
+  const double b0 = std::sqrt(beta_start), b1 = std::sqrt(beta_end);
+  double prod = 1.0;
+  for (int i = 0; i < NT; ++i) {
+    const double sb = NT > 1 ? b0 + (b1 - b0) * i / (NT - 1) : b0;
+    prod *= 1.0 - sb * sb;
+    ac[i] = prod;
+  }
+  return ac;
+}
+// trailing spacing from t_start (or NT - 1 when negative): round(top - k top / steps) - 1
+std::vector<int> ddim_timesteps(int NT, int steps, int t_start) {
+  const int top = t_start < 0 ? NT : t_start + 1;
+  std::vector<int> ts(steps);
+  for (int k = 0; k < steps; ++k) ts[k] = (int)std::nearbyint((double)top - (double)k * top / steps) - 1;
+  return ts;
+}
+
 thread_local ug_ctx* g_scratch[2] = {nullptr, nullptr};
 ug_ctx* scratch_ctx(int dtype) {
   UG_CHECK(dtype == UG_F16 || dtype == UG_BF16, UG_ERR_INVALID, "dtype must be UG_F16 or UG_BF16");
@@ -519,20 +539,8 @@ int ug_refine_frames_2d(ug_ctx* u, const char* unet_prefix, const char* controln
     UG_CHECK(g.in_channels == 4 && g.out_channels == 4, UG_ERR_INVALID, "refinement needs a 4 -> 4 channel UNet");
     const int NT = g.num_train_timesteps;
     UG_CHECK(steps >= 1 && steps <= NT && t_start < NT, UG_ERR_INVALID, "steps / t_start out of range");
-    // scaled-linear betas -> cumulative alpha products (double, like the host-side scheduler)
-    std::vector<double> ac(NT);
-    {
-      const double b0 = std::sqrt((double)g.beta_start), b1 = std::sqrt((double)g.beta_end);
-      double prod = 1.0;
-      for (int i = 0; i < NT; ++i) {
-        const double sb = NT > 1 ? b0 + (b1 - b0) * i / (NT - 1) : b0;
-        prod *= 1.0 - sb * sb;
-        ac[i] = prod;
-      }
-    }
-    const int top = t_start < 0 ? NT : t_start + 1;
-    std::vector<int> ts(steps);
-    for (int k = 0; k < steps; ++k) ts[k] = (int)std::nearbyint((double)top - (double)k * top / steps) - 1;
+    const std::vector<double> ac = ddim_alphas_cumprod(NT, (double)g.beta_start, (double)g.beta_end);
+    const std::vector<int> ts = ddim_timesteps(NT, steps, t_start);
     const std::string P = norm_prefix(unet_prefix), Q = norm_prefix(controlnet_prefix);
     const std::string sig = "refine2d:" + P + Q + ":" + std::to_string(F) + "x" + std::to_string(h) + "x" + std::to_string(w);
     run_sized(u, sig, stream, [&](Ctx& c) {
@@ -594,6 +602,37 @@ int ug_vae2d_decode(ug_ctx* u, const float* lat, int N, int h, int w, float* img
                                         c.cfg.vae_latent_channels, h, w, 8, z16, c.fmt, c.stream), "latents in");
       vae2d_decode(c, z16, N, h, w, img, normals_u8);
     });
+  });
+}
+
+// ---- host-only schedule tables (no device needed): what the step loops above iterate over
+int ug_karras_schedule(const ug_model_cfg* cfg, int steps, double* sigmas, double* timesteps, double* init_noise_sigma) {
+  return guard([&] {
+    UG_CHECK(cfg && sigmas && steps >= 1 && steps <= 1000, UG_ERR_INVALID, "bad argument");
+    const std::vector<double> sig = karras_sigmas(*cfg, steps);
+    for (int i = 0; i <= steps; ++i) sigmas[i] = sig[i];
+    if (timesteps)
+      for (int i = 0; i < steps; ++i) timesteps[i] = 0.25 * std::log(sig[i]);
+    if (init_noise_sigma) *init_noise_sigma = std::sqrt(sig[0] * sig[0] + 1.0);
+  });
+}
+
+int ug_ddim_schedule(const ug_unet2d_cfg* cfg, int steps, int t_start, int* timesteps, double* c_x0, double* c_x) {
+  return guard([&] {
+    UG_CHECK(cfg && timesteps && steps >= 1 && steps <= cfg->num_train_timesteps && t_start < cfg->num_train_timesteps,
+             UG_ERR_INVALID, "bad argument");
+    const int NT = cfg->num_train_timesteps;
+    const std::vector<double> ac = ddim_alphas_cumprod(NT, (double)cfg->beta_start, (double)cfg->beta_end);
+    const std::vector<int> ts = ddim_timesteps(NT, steps, t_start);
+    for (int i = 0; i < steps; ++i) {
+      const int t = ts[i], tp = i + 1 < steps ? ts[i + 1] : -1;
+      UG_CHECK(t >= 0 && t < NT, UG_ERR_INVALID, "timestep out of range");
+      timesteps[i] = t;
+      const double a_t = ac[t], a_p = tp >= 0 ? ac[tp] : 1.0;
+      const double cx = std::sqrt((1.0 - a_p) / (1.0 - a_t));
+      if (c_x) c_x[i] = cx;
+      if (c_x0) c_x0[i] = std::sqrt(a_p) - std::sqrt(a_t) * cx;
+    }
   });
 }
 

@@ -1260,12 +1260,17 @@ int launch_temporal_attention(const void* qkv, void* out, int Tn, long long P, i
     return (int)err;
   } else {
     const size_t smem = (size_t)wpb * 3 * 64 * 128;
-    UG_DISPATCH_FMT(fmt, {
-      cudaFuncSetAttribute(temporal_attn_kernel<T, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      temporal_attn_kernel<T, 64><<<grid, wpb * 32, smem, st>>>(qkv, out, Tn, P, C, sl);
-    });
+    static bool configured = false;      // once, outside any stream capture (the first call of a loop is eager)
+    if (!configured) {
+      cudaFuncSetAttribute(temporal_attn_kernel<__half, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(temporal_attn_kernel<__nv_bfloat16, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      configured = true;
+    }
+    cudaError_t err;
+    UG_DISPATCH_FMT(fmt, (err = launch_pdl(temporal_attn_kernel<T, 64>, dim3(grid), dim3(wpb * 32), smem, st, qkv, out,
+                                           Tn, P, C, sl)));
+    return (int)err;
   }
-  return last_err();
 }
 
 int launch_cross_attention(const void* q, int ldq, const void* kv, void* out, int F, int N, int C, int Lk,
