@@ -128,6 +128,9 @@ def test_2d_param_inventory_matches_published_sizes():
     c = stablenormal_config("full")
     assert count_params(unet2d_param_shapes(c.unet2d)) == 865_910_724
     assert count_params(vae2d_param_shapes(c.vae2d)) == 83_653_863
+    from unigeo_b200.config import ClipConfig
+    from unigeo_b200.weights import clip_param_shapes
+    assert count_params(clip_param_shapes(ClipConfig())) == 632_076_800        # CLIP ViT-H/14 vision tower + projection
     shapes = controlnet_param_shapes(c.unet2d)
     assert sum(k.startswith("controlnet_down_blocks.") and k.endswith(".weight") for k in shapes) == 12
     assert "controlnet_mid_block.weight" in shapes and "up_blocks.0.resnets.0.conv1.weight" not in shapes
