@@ -217,3 +217,43 @@ def test_refine_loop_graph_replay_is_bit_identical(bundle):
     ref = e2.refine_2d("unet2d", "controlnet", d["il"] * 0.5, d["x"] + 1.0, 2)       # eager in a fresh context
     assert torch.equal(other, ref)
     assert e.launch_count() - n0 == 4 * (n1 - n0)           # replays are counted like the launches they contain
+
+
+def test_plugin_with_yoso_start_and_checkpoint_directory(bundle, tmp_path):
+    """(1) yoso=True: the one-step initialiser (its own UNet + ControlNet) provides the start latent; (2) the same
+    weights written as a hub-style checkpoint directory (<dir>/<net>/*.safetensors, <dir>/vae, prompt_embeds.pt) and
+    loaded through ``weights=<dir>`` give bit-identical outputs; both against the oracle predictor."""
+    import os
+    from safetensors.torch import save_file
+    from oracle.stablenormal import stablenormal_predict
+    from unigeo_b200.model import StableNormal
+    from unigeo_b200.weights import (controlnet_param_shapes, synthetic_state_dict, unet2d_param_shapes,
+                                     vae2d_param_shapes)
+    cfg, sn, _, _, _, d = bundle
+    data = {"images": [f.transpose(2, 0, 1).astype(np.float32) for f in d["u8"]]}
+    noise = torch.randn(Fr, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(10))
+    plug = StableNormal(config="tiny", num_inference_steps=2, weight_seed=0, yoso=True)
+    out = plug.forward(data, init_noise=noise)
+    sds = {"unet2d": synthetic_state_dict(unet2d_param_shapes(sn.unet2d), 3000),
+           "controlnet": synthetic_state_dict(controlnet_param_shapes(sn.unet2d), 3010),
+           "yoso_unet": synthetic_state_dict(unet2d_param_shapes(sn.unet2d), 3020),
+           "yoso_controlnet": synthetic_state_dict(controlnet_param_shapes(sn.unet2d), 3030)}
+    vsd = synthetic_state_dict(vae2d_param_shapes(sn.vae2d), 4000)
+    prompt = torch.randn(sn.unet2d.context_len, sn.unet2d.cross_attention_dim,
+                         generator=torch.Generator().manual_seed(5000))
+    with torch.no_grad():
+        ref_u8 = stablenormal_predict(sds["unet2d"], sds["controlnet"], vsd, sn, d["u8"], prompt[None], noise, 2,
+                                      yoso_unet_sd=sds["yoso_unet"], yoso_ctrl_sd=sds["yoso_controlnet"])
+    ref = StableNormal.postprocess(list(ref_u8))["pred_normals"]
+    assert angular_deg(out["pred_normals"], ref).mean().item() <= 1.0
+    plain = StableNormal(config="tiny", num_inference_steps=2, weight_seed=0).forward(data, init_noise=noise)
+    assert angular_deg(plain["pred_normals"], out["pred_normals"]).mean().item() > 1.0     # the start latent matters
+    root = str(tmp_path)
+    for net, sd in sds.items():
+        os.makedirs(os.path.join(root, net))
+        save_file({k: v.contiguous() for k, v in sd.items()}, os.path.join(root, net, "diffusion_pytorch_model.safetensors"))
+    os.makedirs(os.path.join(root, "vae"))
+    save_file({k: v.contiguous() for k, v in vsd.items()}, os.path.join(root, "vae", "diffusion_pytorch_model.safetensors"))
+    torch.save(prompt, os.path.join(root, "prompt_embeds.pt"))
+    disk = StableNormal(config="tiny", num_inference_steps=2, weights=root, yoso=True).forward(data, init_noise=noise)
+    assert torch.equal(disk["pred_normals"], out["pred_normals"])
