@@ -284,6 +284,15 @@ gn_fused_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x
     __syncthreads();
     if (threadIdx.x == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
   }
+  // gamma / beta of this thread's channels are fetched before the wait: one L2 round trip off the critical path
+  constexpr int kGB = 8;                                  // C <= 2560, blockDim >= 320 there: at most 8 channels each
+  float gpre[kGB], bpre[kGB];
+#pragma unroll
+  for (int i = 0; i < kGB; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    gpre[i] = c < C ? __ldg(gamma + c) : 0.f;
+    bpre[i] = c < C ? __ldg(beta + c) : 0.f;
+  }
   if (threadIdx.x == 0) {
     unsigned int v;
     do {
@@ -303,11 +312,15 @@ gn_fused_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x
       s_rstd[threadIdx.x] = __ldcg(mr + (set * G + threadIdx.x) * 2 + 1);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const int g = c / cs;
-      const float ga = gamma[c] * s_rstd[g];
-      s_a[c] = ga;
-      s_b[c] = beta[c] - s_mean[g] * ga;
+#pragma unroll
+    for (int i = 0; i < kGB; ++i) {
+      const int c = threadIdx.x + i * blockDim.x;
+      if (c < C) {
+        const int g = c / cs;
+        const float ga = gpre[i] * s_rstd[g];
+        s_a[c] = ga;
+        s_b[c] = bpre[i] - s_mean[g] * ga;
+      }
     }
     __syncthreads();
     if (rr < rpb) {
@@ -1085,7 +1098,8 @@ inline GnGeom gn_geom(int nvec, long long rows_per_set, long long sets) {
   g.threads = nvec * rpb;   // >= 64 whenever C >= 64 * 8 / rpb ... padded below for tiny C
   if (g.threads < 64) g.threads = 64;
   long long want = (148LL * 4 + sets - 1) / sets;
-  long long maxc = (rows_per_set + rpb * 4 - 1) / (rpb * 4);
+  long long maxc = (rows_per_set + rpb * 8 - 1) / (rpb * 8);   // one batch of 8 loads per thread at least: fewer,
+                                                               // fatter chunks shorten the partial fold
   if (want > maxc) want = maxc;
   if (want < 1) want = 1;
   g.chunk_rows = (rows_per_set + want - 1) / want;
