@@ -68,6 +68,11 @@ void run_sized(ug_ctx* u, const std::string& sig, void* stream, const std::funct
 void run_graphed(ug_ctx* u, const std::string& key, const std::function<void(Ctx&)>& body) {
   static const bool off = getenv("UG_NO_GRAPH") != nullptr;
   Ctx& c = u->c;
+  if (u->graphs.size() > 16 && u->graphs.find(key) == u->graphs.end()) {   // bound the cache: drop everything, re-learn
+    for (auto& kv : u->graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    u->graphs.clear();
+  }
   GraphEntry& g = u->graphs[key];
   if (off || c.profile || g.disabled) { body(c); return; }
   if (g.exec && g.epoch != c.ptr_epoch) {
