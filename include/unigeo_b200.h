@@ -182,6 +182,26 @@ int ug_vae_decode_frames(ug_ctx* ctx, const float* lat, int T, int h, int w, int
 int ug_depth_postprocess(ug_ctx* ctx, const float* frames, const float* intrinsics, int T, int H, int W,
                          float* depths, float* normals, void* stream);
 
+/* ---- consumer side of the plugin boundary: the two metric functions eval.py applies to the outputs, on the device
+ * (SURVEY.md 8(f)-3), so that depths / normals can be scored where they were produced.
+ * ug_depth_metrics replaces depth_evaluation(pred, gt, custom_mask=mask, align_with_lstsq=True)
+ * (metrics/eval_depth.py:6-246 with metrics/alignment.py:150-167; call site eval.py:49): pred, gt fp32 [n] on the
+ * device (any [Nf][H][W] flattened), mask uint8 [n] (nullable, 0 = excluded), valid = gt > 0 && gt < max_depth;
+ * scale/shift fitted over `valid`, errors over valid && mask.  out11 (HOST doubles): Abs Rel, Sq Rel, RMSE,
+ * Log RMSE, delta<1, delta<1.25, delta<1.25^2, delta<1.25^3, valid_pixels, scale, shift (all 0 when nothing is
+ * valid, eval_depth.py:217-227).  err_map / pred_aligned / gt_valid: nullable fp32 [n] device outputs = the three
+ * full-size maps the reference returns beside the dict (eval_depth.py:166-213).
+ * ug_normal_metrics replaces normal_evaluation (metrics/eval_normal.py:4-72; call site eval.py:54): pred, gt fp32
+ * [n][3], mask uint8 [n] (nullable).  out8 (HOST doubles): normal mean, median (torch.median: lower middle value,
+ * exact), rmse, angle<5, <7.5, <11.25, <22.5, <30 in percent (NaN when the mask is empty); err_deg: nullable fp32
+ * [n] device output = the per-pixel angular error in degrees before masking (eval_normal.py:12-18).
+ * Both synchronise `stream` before returning (they return host scalars). */
+int ug_depth_metrics(ug_ctx* ctx, const float* pred, const float* gt, const unsigned char* mask, long long n,
+                     float max_depth, double* out11, float* err_map, float* pred_aligned, float* gt_valid,
+                     void* stream);
+int ug_normal_metrics(ug_ctx* ctx, const float* pred, const float* gt, const unsigned char* mask, long long n,
+                      double* out8, float* err_deg, void* stream);
+
 /* Replaces [UPSTREAM] encode_video (antialiased 224x224 resize, CLIP normalisation, ViT + projection):
  * video fp32 [F][3][H][W] in [-1,1] (ug_vae_encode_frames' video_nchw) -> image embeddings fp32 [F][proj_dim],
  * the encoder_hidden_states ug_set_clip_context takes.  Weight keys: "clip." + transformers state_dict names;

@@ -90,6 +90,8 @@ _SIGNATURES = {
     "ug_vae_encode_frames": ([_P, _P, _P, _F, _I, _I, _I, _P, _P, _P], C.c_int),
     "ug_vae_decode_frames": ([_P, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "ug_depth_postprocess": ([_P, _P, _P, _I, _I, _I, _P, _P, _P], C.c_int),
+    "ug_depth_metrics": ([_P, _P, _P, _P, _L, _F, C.POINTER(C.c_double), _P, _P, _P, _P], C.c_int),
+    "ug_normal_metrics": ([_P, _P, _P, _P, _L, C.POINTER(C.c_double), _P, _P], C.c_int),
     "ug_karras_schedule": ([C.POINTER(ModelCfg), _I, C.POINTER(C.c_double), C.POINTER(C.c_double),
                             C.POINTER(C.c_double)], C.c_int),
     "ug_ddim_schedule": ([C.POINTER(UNet2DCfg), _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_double),

@@ -459,6 +459,39 @@ int ug_depth_postprocess(ug_ctx* u, const float* frames, const float* intrinsics
   });
 }
 
+int ug_depth_metrics(ug_ctx* u, const float* pred, const float* gt, const unsigned char* mask, long long n,
+                     float max_depth, double* out11, float* err_map, float* pred_aligned, float* gt_valid,
+                     void* stream) {
+  return guard([&] {
+    UG_CHECK(u && pred && gt && out11, UG_ERR_INVALID, "null argument");
+    UG_CHECK(n >= 1, UG_ERR_INVALID, "n must be positive");
+    run_sized(u, "dmetrics:" + std::to_string(n), stream, [&](Ctx& c) {
+      void* ws = c.ws.alloc((size_t)metrics_workspace_bytes(n));
+      if (!c.dry) {
+        op_check(c, launch_depth_metrics(pred, gt, mask, n, max_depth, ws, out11, err_map, pred_aligned, gt_valid,
+                                         c.stream), "depth_metrics", 0.0, (mask ? 17.0 : 16.0) * n);
+        c.launches += 4;   // fit, fold, solve, errors, fold behind one launcher
+      }
+    });
+  });
+}
+
+int ug_normal_metrics(ug_ctx* u, const float* pred, const float* gt, const unsigned char* mask, long long n,
+                      double* out8, float* err_deg, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && pred && gt && out8, UG_ERR_INVALID, "null argument");
+    UG_CHECK(n >= 1, UG_ERR_INVALID, "n must be positive");
+    run_sized(u, "nmetrics:" + std::to_string(n), stream, [&](Ctx& c) {
+      void* ws = c.ws.alloc((size_t)metrics_workspace_bytes(n));
+      if (!c.dry) {
+        op_check(c, launch_normal_metrics(pred, gt, mask, n, ws, out8, err_deg, c.stream), "normal_metrics", 0.0,
+                 (28.0 + 4.0 * 4.0 + (mask ? 1.0 : 0.0)) * n);
+        c.launches += 9;   // errors, fold, 4 x (histogram, step) behind one launcher
+      }
+    });
+  });
+}
+
 int ug_vae_decode_temporal(ug_ctx* u, const float* lat, int T, int h, int w, int chunk, float* img, void* stream) {
   return guard([&] {
     UG_CHECK(u && lat && img, UG_ERR_INVALID, "null argument");

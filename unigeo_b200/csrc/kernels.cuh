@@ -93,6 +93,17 @@ int launch_euler_step(float* latents, const float* v, float sigma, float sigma_n
 long long post_workspace_floats(long long pixels);
 int launch_depth_postprocess(const float* frames, const float* K, int T, int H, int W, float* depth, float* normals,
                              float* ws, cudaStream_t st);
+// ---- metric kernels (metrics.cu): eval.py:49 / :54 on the device; results land in host doubles (the launchers
+// synchronise `st`).  ws: metrics_workspace_bytes(n) bytes.  mask nullable (uint8, 0 = excluded).
+long long metrics_workspace_bytes(long long n);
+// out[11]: Abs Rel, Sq Rel, RMSE, Log RMSE, delta<1, <1.25, <1.25^2, <1.25^3, valid_pixels, scale, shift;
+// err_map / pred_aligned / gt_valid: nullable fp32 [n] maps (eval_depth.py:166-213)
+int launch_depth_metrics(const float* pred, const float* gt, const unsigned char* mask, long long n, float max_depth,
+                         void* ws, double* out_host, float* err_map, float* pred_aligned, float* gt_valid,
+                         cudaStream_t st);
+// out[8]: normal mean, median, rmse, angle<5, <7.5, <11.25, <22.5, <30 (percent); err_deg nullable fp32 [n]
+int launch_normal_metrics(const float* pred, const float* gt, const unsigned char* mask, long long n, void* ws,
+                          double* out_host, float* err_deg, cudaStream_t st);
 // frames fp32 [T][HW][3] in [0,1] (+ noise fp32 [T][3][HW] * ns) -> 16-bit [T][HW][8]; video_nchw (nullable)
 // receives frames*2-1 as fp32 [T][3][HW] (the CLIP branch's input)
 int launch_frames_in(const float* frames, const float* noise, float ns, int T, long long HW, void* y,

@@ -221,6 +221,47 @@ class Engine:
                                                      normals.data_ptr(), _stream()))
         return depth, normals
 
+    # ------------------------------------------------------------------ metric kernels (eval.py:49 / :54)
+    def _mask_u8(self, mask, n: int):
+        if mask is None:
+            return None
+        m = torch.as_tensor(mask).to(self.device)
+        m = (m != 0).to(torch.uint8).contiguous().reshape(-1)
+        assert m.numel() == n, "custom_mask must have one entry per pixel"
+        return m
+
+    def depth_metrics(self, pred: torch.Tensor, gt: torch.Tensor, mask=None, max_depth: float = 80.0,
+                      with_maps: bool = False):
+        """Scale/shift-aligned depth metrics of one clip ([Nf,H,W] or [H,W] tensors, any device).
+        Returns (list of 11 floats, maps | None): see ug_depth_metrics in include/unigeo_b200.h."""
+        p, g = _f32(pred, self.device), _f32(gt, self.device)
+        assert p.shape == g.shape
+        n = p.numel()
+        m = self._mask_u8(mask, n)
+        out = (C.c_double * 11)()
+        maps = [torch.empty_like(g) for _ in range(3)] if with_maps else [None] * 3
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_depth_metrics(self._ctx, p.data_ptr(), g.data_ptr(),
+                                                 m.data_ptr() if m is not None else None, n, float(max_depth), out,
+                                                 *[t.data_ptr() if t is not None else None for t in maps],
+                                                 _stream()))
+        return list(out), (tuple(maps) if with_maps else None)
+
+    def normal_metrics(self, pred: torch.Tensor, gt: torch.Tensor, mask=None, with_map: bool = False):
+        """Angular-error metrics of one clip ([Nf,H,W,3] tensors, any device) -> list of 8 floats
+        (with_map: also the per-pixel error in degrees, [Nf,H,W])."""
+        p, g = _f32(pred, self.device), _f32(gt, self.device)
+        assert p.shape == g.shape and p.shape[-1] == 3
+        n = p.numel() // 3
+        m = self._mask_u8(mask, n)
+        out = (C.c_double * 8)()
+        err = torch.empty(p.shape[:-1], dtype=torch.float32, device=self.device) if with_map else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_normal_metrics(self._ctx, p.data_ptr(), g.data_ptr(),
+                                                  m.data_ptr() if m is not None else None, n, out,
+                                                  err.data_ptr() if with_map else None, _stream()))
+        return (list(out), err) if with_map else list(out)
+
     # ------------------------------------------------------------------ StableNormal path (2-D UNet)
     def set_text_context(self, net: str, tokens: torch.Tensor) -> None:
         """tokens [L,D] (shared prompt) or [F,L,D]: encoder_hidden_states of network ``net`` ("unet2d", ...)."""

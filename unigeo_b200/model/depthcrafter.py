@@ -75,24 +75,35 @@ class DepthCrafter:
         np.stack([np.asarray(x, dtype=np.float32) for x in imgs], axis=0, out=self._stage.numpy())
         return self.engine.prepare_frames(self._stage.to(self.device, non_blocking=True))
 
-    def prepare_output(self, frames: torch.Tensor, data):
-        """reference :92-97 + :48-69 on the device; returns CPU float32 tensors (pinned pages, so the
-        device->host copy runs at PCIe speed; torch's host allocator recycles them)."""
+    def prepare_output_device(self, frames: torch.Tensor, data):
+        """reference :92-97 + :48-69 on the device; the tensors stay there (scoring with
+        ``unigeo_b200.metrics`` then moves 19 scalars instead of 2 x 59 MB)."""
         K = torch.from_numpy(np.stack([np.asarray(k, dtype=np.float32) for k in data["intrinsics"]], 0))
         depth, normals = depth_and_normals(self.engine, frames, K)
-        d = torch.empty(depth.shape, dtype=torch.float32, pin_memory=True)
-        n = torch.empty(normals.shape, dtype=torch.float32, pin_memory=True)
-        d.copy_(depth, non_blocking=True)
-        n.copy_(normals, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return {"pred_depths": d, "pred_normals": n}
+        return {"pred_depths": depth, "pred_normals": normals}
 
-    def forward(self, data, **debug_inputs):
-        """``debug_inputs``: enc / aug_noise / init_noise tensors to pin the random draws (parity tests)."""
+    def prepare_output(self, frames: torch.Tensor, data):
+        """``prepare_output_device`` + the copy to CPU float32 tensors the reference contract asks for (pinned
+        pages, so the device->host copy runs at PCIe speed; torch's host allocator recycles them)."""
+        dev = self.prepare_output_device(frames, data)
+        out = {k: torch.empty(v.shape, dtype=torch.float32, pin_memory=True) for k, v in dev.items()}
+        for k, v in dev.items():
+            out[k].copy_(v, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
+
+    def _run(self, data, **debug_inputs):
         frames = self.prepare_input_device(data)
         gen = None
         if self.seed is not None:
             gen = torch.Generator(device=self.device).manual_seed(int(self.seed))
-        out = self.pipeline(frames, num_inference_steps=self.num_inference_steps, generator=gen,
-                            output_type="pt", **debug_inputs)
-        return self.prepare_output(out, data)
+        return self.pipeline(frames, num_inference_steps=self.num_inference_steps, generator=gen,
+                             output_type="pt", **debug_inputs)
+
+    def forward(self, data, **debug_inputs):
+        """``debug_inputs``: enc / aug_noise / init_noise tensors to pin the random draws (parity tests)."""
+        return self.prepare_output(self._run(data, **debug_inputs), data)
+
+    def forward_device(self, data, **debug_inputs):
+        """``forward`` without the final device->host copy: same values, CUDA tensors."""
+        return self.prepare_output_device(self._run(data, **debug_inputs), data)
