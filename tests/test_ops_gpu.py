@@ -173,3 +173,24 @@ def test_temporal_attention(cuda, dtype, T, P, C):
     p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, -1)
     ref = (p @ v).permute(2, 0, 1, 3).reshape(T, P, C)
     check("tattn", ops.temporal_attention(qkv, T, P, C), ref, dtype, tol_scale=2.0)
+
+
+def test_balanced_tile_lists_do_not_change_a_bit(cuda):
+    """tapgemm deals ragged-width tiles to the CTAs from a host-built balanced list (UG_SCHED, read once per process);
+    every tile is computed independently, so the outputs must equal the round-robin order's bit for bit."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, UG_SCHED=flag)
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "ab_sched.py"), "--quick"], env=env,
+                           capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    a, b = outs
+    assert [x["op"] for x in a["rows"]] == [x["op"] for x in b["rows"]] and len(a["rows"]) >= 5
+    for x, y in zip(a["rows"], b["rows"]):
+        assert x["sha"] == y["sha"], (x, y)

@@ -10,7 +10,12 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
 #include <mutex>
+#include <queue>
+#include <vector>
 
 namespace ug {
 
@@ -298,6 +303,14 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   };
   const int num_iters = a.num_taps * a.kchunks;
   const int unit0 = blockIdx.x / CTAS, unit_stride = gridDim.x / CTAS;
+  // i-th unit of this CTA (pair): round-robin, or the host's balanced list (ragged N tiles cost less than full ones,
+  // and a plain round-robin leaves the CTAs that drew one unit more holding the whole tail).  All three roles walk
+  // the same sequence.
+  auto unit_at = [&](int i) -> int {
+    if (a.sched != nullptr) return i < a.sched_len ? __ldg(a.sched + (size_t)unit0 * a.sched_len + i) : -1;
+    const long long t = (long long)unit0 + (long long)i * unit_stride;
+    return t < total_tiles ? (int)t : -1;
+  };
   // N extent of the tile starting at column n0: ragged last tile, rounded up to the UMMA granularity
   auto n_cur = [&](int n0) {
     const int rem = (a.n_total - n0 + G16 - 1) / G16 * G16;
@@ -345,7 +358,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t tx_bytes = ((uint32_t)(a.bw * a.bh * a.bn) * (BK * 2) +
                                  (uint32_t)(a.b_mn_major ? BK : BN / CTAS) * (BK * 2)) * CTAS;
       int it_g = 0;   // ring position, continuous across tiles
-      for (int t = unit0; t < total_tiles; t += unit_stride) {
+      for (int ui = 0, t; (t = unit_at(ui)) >= 0; ++ui) {
         int m_lin, n_tile_p, z;
         decode(t, m_lin, n_tile_p, z);
         int m_tile = m_lin * CTAS + rank;
@@ -394,7 +407,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (rank == 0) {
       const uint32_t bstep = a.b_mn_major ? 128u : 2u;
       int it_g = 0, tl = 0;
-      for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
+      for (int ui = 0, t; (t = unit_at(ui)) >= 0; ++ui, ++tl) {
         int m_lin_u, n_tile_u, z_u;
         decode(t, m_lin_u, n_tile_u, z_u);
         const int n0 = n_tile_u * BN;
@@ -456,7 +469,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int slab_it = 0;
     uint32_t ring_it = 0;                   // chunk ring position of this column group (res_tma path)
     int tl = 0;
-    for (int t = unit0; t < total_tiles; t += unit_stride, ++tl) {
+    for (int ui = 0, t; (t = unit_at(ui)) >= 0; ++ui, ++tl) {
       int m_lin, n_tile, z;
       decode(t, m_lin, n_tile, z);
       int m_tile = m_lin * CTAS + rank;
@@ -924,6 +937,85 @@ int tapgemm_pick_bn(const TapGemmArgs& a, int batch) {
   return tapgemm_pick_tile(a, batch, &ctas);
 }
 
+// Balanced unit lists for launches whose last N tile is ragged (cheaper than a full one) and that run more than one
+// wave: units are dealt in their normal order (M- or N-fastest, so the L2 reuse pattern is unchanged) to the CTA
+// (pair) that becomes free first under the picker's cost model -- what a dynamic tile counter would do, computed once
+// per shape on the host and kept in device memory for the life of the process (stable pointers: CUDA-graph safe).
+// Tiles are computed independently, so the assignment cannot change a single output bit (tested).  UG_SCHED=0 = off.
+namespace {
+struct SchedKey {
+  int dev, pm_tiles, n_tiles, batch, n_fastest, n_total, bn, ctas, slots, iters;
+  bool operator<(const SchedKey& o) const {
+    return std::memcmp(this, &o, sizeof(SchedKey)) < 0;
+  }
+};
+struct SchedVal { int* dev_ptr; int len; };
+
+bool tapgemm_schedule(const TapGemmArgs& a, int ctas, int pm_tiles, int slots, cudaStream_t stream, SchedVal* out) {
+  static const bool off = [] { const char* e = getenv("UG_SCHED"); return e && atoi(e) == 0; }();
+  const long long units = (long long)pm_tiles * a.n_tiles * a.batch;
+  if (off || units <= slots || a.n_total % a.bn_tile == 0 || units > (1 << 22)) return false;
+  static std::mutex mu;
+  static std::map<SchedKey, SchedVal> cache;
+  SchedKey key;
+  std::memset(&key, 0, sizeof(key));
+  cudaGetDevice(&key.dev);
+  key.pm_tiles = pm_tiles; key.n_tiles = a.n_tiles; key.batch = a.batch; key.n_fastest = a.n_fastest;
+  key.n_total = a.n_total; key.bn = a.bn_tile; key.ctas = ctas; key.slots = slots;
+  key.iters = a.num_taps * a.kchunks;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) { *out = it->second; return it->second.dev_ptr != nullptr; }
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return false;                        // never allocate / copy under capture; this launch stays round-robin
+  }
+  const int g16 = 16 * ctas;
+  auto unit_cost = [&](int t) -> long long {
+    int n_tile;
+    if (a.n_fastest) {
+      const int per_z = pm_tiles * a.n_tiles;
+      const int u = t % per_z, m_lin = u / a.n_tiles;
+      n_tile = (u - m_lin * a.n_tiles + m_lin) % a.n_tiles;
+    } else {
+      n_tile = (t / pm_tiles) % a.n_tiles;
+    }
+    const int rem = (a.n_total - n_tile * a.bn_tile + g16 - 1) / g16 * g16;
+    const long long bn = rem < a.bn_tile ? rem : a.bn_tile;
+    const long long per = ctas == 1 ? 256 + 2 * bn : (2 * bn > 256 + bn ? 2 * bn : 256 + bn);
+    const long long mma = (long long)key.iters * per, epi = 8 * bn + 200;      // epilogue overlaps the next tile
+    return (mma > epi ? mma : epi) + 48;
+  };
+  std::vector<long long> busy(slots, 0);
+  std::vector<std::vector<int>> lists(slots);
+  // (finish time, slot) min-heap; ties go to the lowest slot, so equal costs reproduce the round-robin order
+  std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>,
+                      std::greater<std::pair<long long, int>>> heap;
+  for (int s2 = 0; s2 < slots; ++s2) heap.push({0, s2});
+  for (int t = 0; t < (int)units; ++t) {
+    auto top = heap.top();
+    heap.pop();
+    lists[top.second].push_back(t);
+    heap.push({top.first + unit_cost(t), top.second});
+  }
+  size_t len = 0;
+  for (auto& l : lists) len = l.size() > len ? l.size() : len;
+  std::vector<int> table((size_t)slots * len, -1);
+  for (int s2 = 0; s2 < slots; ++s2)
+    for (size_t i = 0; i < lists[s2].size(); ++i) table[(size_t)s2 * len + i] = lists[s2][i];
+  SchedVal v{nullptr, (int)len};
+  if (cudaMalloc(&v.dev_ptr, table.size() * sizeof(int)) != cudaSuccess ||
+      cudaMemcpy(v.dev_ptr, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    v.dev_ptr = nullptr;
+  }
+  cache.emplace(key, v);
+  *out = v;
+  return v.dev_ptr != nullptr;
+}
+}  // namespace
+
 int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC,
                    const TapGemmArgs& args_in, int batch, cudaStream_t stream, const CUtensorMap* tmR) {
   static bool configured = false;
@@ -963,6 +1055,12 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   const long long units = ((m_tiles + ctas - 1) / ctas) * args.n_tiles * batch;
   if (units <= 0 || units > 0x7fffffffLL) return (int)cudaErrorInvalidValue;
   const int sms = tapgemm_num_sms();
+  {
+    SchedVal sv{nullptr, 0};
+    const bool have = tapgemm_schedule(args, ctas, (int)((m_tiles + ctas - 1) / ctas), sms / ctas, stream, &sv);
+    args.sched = have ? sv.dev_ptr : nullptr;
+    args.sched_len = have ? sv.len : 0;
+  }
   if (ctas == 1) {
     const int grid = (int)(units < sms ? units : sms);
     return (int)launch_pdl(tapgemm_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes,

@@ -50,6 +50,8 @@ struct TapGemmArgs {
                            // tmC / tmR are 32-column SWIZZLE_64B maps of the output / residual tensor
   int n_tiles, batch;      // filled by launch_tapgemm
   int n_fastest;           // tile order (filled by launch_tapgemm): N tiles of one M tile run concurrently
+  const int* sched;        // filled by launch_tapgemm: [grid units][sched_len] unit indices (-1 = none) when the host
+  int sched_len;           // balanced ragged-width tiles over the CTAs (list scheduling); nullptr = round-robin
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
   int out_fp32;
   int act;                 // 1: exact (erf) GELU on (acc * scale + bias) before residual / blend (ViT MLPs)
