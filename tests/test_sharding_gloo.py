@@ -40,6 +40,12 @@ def _worker(rank, world, port, q):
         video = sh.assemble_scene([full[k] for k in range(n)], starts, N, ov)
         single = sh.assemble_scene(sh.stitch_scene(clips, list(range(n)), n, ov), starts, N, ov)
         q.put((torch.allclose(video, single, atol=1e-6), torch.allclose(video, scene, atol=1e-4)))
+    # per-clip metric rows -> every rank, in clip order (5 clips on 2 ranks: rank 1 pads one row)
+    rows = torch.tensor([[float(k), 10.0 * k + 0.5] for k in mine], dtype=torch.float64)
+    table = sh.gather_metric_rows(mine, rows, n, rank, world)
+    want = torch.tensor([[float(k), 10.0 * k + 0.5] for k in range(n)], dtype=torch.float64)
+    assert torch.equal(table, want), table
+    assert torch.equal(sh.average_row(table), want.mean(0))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -2,7 +2,7 @@
 clip_length / clip_overlap, configs/depthcrafter_scannetpp.yaml:5-6, dataset/scannetpp/scannetpp.py:44) sharded
 across the ranks; every rank runs the plugin call on its clips with NO communication, then ONE NCCL all-gather
 of the overlap frames feeds the scale/shift chain + ramp (unigeo_b200/sharding.py), and the per-clip metric
-rows are gathered on rank 0.  Prints one JSON line on rank 0.
+rows (device metric kernels on device-resident outputs) are all-gathered.  Prints one JSON line on rank 0.
 
     python tools/run_scene.py                                   # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/run_scene.py
@@ -67,10 +67,12 @@ def sync():
 
 sync()
 t0 = time.perf_counter()
-outs = [plug.forward(clip_of(k)) for k in mine]
+# forward_device: depths / normals stay on the GPU -- the stitch and the metric kernels read them there, and only the
+# 17 metric scalars per clip come back (eval.py would move 2 x 59 MB per clip to the host and score there)
+outs = [plug.forward_device(clip_of(k)) for k in mine]
 torch.cuda.synchronize()
 t_clips = time.perf_counter() - t0
-depths = [o["pred_depths"].to(plug.device) for o in outs]
+depths = [o["pred_depths"] for o in outs]
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 stitched = sh.stitch_scene(depths, mine, a.clips, a.overlap, rank, world)
@@ -79,25 +81,31 @@ sync()
 t_total = time.perf_counter() - t0
 stitch_ms = e0.elapsed_time(e1)
 
-# per-clip metrics (oracle metrics = the reference's metric functions restated; test infrastructure, fine in a tool)
-from oracle import metrics as OM  # noqa: E402
-rows = []
+# per-clip metric rows on the device (ug_depth_metrics / ug_normal_metrics), gathered with ONE fixed-size all-gather
+from unigeo_b200 import metrics as DM  # noqa: E402
+t1 = time.perf_counter()
+local_rows = []
 for k, o in zip(mine, outs):
     gt = gt_label(clip_of(k))
-    m = OM.depth_evaluation(o["pred_depths"], gt["gt_depths"], gt["gt_masks"])
-    rows.append((k, float(m["Abs Rel"])))
-t = torch.tensor([t_clips, t_total, stitch_ms], device=plug.device, dtype=torch.float64)
+    d = DM.depth_evaluation(o["pred_depths"], gt["gt_depths"], custom_mask=gt["gt_masks"], align_with_lstsq=True,
+                            engine=plug.engine, with_maps=False)[0]
+    n = DM.normal_evaluation(o["pred_normals"], gt["gt_normals"], custom_mask=gt["gt_masks"], engine=plug.engine)
+    local_rows.append([float(d[key]) for key in DM.DEPTH_KEYS] + [float(n[key]) for key in DM.NORMAL_KEYS])
+table = sh.gather_metric_rows(mine, torch.tensor(local_rows, dtype=torch.float64, device=plug.device), a.clips, rank,
+                              world)
+torch.cuda.synchronize()
+t_metrics = time.perf_counter() - t1
+avg = sh.average_row(table)
+rows = [(k, float(table[k, 0])) for k in range(a.clips)]
+t = torch.tensor([t_clips, t_total, stitch_ms, t_metrics], device=plug.device, dtype=torch.float64)
 if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    allrows = [None] * world
-    dist.all_gather_object(allrows, rows)
-    rows = sorted(r for rr in allrows for r in rr)
 # seam check: after stitching, the ramped head of clip k starts exactly at clip k-1's (aligned) tail
 seam = None
 if world == 1:
     seam = max(float((stitched[k][0] - stitched[k - 1][-a.overlap]).abs().max()) for k in range(1, a.clips))
 if rank == 0:
-    tc, tt, sm = t.tolist()
+    tc, tt, sm, tm = t.tolist()
     print(json.dumps({
         "workload": f"scene of {a.clips} clips x {a.frames} frames (overlap {a.overlap}, {num_frames} distinct frames) at "
                     f"{a.height}x{a.width}, {a.steps} denoising steps per clip, clip-sharded over {world} GPU(s)",
@@ -105,7 +113,10 @@ if rank == 0:
         "seconds_clips": tc, "seconds_total_incl_stitch": tt, "stitch_ms_device": sm,
         "clips_per_s": a.clips / tt, "denoising_steps_per_s": a.clips * a.steps / tt,
         "collective": "one all_gather of [clips/rank, 2, overlap, H, W] fp32 overlap frames (NCCL)" if world > 1 else "none",
-        "abs_rel_per_clip": [round(v, 5) for _, v in rows], "seam_max_abs_after_stitch": seam}))
+        "abs_rel_per_clip": [round(v, 5) for _, v in rows], "seam_max_abs_after_stitch": seam,
+        "metrics_seconds_all_local_clips": tm,
+        "metrics": "device kernels (ug_depth_metrics / ug_normal_metrics) on device-resident outputs; rows all-gathered",
+        "average_row": {key: round(float(v), 5) for key, v in zip(DM.DEPTH_KEYS + DM.NORMAL_KEYS, avg.tolist())}}))
 if world > 1:
     dist.barrier()
     dist.destroy_process_group()

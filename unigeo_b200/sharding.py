@@ -90,3 +90,27 @@ def assemble_scene(stitched: Sequence[torch.Tensor], starts: Sequence[int], num_
         keep = d if last else d[: d.shape[0] - overlap]
         frames.append(keep)
     return torch.cat(frames, 0)[:num_frames]
+
+
+def gather_metric_rows(local_ids: Sequence[int], local_rows: torch.Tensor, num_clips: int, rank: int = 0,
+                       world: int = 1) -> torch.Tensor:
+    """Per-clip metric rows (the 9 + 8 floats eval.py:49-57 puts in one CSV line) from every rank
+    to every rank: local_rows [len(local_ids), K] float64 -> [num_clips, K] in clip order.  One fixed-size
+    all-gather (NCCL on GPUs, gloo in the CPU test); ranks with fewer clips pad with NaN rows."""
+    local_rows = local_rows.to(torch.float64)
+    K = local_rows.shape[1]
+    per_rank = (num_clips + world - 1) // world
+    buf = torch.full((per_rank, K), float("nan"), dtype=torch.float64, device=local_rows.device)
+    buf[: local_rows.shape[0]] = local_rows
+    gathered = _gather(buf, world)
+    out = torch.full((num_clips, K), float("nan"), dtype=torch.float64, device=local_rows.device)
+    for r in range(world):
+        ids = clips_of_rank(num_clips, r, world)
+        if ids:
+            out[torch.as_tensor(ids, device=out.device)] = gathered[r][: len(ids)]
+    return out
+
+
+def average_row(rows: torch.Tensor) -> torch.Tensor:
+    """The 'Average' line metrics/save_utils.py:64-90 appends: column means over the clips."""
+    return rows.mean(dim=0)
