@@ -364,6 +364,157 @@ gn_fused_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x
   }
 }
 
+// ------------------------------------------------------------------ GroupNorm over a thread-block cluster
+// For statistics sets that fit the shared memory of one cluster (<= 8 CTAs x 64 KB of rows: the per-frame GroupNorms
+// of the UNet's two lowest resolutions): each CTA pulls its rows from HBM ONCE into shared memory while it accumulates
+// its partial sums, the cluster exchanges the per-group partials through distributed shared memory (every CTA folds
+// them in rank order: deterministic, identical on all ranks), and the rows are normalised straight out of shared
+// memory.  No global partials, no tickets or flags, no second read of x: the one-launch kernel above spends 19-33 us
+// on a 3-25 MB tensor in its launch -> partials -> ticket -> fold -> flag -> apply chain.
+template <typename T>
+__global__ void __launch_bounds__(320)
+gn_cluster_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2, long long rows_per_set,
+                  int chunk_rows, int G, int cs, float inv_cnt, float eps, const float* __restrict__ gamma,
+                  const float* __restrict__ beta, int silu, void* __restrict__ y) {
+  pdl_launch_dependents();
+  extern __shared__ __align__(16) unsigned char s_cl[];
+  const int nvec = nv1 + nv2;
+  const int C = nvec * 8;
+  const int rpb = blockDim.x / nvec;
+  const int c8 = threadIdx.x % nvec;
+  const int rr = threadIdx.x / nvec;
+  const unsigned int S = gridDim.x;                     // the cluster spans the grid's x extent
+  const unsigned int rank = blockIdx.x;
+  const long long set = blockIdx.y;
+  const long long r_begin = (long long)rank * chunk_rows;
+  long long r_stop = r_begin + chunk_rows;
+  if (r_stop > rows_per_set) r_stop = rows_per_set;
+  const int nrows = r_stop > r_begin ? (int)(r_stop - r_begin) : 0;
+  uint4* tile = reinterpret_cast<uint4*>(s_cl);                                   // [chunk_rows][nvec]
+  float* s_part = reinterpret_cast<float*>(s_cl + (size_t)chunk_rows * nvec * 16); // [2][rpb][C]; later s_a | s_b
+  float* s_stat = s_part + (size_t)2 * rpb * C;                                   // [G][2], read by the peers
+  float* s_mean = s_stat + 2 * G;
+  float* s_rstd = s_mean + G;
+  // the affine parameters are weights, not the previous kernel's output: fetch them ahead of the dependency wait
+  constexpr int kGB = 8;
+  float gpre[kGB], bpre[kGB];
+#pragma unroll
+  for (int i = 0; i < kGB; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    gpre[i] = c < C ? __ldg(gamma + c) : 0.f;
+    bpre[i] = c < C ? __ldg(beta + c) : 0.f;
+  }
+  pdl_wait();
+  // ---- phase 1: rows -> shared memory, partial (sum, sumsq) per channel
+  {
+    float2 a[4], q[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a[j] = make_float2(0.f, 0.f); q[j] = make_float2(0.f, 0.f); }
+    if (rr < rpb) {
+      for (int r = rr; r < nrows; r += 8 * rpb) {
+        uint4 u[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rk = r + k * rpb;
+          u[k] = rk < nrows ? __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r_begin + rk, c8))
+                            : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int rk = r + k * rpb;
+          if (rk < nrows) tile[(size_t)rk * nvec + c8] = u[k];
+          float2 f[4];
+          unpack4x2<T>(u[k], f);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { a[j] = __fadd2_rn(a[j], f[j]); q[j] = __ffma2_rn(f[j], f[j], q[j]); }
+        }
+      }
+      float2* ps = reinterpret_cast<float2*>(s_part + (size_t)rr * C + c8 * 8);
+      float2* pq = reinterpret_cast<float2*>(s_part + (size_t)(rpb + rr) * C + c8 * 8);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { ps[j] = a[j]; pq[j] = q[j]; }
+    }
+  }
+  __syncthreads();
+  {
+    // L lanes per group (fixed strided split + xor tree: the same order on every run)
+    int L = 8;
+    while (L > 1 && G * L > (int)blockDim.x) L >>= 1;
+    const int g = threadIdx.x / L, l = threadIdx.x % L;
+    float sa = 0.f, sq = 0.f;
+    if (g < G) {
+      const int per_group = rpb * cs;
+      for (int e = l; e < per_group; e += L) {
+        const int r = e / cs, cc = g * cs + (e - r * cs);
+        sa += s_part[(size_t)r * C + cc];
+        sq += s_part[(size_t)(rpb + r) * C + cc];
+      }
+    }
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ta = __shfl_xor_sync(0xffffffffu, sa, o), tq = __shfl_xor_sync(0xffffffffu, sq, o);
+      if (o < L) { sa += ta; sq += tq; }
+    }
+    if (g < G && l == 0) {
+      s_stat[2 * g] = sa;
+      s_stat[2 * g + 1] = sq;
+    }
+  }
+  cluster_arrive_release();                             // partials of this CTA are visible to the cluster ...
+  cluster_wait_acquire();                               // ... and everybody else's are visible here
+  if (threadIdx.x < G) {
+    float2 v[8];                                        // all remote reads in flight at once (S <= 8)
+#pragma unroll
+    for (unsigned int r = 0; r < 8; ++r)
+      v[r] = r < S ? ld_dsmem_f2(s_stat + 2 * threadIdx.x, r) : make_float2(0.f, 0.f);
+    float sa = 0.f, sq = 0.f;
+#pragma unroll
+    for (unsigned int r = 0; r < 8; ++r) {              // rank order on every CTA: one result, bit for bit
+      sa += v[r].x;
+      sq += v[r].y;
+    }
+    const float mean = sa * inv_cnt;
+    const float var = fmaxf(sq * inv_cnt - mean * mean, 0.f);
+    s_mean[threadIdx.x] = mean;
+    s_rstd[threadIdx.x] = rsqrtf(var + eps);
+  }
+  cluster_arrive_release();                             // done reading the peers (waited for before exit)
+  __syncthreads();
+  // ---- phase 2: y = act((x - mean) * rstd * gamma + beta) out of shared memory
+  float* s_a = s_part;
+  float* s_b = s_part + C;
+#pragma unroll
+  for (int i = 0; i < kGB; ++i) {
+    const int c = threadIdx.x + i * blockDim.x;
+    if (c < C) {
+      const int g = c / cs;
+      const float ga = gpre[i] * s_rstd[g];
+      s_a[c] = ga;
+      s_b[c] = bpre[i] - s_mean[g] * ga;
+    }
+  }
+  __syncthreads();
+  if (rr < rpb) {
+    float2 sa[4], sb[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sa[j] = reinterpret_cast<const float2*>(s_a + c8 * 8)[j];
+      sb[j] = reinterpret_cast<const float2*>(s_b + c8 * 8)[j];
+    }
+    uint4* yo = reinterpret_cast<uint4*>(y) + (set * rows_per_set + r_begin) * nvec + c8;
+    for (int r = rr; r < nrows; r += rpb) {
+      float2 f0[4];
+      unpack4x2<T>(tile[(size_t)r * nvec + c8], f0);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 v0 = __ffma2_rn(f0[j], sa[j], sb[j]);
+        f0[j] = silu ? silu2(v0) : v0;
+      }
+      yo[(size_t)r * nvec] = pack4x2<T>(f0);
+    }
+  }
+  cluster_wait_acquire();                               // a CTA's shared memory must outlive its peers' reads
+}
+
 // ------------------------------------------------------------------ GroupNorm finalize
 // one CTA per statistics set: (mean, rstd) per group from the per-chunk partials, summed in a fixed
 // order (thread k adds chunks k, k+8, ...; the 8 lanes of a group are then folded in lane order).
@@ -1209,6 +1360,61 @@ int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long ro
   cudaError_t err;
   UG_DISPATCH_FMT(fmt, (err = launch_pdl(gn_apply_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
                                          rows_per_set, g.chunk_rows, G, C / G, mr, gamma, beta, silu, y)));
+  return (int)err;
+}
+
+// GroupNorm over clusters of <= 8 CTAs (gn_cluster_kernel); cudaErrorNotSupported when a statistics set does not fit
+// the shared memory of one cluster (caller uses launch_gn_fused).  UG_GN_CLUSTER=0 disables.
+int launch_gn_cluster(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set, int G,
+                      float eps, const float* gamma, const float* beta, int silu, void* y, int fmt, cudaStream_t st) {
+  static const bool off = [] { const char* e = getenv("UG_GN_CLUSTER"); return e && atoi(e) == 0; }();
+  const int C = C1 + C2;
+  const int nvec = C / 8;
+  if (off || (C1 & 7) || (C2 & 7) || C % G || G > 64 || nvec > 320 || nvec < 1 || rows % rows_per_set)
+    return (int)cudaErrorNotSupported;
+  const long long sets = rows / rows_per_set;
+  const int rpb = 320 / nvec;
+  const int threads = nvec * rpb;
+  if (threads < G || sets > 65535 || rows_per_set > (1 << 24)) return (int)cudaErrorNotSupported;
+  // measured (tools/ab_gn.py): the cluster form wins while a CTA's rows stay <= 64 KB (17 -> 13, 23 -> 17, 25 -> 20 us
+  // at the L3 / L2 shapes) and loses at 123+ KB per CTA (one 320-thread CTA per SM cannot keep enough loads in flight)
+  constexpr size_t kBudget = 96 * 1024, kTileMax = 64 * 1024;
+  const size_t fixed = ((size_t)2 * rpb * C + 4 * G) * sizeof(float);
+  int S = 8;
+  while (S > 1 && S > rows_per_set) S >>= 1;
+  const int chunk_rows = (int)((rows_per_set + S - 1) / S);
+  const size_t tile_bytes = (size_t)chunk_rows * nvec * 16;
+  const size_t smem = tile_bytes + fixed;
+  if (tile_bytes > kTileMax || smem > kBudget) return (int)cudaErrorNotSupported;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gn_cluster_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kBudget);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gn_cluster_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               (int)kBudget);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)S, (unsigned)sets);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  static const bool no_pdl = getenv("UG_NO_PDL") != nullptr;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)S;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = no_pdl ? 1 : 2;
+  const float inv_cnt = 1.0f / ((float)rows_per_set * (float)(C / G));
+  cudaError_t err;
+  UG_DISPATCH_FMT(fmt, (err = cudaLaunchKernelEx(&cfg, gn_cluster_kernel<T>, x1, C1 / 8, x2, C2 / 8, rows_per_set,
+                                                 chunk_rows, G, C / G, inv_cnt, eps, gamma, beta, silu, y)));
   return (int)err;
 }
 

@@ -24,6 +24,10 @@ int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long ro
 int launch_gn_fused(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set, int G,
                     float eps, float* stats, unsigned int* counters, const float* gamma, const float* beta, int silu,
                     void* y, int fmt, cudaStream_t st);
+// the same in one launch over clusters of <= 8 CTAs whose shared memory holds a whole statistics set (x read from
+// HBM once, partial sums exchanged through distributed shared memory).  cudaErrorNotSupported when a set does not fit.
+int launch_gn_cluster(const void* x1, int C1, const void* x2, int C2, long long rows, long long rows_per_set, int G,
+                      float eps, const float* gamma, const float* beta, int silu, void* y, int fmt, cudaStream_t st);
 // folds the partials into (mean, rstd) per (set, group), stored behind the partials in `stats`
 int launch_gn_finalize(int C, long long rows, long long rows_per_set, int G, float eps, float* stats,
                        cudaStream_t st);

@@ -458,6 +458,14 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
     }
     static const bool two_pass = getenv("UG_GN_TWO_PASS") != nullptr;
     const std::string shape = "rows" + std::to_string(rows) + " C" + std::to_string(C1 + C2) + " sets" + std::to_string(sets);
+    if (!two_pass) {      // sets that fit one cluster's shared memory: x read once, no global flags
+      const int rc = launch_gn_cluster(x1, C1, x2, C2, rows, rows_per_set, G, eps, gamma, beta, silu, y, c.fmt, c.stream);
+      if (rc != (int)cudaErrorNotSupported) {
+        op_check(c, rc, prof_name(c, "gn_cluster", shape), 0.0, 4.0 * rows * (C1 + C2));
+        c.ws.release(m);
+        return;
+      }
+    }
     int r = two_pass ? (int)cudaErrorNotSupported
                      : launch_gn_fused(x1, C1, x2, C2, rows, rows_per_set, G, eps, stats, c.gn_counters, gamma, beta, silu,
                                        y, c.fmt, c.stream);
