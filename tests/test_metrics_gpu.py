@@ -123,12 +123,13 @@ def test_full_size_properties(cuda):
     for k in ("Abs Rel", "Sq Rel", "RMSE", "Log RMSE"):
         assert abs(r1[k] - r2[k]) <= 1e-4 * max(1.0, r1[k]), (k, r1[k], r2[k])
     exact = depth_evaluation(0.25 * gt - 1.0, gt, custom_mask=mask, align_with_lstsq=True, with_maps=False)[0]
-    assert exact["Abs Rel"] < 1e-5 and exact["delta < 1.25"] == 1.0
+    assert exact["Abs Rel"] < 1e-5 and exact["delta < 1.25"] > 0.9999     # gt arbitrarily close to 0 in this draw
     n = torch.nn.functional.normalize(torch.randn(shape + (3,), generator=g, device=cuda), dim=-1)
     same = normal_evaluation(n, n, custom_mask=mask)
-    assert same["normal mean"] < 0.05 and same["angle < 5"] == 100.0
+    # cos = 1 / (1 + 1e-6) in the reference's formula (eval_normal.py:15): acos gives 0.081 degrees, not 0
+    assert same["normal mean"] < 0.15 and same["angle < 5"] == 100.0
     anti = normal_evaluation(n, -n, custom_mask=mask)
-    assert anti["normal mean"] > 179.95 and anti["angle < 30"] == 0.0 and abs(anti["normal median"] - 180.0) < 0.05
+    assert anti["normal mean"] > 179.85 and anti["angle < 30"] == 0.0 and abs(anti["normal median"] - 180.0) < 0.15
     # median of a known distribution: pred tilted from gt = +z by theta in [0, 60) degrees, uniform
     theta = torch.rand(shape, generator=g, device=cuda) * (np.pi / 3)
     z = torch.zeros(shape + (3,), device=cuda)
