@@ -217,6 +217,15 @@ int ug_clip_embed(ug_ctx* ctx, const float* video, int F, int H, int W, float* e
 int ug_karras_schedule(const ug_model_cfg* cfg, int steps, double* sigmas, double* timesteps, double* init_noise_sigma);
 int ug_ddim_schedule(const ug_unet2d_cfg* cfg, int steps, int t_start, int* timesteps, double* c_x0, double* c_x);
 
+/* Host-only: the per-CTA unit lists tapgemm uses when the last N tile of a launch is ragged (balanced by list
+ * scheduling under the tile picker's cost model; every unit exactly once).  m_units = M tiles (pairs of M tiles when
+ * ctas == 2), slots = CTAs (CTA pairs) of the persistent grid, k_iters = taps x 64-channel chunks.  units_out
+ * (nullable) receives a [slots][len] table (-1 = none), cap = its capacity in ints; returns len (>= 1) or a negative
+ * ug_status.  max_cost / rr_max_cost (nullable): modelled cost of the heaviest CTA under this assignment / under
+ * round-robin.  No device needed. */
+int ug_tile_schedule(int m_units, int n_total, int bn_tile, int batch, int n_fastest, int ctas, int slots, int k_iters,
+                     int* units_out, int cap, long long* max_cost, long long* rr_max_cost);
+
 /* Kernels launched on behalf of this context since the last reset (bench "gpu_launches"). */
 long long ug_ctx_launch_count(ug_ctx* ctx, int reset);
 /* Bytes of workspace currently reserved. */

@@ -236,3 +236,43 @@ def test_product_never_imports_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "harness" not in src or f == "__init__.py", f
+
+
+def test_tile_schedule_is_a_balanced_partition_without_gpu():
+    """ug_tile_schedule (host-only): the per-CTA unit lists tapgemm walks when the last N tile is ragged.  Every unit
+    appears exactly once, equal-cost launches reproduce round-robin, the heaviest CTA is never heavier than under
+    round-robin, and the cfg2 shape that motivated it (M19200 N640: 225 units on 74 CTA pairs) gets lighter."""
+    import ctypes as C
+    from unigeo_b200 import _lib
+    lib = _lib.load()
+
+    def sched(m_units, n_total, bn, batch, nfast, ctas, slots, iters):
+        mx, rr = C.c_longlong(), C.c_longlong()
+        ln = lib.ug_tile_schedule(m_units, n_total, bn, batch, nfast, ctas, slots, iters, None, 0, C.byref(mx), C.byref(rr))
+        assert ln >= 1, _lib.load().ug_last_error()
+        tab = (C.c_int * (slots * ln))()
+        assert lib.ug_tile_schedule(m_units, n_total, bn, batch, nfast, ctas, slots, iters, tab, slots * ln, None, None) == ln
+        return [list(tab[s * ln:(s + 1) * ln]) for s in range(slots)], mx.value, rr.value
+
+    cases = [(75, 640, 256, 1, 0, 2, 74, 10), (75, 640, 256, 1, 1, 2, 74, 40), (300, 320, 192, 1, 0, 2, 74, 45),
+             (300, 320, 192, 1, 1, 2, 74, 5), (150, 640, 256, 1, 0, 1, 148, 10), (19, 1280, 192, 1, 0, 2, 74, 20),
+             (7, 100, 64, 3, 0, 1, 5, 1), (1, 320, 192, 1, 0, 2, 74, 5), (75, 1920, 256, 1, 0, 2, 74, 10)]
+    for m_units, n_total, bn, batch, nfast, ctas, slots, iters in cases:
+        lists, mx, rr = sched(m_units, n_total, bn, batch, nfast, ctas, slots, iters)
+        n_tiles = -(-n_total // bn)
+        flat = [u for l in lists for u in l if u >= 0]
+        assert sorted(flat) == list(range(m_units * n_tiles * batch)), (m_units, n_total, bn)
+        for l in lists:                                   # -1 padding only at the end, units ascending per CTA
+            real = [u for u in l if u >= 0]
+            assert l[:len(real)] == real and real == sorted(real)
+        assert mx <= rr
+    # equal-cost units (N a multiple of the tile): exactly the round-robin order
+    lists, mx, rr = sched(40, 512, 256, 1, 0, 2, 7, 8)
+    assert mx == rr and all([u for u in l if u >= 0] == list(range(s, 80, 7)) for s, l in enumerate(lists))
+    # the motivating shape: 150 full + 75 half-width units on 74 pairs
+    _, mx, rr = sched(75, 640, 256, 1, 0, 2, 74, 10)
+    assert mx < rr
+    # argument validation
+    assert lib.ug_tile_schedule(10, 320, 100, 1, 0, 2, 74, 5, None, 0, None, None) < 0
+    tab = (C.c_int * 4)()
+    assert lib.ug_tile_schedule(300, 320, 192, 1, 0, 2, 74, 5, tab, 4, None, None) < 0

@@ -148,8 +148,9 @@ def test_plugin_scored_on_device(cuda):
     from unigeo_b200.model import DepthCrafter
     data = make_clip(5, 128, 256, seed=3)
     plug = DepthCrafter(config="tiny", dtype="fp16", weights="synthetic", num_inference_steps=2, clip="none", seed=1)
-    dev = plug.forward_device(data)
-    cpu = plug.forward(data)
+    enc = torch.randn(5, plug.cfg.clip_embed_dim, generator=torch.Generator().manual_seed(2))
+    dev = plug.forward_device(data, enc=enc)          # seed=1: both calls draw the same noise
+    cpu = plug.forward(data, enc=enc)
     assert dev["pred_depths"].is_cuda and torch.equal(dev["pred_depths"].cpu(), cpu["pred_depths"])
     assert torch.equal(dev["pred_normals"].cpu(), cpu["pred_normals"])
     gt = gt_label(data)

@@ -96,6 +96,8 @@ _SIGNATURES = {
                             C.POINTER(C.c_double)], C.c_int),
     "ug_ddim_schedule": ([C.POINTER(UNet2DCfg), _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_double),
                           C.POINTER(C.c_double)], C.c_int),
+    "ug_tile_schedule": ([_I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int), _I, C.POINTER(C.c_longlong),
+                          C.POINTER(C.c_longlong)], C.c_int),
     "ug_ctx_launch_count": ([_P, _I], C.c_longlong),
     "ug_ctx_workspace_bytes": ([_P], C.c_longlong),
     "ug_ctx_graph_count": ([_P], C.c_longlong),

@@ -459,6 +459,27 @@ int ug_depth_postprocess(ug_ctx* u, const float* frames, const float* intrinsics
   });
 }
 
+int ug_tile_schedule(int m_units, int n_total, int bn_tile, int batch, int n_fastest, int ctas, int slots, int k_iters,
+                     int* units_out, int cap, long long* max_cost, long long* rr_max_cost) {
+  int ret = 0;
+  const int rc = guard([&] {
+    UG_CHECK(m_units >= 1 && n_total >= 1 && batch >= 1 && slots >= 1 && k_iters >= 1, UG_ERR_INVALID, "bad extents");
+    UG_CHECK((ctas == 1 || ctas == 2) && bn_tile >= 16 * ctas && bn_tile <= 256 && bn_tile % (16 * ctas) == 0,
+             UG_ERR_INVALID, "bn_tile must be a multiple of 16 * ctas, <= 256");
+    const int n_tiles = (n_total + bn_tile - 1) / bn_tile;
+    UG_CHECK((long long)m_units * n_tiles * batch <= (1 << 22), UG_ERR_INVALID, "too many units");
+    std::vector<int> table;
+    const int len = tapgemm_build_schedule(m_units, n_tiles, batch, n_fastest ? 1 : 0, n_total, bn_tile, ctas, slots,
+                                           k_iters, &table, max_cost, rr_max_cost);
+    if (units_out != nullptr) {
+      UG_CHECK((long long)cap >= (long long)slots * len, UG_ERR_INVALID, "units_out too small");
+      std::memcpy(units_out, table.data(), table.size() * sizeof(int));
+    }
+    ret = len;
+  });
+  return rc != UG_OK ? rc : ret;
+}
+
 int ug_depth_metrics(ug_ctx* u, const float* pred, const float* gt, const unsigned char* mask, long long n,
                      float max_depth, double* out11, float* err_map, float* pred_aligned, float* gt_valid,
                      void* stream) {

@@ -942,6 +942,56 @@ int tapgemm_pick_bn(const TapGemmArgs& a, int batch) {
 // (pair) that becomes free first under the picker's cost model -- what a dynamic tile counter would do, computed once
 // per shape on the host and kept in device memory for the life of the process (stable pointers: CUDA-graph safe).
 // Tiles are computed independently, so the assignment cannot change a single output bit (tested).  UG_SCHED=0 = off.
+// Pure host part (no CUDA): per-slot unit lists as a [slots][len] table (-1 = none); returns len.  max_cost / rr_max_cost
+// (nullable) receive the heaviest slot's modelled cost under this assignment and under plain round-robin.
+int tapgemm_build_schedule(int pm_tiles, int n_tiles, int batch, int n_fastest, int n_total, int bn_tile, int ctas,
+                           int slots, int iters, std::vector<int>* table, long long* max_cost, long long* rr_max_cost) {
+  const long long units = (long long)pm_tiles * n_tiles * batch;
+  const int g16 = 16 * ctas;
+  auto unit_cost = [&](int t) -> long long {
+    int n_tile;
+    if (n_fastest) {
+      const int per_z = pm_tiles * n_tiles;
+      const int u = t % per_z, m_lin = u / n_tiles;
+      n_tile = (u - m_lin * n_tiles + m_lin) % n_tiles;
+    } else {
+      n_tile = (t / pm_tiles) % n_tiles;
+    }
+    const int rem = (n_total - n_tile * bn_tile + g16 - 1) / g16 * g16;
+    const long long bn = rem < bn_tile ? rem : bn_tile;
+    const long long per = ctas == 1 ? 256 + 2 * bn : (2 * bn > 256 + bn ? 2 * bn : 256 + bn);
+    const long long mma = (long long)iters * per, epi = 8 * bn + 200;      // epilogue overlaps the next tile
+    return (mma > epi ? mma : epi) + 48;
+  };
+  std::vector<std::vector<int>> lists(slots);
+  std::vector<long long> rr(slots, 0);
+  // (finish time, slot) min-heap; ties go to the lowest slot, so equal costs reproduce the round-robin order
+  std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>,
+                      std::greater<std::pair<long long, int>>> heap;
+  for (int s2 = 0; s2 < slots; ++s2) heap.push({0, s2});
+  long long worst = 0;
+  for (int t = 0; t < (int)units; ++t) {
+    auto top = heap.top();
+    heap.pop();
+    lists[top.second].push_back(t);
+    const long long c = unit_cost(t);
+    heap.push({top.first + c, top.second});
+    if (top.first + c > worst) worst = top.first + c;
+    rr[t % slots] += c;
+  }
+  size_t len = 0;
+  for (auto& l : lists) len = l.size() > len ? l.size() : len;
+  table->assign((size_t)slots * len, -1);
+  for (int s2 = 0; s2 < slots; ++s2)
+    for (size_t i = 0; i < lists[s2].size(); ++i) (*table)[(size_t)s2 * len + i] = lists[s2][i];
+  if (max_cost) *max_cost = worst;
+  if (rr_max_cost) {
+    *rr_max_cost = 0;
+    for (long long v : rr) *rr_max_cost = v > *rr_max_cost ? v : *rr_max_cost;
+  }
+  return (int)len;
+}
+
 namespace {
 struct SchedKey {
   int dev, pm_tiles, n_tiles, batch, n_fastest, n_total, bn, ctas, slots, iters;
@@ -971,40 +1021,10 @@ bool tapgemm_schedule(const TapGemmArgs& a, int ctas, int pm_tiles, int slots, c
     cudaGetLastError();
     return false;                        // never allocate / copy under capture; this launch stays round-robin
   }
-  const int g16 = 16 * ctas;
-  auto unit_cost = [&](int t) -> long long {
-    int n_tile;
-    if (a.n_fastest) {
-      const int per_z = pm_tiles * a.n_tiles;
-      const int u = t % per_z, m_lin = u / a.n_tiles;
-      n_tile = (u - m_lin * a.n_tiles + m_lin) % a.n_tiles;
-    } else {
-      n_tile = (t / pm_tiles) % a.n_tiles;
-    }
-    const int rem = (a.n_total - n_tile * a.bn_tile + g16 - 1) / g16 * g16;
-    const long long bn = rem < a.bn_tile ? rem : a.bn_tile;
-    const long long per = ctas == 1 ? 256 + 2 * bn : (2 * bn > 256 + bn ? 2 * bn : 256 + bn);
-    const long long mma = (long long)key.iters * per, epi = 8 * bn + 200;      // epilogue overlaps the next tile
-    return (mma > epi ? mma : epi) + 48;
-  };
-  std::vector<long long> busy(slots, 0);
-  std::vector<std::vector<int>> lists(slots);
-  // (finish time, slot) min-heap; ties go to the lowest slot, so equal costs reproduce the round-robin order
-  std::priority_queue<std::pair<long long, int>, std::vector<std::pair<long long, int>>,
-                      std::greater<std::pair<long long, int>>> heap;
-  for (int s2 = 0; s2 < slots; ++s2) heap.push({0, s2});
-  for (int t = 0; t < (int)units; ++t) {
-    auto top = heap.top();
-    heap.pop();
-    lists[top.second].push_back(t);
-    heap.push({top.first + unit_cost(t), top.second});
-  }
-  size_t len = 0;
-  for (auto& l : lists) len = l.size() > len ? l.size() : len;
-  std::vector<int> table((size_t)slots * len, -1);
-  for (int s2 = 0; s2 < slots; ++s2)
-    for (size_t i = 0; i < lists[s2].size(); ++i) table[(size_t)s2 * len + i] = lists[s2][i];
-  SchedVal v{nullptr, (int)len};
+  std::vector<int> table;
+  const int len = tapgemm_build_schedule(pm_tiles, a.n_tiles, a.batch, a.n_fastest, a.n_total, a.bn_tile, ctas, slots,
+                                         key.iters, &table, nullptr, nullptr);
+  SchedVal v{nullptr, len};
   if (cudaMalloc(&v.dev_ptr, table.size() * sizeof(int)) != cudaSuccess ||
       cudaMemcpy(v.dev_ptr, table.data(), table.size() * sizeof(int), cudaMemcpyHostToDevice) != cudaSuccess) {
     cudaGetLastError();

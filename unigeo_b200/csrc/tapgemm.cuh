@@ -17,6 +17,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <vector>
 
 namespace ug {
 
@@ -94,6 +95,10 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 // needs tiles_*, n_total, geglu, b_mn_major filled in; returns bn_tile and the CTA count per tile.
 // The B tensor map's box must have bn_tile / ctas rows.
 int tapgemm_pick_tile(const TapGemmArgs& args, int batch, int* ctas);
+// Balanced per-CTA unit lists for launches with ragged N tiles (pure host code): [slots][len] table, -1 = none;
+// returns len.  max_cost / rr_max_cost (nullable): modelled cost of the heaviest slot, here and under round-robin.
+int tapgemm_build_schedule(int pm_tiles, int n_tiles, int batch, int n_fastest, int n_total, int bn_tile, int ctas,
+                           int slots, int iters, std::vector<int>* table, long long* max_cost, long long* rr_max_cost);
 int tapgemm_pick_bn(const TapGemmArgs& args, int batch);
 int tapgemm_num_sms();
 
