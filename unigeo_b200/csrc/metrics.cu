@@ -36,14 +36,17 @@ __device__ __forceinline__ void block_reduce_store(double (&v)[NV], double* __re
   }
 }
 
-// fold [blocks][NV] partials in block order -> out[NV]
+// fold [blocks][NV] partials -> out[NV]: warp w owns column w, lane l adds blocks l, l + 32, ... in order, then a
+// fixed xor tree over the lanes (deterministic; a one-thread loop over 592 blocks cost 37 us of serial L2 round trips)
 template <int NV>
-__global__ void fold_kernel(const double* __restrict__ part, int blocks, double* __restrict__ out) {
-  if (threadIdx.x < NV) {
-    double t = 0.0;
-    for (int b = 0; b < blocks; ++b) t += part[(size_t)b * NV + threadIdx.x];
-    out[threadIdx.x] = t;
-  }
+__global__ void __launch_bounds__(32 * NV) fold_kernel(const double* __restrict__ part, int blocks,
+                                                        double* __restrict__ out) {
+  const int col = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double t = 0.0;
+  for (int b = lane; b < blocks; b += 32) t += part[(size_t)b * NV + col];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+  if (lane == 0) out[col] = t;
 }
 
 // ---- depth, pass 1: normal equations of [p 1] [s t]^T ~ g over valid = (gt > 0) & (gt < max_depth)
@@ -146,20 +149,33 @@ select_hist_kernel(const unsigned int* __restrict__ bits, long long n, int shift
   __syncthreads();
   if (s_h[threadIdx.x]) atomicAdd(&hist[threadIdx.x], (unsigned long long)s_h[threadIdx.x]);
 }
-__global__ void select_step_kernel(unsigned long long* __restrict__ hist, int shift, unsigned int* __restrict__ state) {
-  unsigned long long k = (unsigned long long)state[2] | ((unsigned long long)state[3] << 32);
-  unsigned int bin = 0;
-  for (; bin < 256; ++bin) {
-    const unsigned long long c = hist[bin];
-    if (k < c) break;
-    k -= c;
+// one 256-thread CTA: inclusive scan of the histogram, the bin holding rank k extends the prefix; re-zeroes hist
+__global__ void __launch_bounds__(256)
+select_step_kernel(unsigned long long* __restrict__ hist, int shift, unsigned int* __restrict__ state) {
+  __shared__ unsigned long long s_c[256];
+  const int b = threadIdx.x;
+  const unsigned long long k = (unsigned long long)state[2] | ((unsigned long long)state[3] << 32);
+  const unsigned int prefix = state[0], pmask = state[1];
+  const unsigned long long mine = hist[b];
+  s_c[b] = mine;
+  __syncthreads();
+  for (int o = 1; o < 256; o <<= 1) {                  // Hillis-Steele inclusive scan
+    const unsigned long long add = b >= o ? s_c[b - o] : 0ull;
+    __syncthreads();
+    s_c[b] += add;
+    __syncthreads();
   }
-  if (bin > 255) bin = 255;
-  state[0] |= bin << shift;
-  state[1] |= 255u << shift;
-  state[2] = (unsigned int)(k & 0xffffffffull);
-  state[3] = (unsigned int)(k >> 32);
-  for (int i = 0; i < 256; ++i) hist[i] = 0ull;
+  const unsigned long long incl = s_c[b], excl = incl - mine;
+  hist[b] = 0ull;
+  // exactly one bin satisfies excl <= k < incl when k < total; bin 255 takes the (impossible) overflow
+  const bool hit = (k >= excl && k < incl) || (b == 255 && k >= incl);
+  if (hit) {
+    const unsigned long long rem = k >= incl ? 0ull : k - excl;
+    state[0] = prefix | ((unsigned int)b << shift);
+    state[1] = pmask | (255u << shift);
+    state[2] = (unsigned int)(rem & 0xffffffffull);
+    state[3] = (unsigned int)(rem >> 32);
+  }
 }
 
 }  // namespace
@@ -178,11 +194,11 @@ int launch_depth_metrics(const float* pred, const float* gt, const unsigned char
   float* stv = reinterpret_cast<float*>(sums + 16);
   const int blocks = (int)((n + kThreads - 1) / kThreads < kBlocks ? (n + kThreads - 1) / kThreads : kBlocks);
   depth_fit_kernel<<<blocks, kThreads, 0, st>>>(pred, gt, n, max_depth, part);
-  fold_kernel<5><<<1, 32, 0, st>>>(part, blocks, sums);
+  fold_kernel<5><<<1, 32 * 5, 0, st>>>(part, blocks, sums);
   depth_solve_kernel<<<1, 1, 0, st>>>(sums, stv);
   depth_err_kernel<<<blocks, kThreads, 0, st>>>(pred, gt, mask, n, max_depth, stv, part, err_map, pred_aligned,
                                                 gt_valid);
-  fold_kernel<9><<<1, 32, 0, st>>>(part, blocks, sums);
+  fold_kernel<9><<<1, 32 * 9, 0, st>>>(part, blocks, sums);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
   double h[9];
@@ -219,7 +235,7 @@ int launch_normal_metrics(const float* pred, const float* gt, const unsigned cha
   unsigned int* bits = state + 16;
   const int blocks = (int)((n + kThreads - 1) / kThreads < kBlocks ? (n + kThreads - 1) / kThreads : kBlocks);
   normal_err_kernel<<<blocks, kThreads, 0, st>>>(pred, gt, mask, n, bits, part, err_deg);
-  fold_kernel<8><<<1, 32, 0, st>>>(part, blocks, sums);
+  fold_kernel<8><<<1, 32 * 8, 0, st>>>(part, blocks, sums);
   double h[8];
   cudaError_t e = cudaMemcpyAsync(h, sums, sizeof(h), cudaMemcpyDeviceToHost, st);
   if (e != cudaSuccess) return (int)e;
@@ -239,7 +255,7 @@ int launch_normal_metrics(const float* pred, const float* gt, const unsigned cha
   if (e != cudaSuccess) return (int)e;
   for (int shift = 24; shift >= 0; shift -= 8) {
     select_hist_kernel<<<blocks, kThreads, 0, st>>>(bits, n, shift, state, hist);
-    select_step_kernel<<<1, 1, 0, st>>>(hist, shift, state);
+    select_step_kernel<<<1, 256, 0, st>>>(hist, shift, state);
   }
   unsigned int med_bits = 0;
   e = cudaMemcpyAsync(&med_bits, state, 4, cudaMemcpyDeviceToHost, st);
