@@ -228,6 +228,33 @@ def test_abi_fails_cleanly_without_gpu():
         Engine(tiny_config())
 
 
+def test_device_metrics_mirror_has_no_cpu_path():
+    """unigeo_b200.metrics keeps the reference's names / keys and raises without a GPU instead of scoring on the CPU;
+    null arguments are rejected at the ABI without touching a device."""
+    import ctypes as C
+    import inspect
+    from unigeo_b200 import _lib, metrics as DM
+    k = np.load(os.path.join(ROOT, "tests", "golden", "metrics_kat.npz"))
+    assert list(DM.DEPTH_KEYS) == [str(x) for x in k["depth_keys"]]          # recorded from the unmodified reference
+    assert list(DM.NORMAL_KEYS) == [str(x) for x in k["normal_keys"]]
+    dp = list(inspect.signature(DM.depth_evaluation).parameters)
+    assert dp[:5] == ["predicted_depth_original", "ground_truth_depth_original", "max_depth", "custom_mask",
+                      "align_with_lstsq"]                                      # metrics/eval_depth.py:6-23 order
+    assert list(inspect.signature(DM.normal_evaluation).parameters)[:3] == [
+        "predicted_normal_original", "ground_truth_normal_original", "custom_mask"]
+    with pytest.raises(NotImplementedError):
+        DM.depth_evaluation(k["pred"], k["gt"], custom_mask=k["mask"], align_with_lad=True)
+    lib = _lib.load()
+    out = (C.c_double * 11)()
+    assert lib.ug_depth_metrics(None, None, None, None, 10, 80.0, out, None, None, None, None) != 0
+    assert b"null" in lib.ug_last_error()
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            DM.depth_evaluation(k["pred"], k["gt"], custom_mask=k["mask"], align_with_lstsq=True)
+        with pytest.raises(RuntimeError):
+            DM.normal_evaluation(k["pn"], k["gn"], custom_mask=k["mask"])
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "unigeo_b200")
     for dirpath, _, files in os.walk(pkg):
