@@ -41,10 +41,21 @@ def _t(x):
     return torch.from_numpy(x) if isinstance(x, np.ndarray) else x
 
 
+# options of the reference signature (metrics/eval_depth.py:6-23) that select another alignment / clipping mode
+_OTHER_MODES = ("post_clip_min", "post_clip_max", "pre_clip_min", "pre_clip_max", "align_with_lad", "align_with_lad2",
+                "metric_scale", "align_with_scale", "disp_input")
+_IGNORED = ("lr", "max_iters", "use_gpu")          # only read by the modes above / a device hint
+
+
 def depth_evaluation(predicted_depth_original, ground_truth_depth_original, max_depth=80, custom_mask=None,
-                     align_with_lstsq=False, engine: Optional[Engine] = None, with_maps: bool = True, **unsupported):
-    if not align_with_lstsq or any(v for v in unsupported.values()):
-        raise NotImplementedError("only align_with_lstsq=True (the mode eval.py:49 uses) runs on the device")
+                     align_with_lstsq=False, engine: Optional[Engine] = None, with_maps: bool = True, **options):
+    unknown = [k for k in options if k not in _OTHER_MODES + _IGNORED]
+    if unknown:
+        raise TypeError(f"depth_evaluation() got unexpected keyword arguments {unknown}")
+    other = [k for k in _OTHER_MODES if options.get(k) not in (None, False)]
+    if not align_with_lstsq or other:
+        raise NotImplementedError("only align_with_lstsq=True without clipping (the mode eval.py:49 uses) runs on the "
+                                  f"device; requested: {other or 'median scaling'}")
     if max_depth is None:
         max_depth = float("inf")
     eng = engine or _default_engine()
