@@ -9,7 +9,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libunigeo_b200.so")
+# UG_LIB selects a differently-compiled copy of the library (development tooling, e.g. the trace build of
+# tools/trace_tapgemm.py); it must exist -- nothing is built or substituted on its behalf
+LIB_PATH = os.environ.get("UG_LIB") or os.path.join(HERE, "libunigeo_b200.so")
 
 UG_F16, UG_BF16, UG_F32 = 0, 1, 2
 
@@ -125,6 +127,8 @@ def load() -> C.CDLL:
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        if os.environ.get("UG_LIB"):
+            raise FileNotFoundError(f"UG_LIB={LIB_PATH} does not exist")
         from .build import build  # needs nvcc; raises with the compiler output otherwise
         build()
     lib = C.CDLL(LIB_PATH)

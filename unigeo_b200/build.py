@@ -40,6 +40,32 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
+def build_variant(tag: str, defines) -> str:
+    """A differently-compiled copy of the whole library (e.g. tag "trace", defines ["UG_TAPGEMM_TRACE"]) as
+    ``libunigeo_b200_<tag>.so`` next to the product library; objects under ``csrc/build/<tag>/``.  Development
+    tooling (tools/trace_tapgemm.py): the product build and its stamp are not touched."""
+    obj_dir = os.path.join(OBJ, tag)
+    os.makedirs(obj_dir, exist_ok=True)
+    lib = os.path.join(HERE, f"libunigeo_b200_{tag}.so")
+    nv = _nvcc()
+    flags = [*NVCC_FLAGS, *[f"-D{d}" for d in defines]]
+
+    def compile_one(src):
+        obj = os.path.join(obj_dir, src.replace(".cu", ".o"))
+        r = subprocess.run([nv, *flags, "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+        return obj
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    r = subprocess.run([nv, "-shared", "-o", lib, *objs, "-gencode", "arch=compute_100a,code=sm_100a"],
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]

@@ -459,6 +459,15 @@ int ug_depth_postprocess(ug_ctx* u, const float* frames, const float* intrinsics
   });
 }
 
+#ifdef UG_TAPGEMM_TRACE
+// trace builds only (tools/trace_tapgemm.py; not part of include/unigeo_b200.h): device buffer the following tapgemm
+// launches stamp -- [grid units][4 roles][16 tiles][4] uint64 -- or NULL to stop
+extern "C" int ug_debug_tapgemm_trace(unsigned long long* dev_buf) {
+  tapgemm_set_trace(dev_buf);
+  return 0;
+}
+#endif
+
 int ug_tile_schedule(int m_units, int n_total, int bn_tile, int batch, int n_fastest, int ctas, int slots, int k_iters,
                      int* units_out, int cap, long long* max_cost, long long* rr_max_cost) {
   int ret = 0;

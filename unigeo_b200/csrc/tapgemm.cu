@@ -19,6 +19,19 @@
 
 namespace ug {
 
+// Per-role time stamps of the persistent kernel (clock64 of the CTA's SM), compiled in only with -DUG_TAPGEMM_TRACE
+// (tools/trace_tapgemm.py builds that variant into its own .so): role 0 producer, 1 UMMA issuer, 2 / 3 epilogue column
+// groups; rank 0 of a pair only, first kTraceTiles units of every CTA.  Expands to nothing in the product build.
+#ifdef UG_TAPGEMM_TRACE
+#define UG_TRACE(role, tile, slot)                                                                             \
+  do {                                                                                                         \
+    if (a.trace != nullptr && rank == 0 && (tile) < kTraceTiles)                                               \
+      a.trace[(((size_t)unit0 * 4 + (role)) * kTraceTiles + (tile)) * 4 + (slot)] = (unsigned long long)clock64(); \
+  } while (0)
+#else
+#define UG_TRACE(role, tile, slot) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int BM = 128;
@@ -359,6 +372,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                  (uint32_t)(a.b_mn_major ? BK : BN / CTAS) * (BK * 2)) * CTAS;
       int it_g = 0;   // ring position, continuous across tiles
       for (int ui = 0, t; (t = unit_at(ui)) >= 0; ++ui) {
+        UG_TRACE(0, ui, 0);
         int m_lin, n_tile_p, z;
         decode(t, m_lin, n_tile_p, z);
         int m_tile = m_lin * CTAS + rank;
@@ -382,6 +396,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const int tap = it / a.kchunks;
           const int kc = it - tap * a.kchunks;
           mbar_wait(&empty_bar[s], ph ^ 1u);
+          if (it == 0) UG_TRACE(0, ui, 1);
+          if (it == num_iters - 1) UG_TRACE(0, ui, 2);
           uint8_t* sa = smem + s * kStB;
           uint8_t* sb = sa + kATileBytes;
           if constexpr (CTAS == 2) {
@@ -414,14 +430,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t idesc = make_idesc_f16(BM * CTAS, n_cur(n0), a.fmt, a.b_mn_major);
         const int buf = tl & 1;
         const uint32_t use = (uint32_t)(tl >> 1);
+        if (lane == 0) UG_TRACE(1, tl, 0);
         mbar_wait(&tmem_empty_bar[buf], (use & 1u) ^ 1u);     // epilogue(s) drained this accumulator
         tc_fence_after();
+        if (lane == 0) UG_TRACE(1, tl, 1);
         const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
         for (int it = 0; it < num_iters; ++it, ++it_g) {
           const int s = it_g % kSt;
           const uint32_t ph = (uint32_t)(it_g / kSt) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (lane == 0 && it == 0) UG_TRACE(1, tl, 2);
+          if (lane == 0 && it == num_iters - 1) UG_TRACE(1, tl, 3);
           if (elect_one()) {
             const uint32_t sa = smem_u32(smem + s * kStB);
             const uint64_t da = make_desc_kmajor_sw128(sa);
@@ -456,9 +476,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int xi = r % a.bw;
     const int yi = (r / a.bw) % a.bh;
     const int ni = r / (a.bw * a.bh);
+    const bool tracer = (q == 0) && lane == 0;            // (debug builds) one stamping thread per column group
+    int trace_tl = 0;
+    (void)tracer; (void)trace_tl;
     auto release = [&](int buf) {           // this warp no longer needs accumulator `buf`
       tc_fence_before();
       __syncwarp();
+      if (tracer) UG_TRACE(2 + hsel, trace_tl, 2);
       if (lane == 0) {
         if constexpr (CTAS == 2) mbar_arrive_leader(&tmem_empty_bar[buf]);
         else mbar_arrive(&tmem_empty_bar[buf]);
@@ -470,6 +494,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t ring_it = 0;                   // chunk ring position of this column group (res_tma path)
     int tl = 0;
     for (int ui = 0, t; (t = unit_at(ui)) >= 0; ++ui, ++tl) {
+      trace_tl = tl;
+      if (tracer) UG_TRACE(2 + hsel, tl, 0);
       int m_lin, n_tile, z;
       decode(t, m_lin, n_tile, z);
       int m_tile = m_lin * CTAS + rank;
@@ -505,6 +531,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const bool prefetching = a.res_tma || (a.tma_store && !a.geglu && (a.res != nullptr || a.blend != nullptr));
       if (!prefetching) {                   // (the prefetching path waits after issuing its first loads)
         mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
+        if (tracer) UG_TRACE(2 + hsel, tl, 1);
         tc_fence_after();
       }
 
@@ -536,6 +563,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (nch > 1) issue_load(1);
         }
         mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
+        if (tracer) UG_TRACE(2 + hsel, tl, 1);
         tc_fence_after();
         bool released = false;
 #pragma unroll 1
@@ -686,6 +714,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         prefetch(0, hsel * 64);                                  // overlaps the wait for the accumulator
         mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
+        if (tracer) UG_TRACE(2 + hsel, tl, 1);
         tc_fence_after();
         bool released = false;
 #pragma unroll 1
@@ -835,6 +864,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         if (!released) release(buf);         // this warp had no chunk in this tile (narrow tile)
       }
+      if (tracer) UG_TRACE(2 + hsel, tl, 3);
     }
     if (issuer && a.tma_store) bulk_wait_group<0>();            // all tile stores have landed
   }
@@ -1036,6 +1066,11 @@ bool tapgemm_schedule(const TapGemmArgs& a, int ctas, int pm_tiles, int slots, c
 }
 }  // namespace
 
+#ifdef UG_TAPGEMM_TRACE
+static unsigned long long* g_trace_buf = nullptr;
+void tapgemm_set_trace(unsigned long long* dev_buf) { g_trace_buf = dev_buf; }
+#endif
+
 int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC,
                    const TapGemmArgs& args_in, int batch, cudaStream_t stream, const CUtensorMap* tmR) {
   static bool configured = false;
@@ -1047,6 +1082,9 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     configured = true;
   }
   TapGemmArgs args = args_in;
+#ifdef UG_TAPGEMM_TRACE
+  args.trace = g_trace_buf;
+#endif
   const int ctas = args.ctas == 2 ? 2 : 1;
   if (args.bn_tile <= 0 || args.bn_tile > 256 || (args.bn_tile & (16 * ctas - 1))) return (int)cudaErrorInvalidValue;
   if (ctas == 2 && args.b_mn_major) return (int)cudaErrorInvalidValue;

@@ -51,6 +51,9 @@ struct TapGemmArgs {
                            // tmC / tmR are 32-column SWIZZLE_64B maps of the output / residual tensor
   int n_tiles, batch;      // filled by launch_tapgemm
   int n_fastest;           // tile order (filled by launch_tapgemm): N tiles of one M tile run concurrently
+#ifdef UG_TAPGEMM_TRACE
+  unsigned long long* trace;   // debug builds (tools/trace_tapgemm.py): [grid units][4 roles][kTraceTiles][4] clock64 stamps
+#endif
   const int* sched;        // filled by launch_tapgemm: [grid units][sched_len] unit indices (-1 = none) when the host
   int sched_len;           // balanced ragged-width tiles over the CTAs (list scheduling); nullptr = round-robin
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
@@ -72,6 +75,12 @@ struct TapGemmArgs {
   float alpha;
   float scale;             // value = acc * scale + ...
 };
+
+#ifdef UG_TAPGEMM_TRACE
+constexpr int kTraceTiles = 16;
+// the buffer every following launch stamps (nullptr = off); set through ug_debug_tapgemm_trace (trace builds only)
+void tapgemm_set_trace(unsigned long long* dev_buf);
+#endif
 
 // Host-side helpers -----------------------------------------------------------------
 struct TmapDesc {
