@@ -53,6 +53,26 @@ def depth_evaluation(pred, gt, custom_mask=None, max_depth=80):
     return res
 
 
+def depth_maps(pred, gt, max_depth=80):
+    """The three full-size maps depth_evaluation returns beside the dict (metrics/eval_depth.py:166-213,
+    align_with_lstsq branch): |s p + t - gt| / gt over valid pixels (0 elsewhere), s p + t everywhere, gt over valid
+    pixels (0 elsewhere); [Nf,H,W] inputs come back flattened to [Nf*H, W] like the reference's (:47-52)."""
+    pred = torch.as_tensor(pred)
+    gt = torch.as_tensor(gt)
+    if pred.dim() == 3:
+        w = pred.shape[-1]
+        pred, gt = pred.reshape(-1, w), gt.reshape(-1, w)
+    mask = (gt > 0) & (gt < max_depth)
+    p, g = pred[mask], gt[mask]
+    A = np.hstack([p.numpy().reshape(-1, 1), np.ones((p.numel(), 1), dtype=p.numpy().dtype)])   # alignment.py:153-160
+    sol = np.linalg.lstsq(A, g.numpy().reshape(-1, 1), rcond=None)[0]
+    s, t = torch.tensor(sol[0]), torch.tensor(sol[1])
+    aligned = pred * s + t                                # :175
+    err = torch.abs(aligned - gt) / gt                    # :178-181
+    zeros = torch.zeros_like(gt)
+    return torch.where(mask, err, zeros), aligned, torch.where(mask, gt, zeros)
+
+
 def normal_evaluation(pred, gt, custom_mask=None):
     """eval.py:54 call shape: [Nf,H,W,3] tensors + bool mask [Nf,H,W]."""
     pred = torch.as_tensor(pred).permute(0, 3, 1, 2)      # eval_normal.py:63-64

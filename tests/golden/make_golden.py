@@ -3,6 +3,8 @@
 
   metrics_kat.npz      metrics/eval_depth.py::depth_evaluation(align_with_lstsq=True, custom_mask)
                        metrics/eval_normal.py::normal_evaluation           (as eval.py:49,54 call them)
+  metrics_kat_edge.npz the same two functions on edge cases (negative aligned predictions, sparse masks with even / odd
+                       counts, custom_mask=None) + the three full-size maps depth_evaluation returns
   depthcrafter_post.npz  model/depthcrafter.py::DepthCrafter.forward with the upstream pipeline replaced
                        by a stub returning fixed frames -> pins prepare_input (:39-45), the
                        disparity->depth lines (:92-97) and prepare_output (:48-69, incl.
@@ -46,6 +48,49 @@ def metrics_kat():
                         depth_keys=np.array(list(res)), depth_vals=np.array([float(v) for v in res.values()]),
                         normal_keys=np.array(list(nres)), normal_vals=np.array([float(v) for v in nres.values()]))
     print("metrics_kat", res, nres)
+
+
+def metrics_kat_edge():
+    """Edge cases of the two metric functions, recorded from the unmodified reference: predictions that turn negative
+    after alignment (the clamp(1e-5) / log branch, eval_depth.py:152), a sparse mask with an even and an odd number of
+    survivors (torch.median's lower-middle rule), custom_mask=None, gt beyond max_depth / <= 0, and the three full-size
+    maps the reference returns beside the dict (eval_depth.py:166-213) for one case."""
+    ed, en = refload.metrics_eval_depth(), refload.metrics_eval_normal()
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    cases = []
+    for name, (Nf, H, W), noise, keep, use_mask in [("neg", (2, 24, 40), 2.5, 0.8, True), ("sparse_even", (3, 17, 23), 0.3, 0.02, True),
+                                                   ("sparse_odd", (3, 17, 23), 0.3, 0.021, True), ("nomask", (1, 33, 31), 0.5, 1.0, False)]:
+        gt = torch.rand(Nf, H, W, generator=g) * 11 - 0.7            # some <= 0
+        gt[0, :2, :3] = 120.0                                         # beyond max_depth
+        pred = 0.21 * gt.clamp(min=0.05) + 0.4 + noise * torch.randn(Nf, H, W, generator=g)
+        if name == "neg":                                             # outliers far below the trend: s p + t < 0 there
+            pred = 0.21 * gt.clamp(min=0.05) + 0.4 + 0.05 * torch.randn(Nf, H, W, generator=g)
+            idx = torch.randperm(pred.numel(), generator=g)[:60]
+            pred.view(-1)[idx] = -6.0
+        mask = torch.rand(Nf, H, W, generator=g) < keep
+        if name == "sparse_odd" and int(mask.sum()) % 2 == 0:
+            mask.view(-1)[int(torch.nonzero(~mask.view(-1))[0])] = True
+        if name == "sparse_even" and int(mask.sum()) % 2 == 1:
+            mask.view(-1)[int(torch.nonzero(~mask.view(-1))[0])] = True
+        pn = torch.nn.functional.normalize(torch.randn(Nf, H, W, 3, generator=g), dim=-1)
+        gn = torch.nn.functional.normalize(pn + 0.8 * torch.randn(Nf, H, W, 3, generator=g), dim=-1)
+        r = ed.depth_evaluation(pred.clone(), gt.clone(), custom_mask=mask.clone() if use_mask else None,
+                                align_with_lstsq=True)
+        nm = mask if use_mask else torch.ones_like(mask)
+        nres = en.normal_evaluation(pn.clone(), gn.clone(), custom_mask=nm.clone())
+        out.update({f"{name}_pred": pred.numpy(), f"{name}_gt": gt.numpy(), f"{name}_mask": mask.numpy(),
+                    f"{name}_use_mask": np.array(use_mask), f"{name}_pn": pn.numpy(), f"{name}_gn": gn.numpy(),
+                    f"{name}_depth_vals": np.array([float(v) for v in r[0].values()]),
+                    f"{name}_normal_vals": np.array([float(v) for v in nres.values()])})
+        if name == "neg":
+            out.update({"neg_err_map": r[1].numpy(), "neg_pred_aligned": r[2].numpy(), "neg_gt_valid": r[3].numpy()})
+        cases.append(name)
+        print("metrics_kat_edge", name, int(nm.sum()), r[0], nres)
+    out["cases"] = np.array(cases)
+    out["depth_keys"] = np.array(list(r[0]))
+    out["normal_keys"] = np.array(list(nres))
+    np.savez_compressed(os.path.join(OUT, "metrics_kat_edge.npz"), **out)
 
 
 def depthcrafter_post():
@@ -120,6 +165,7 @@ if __name__ == "__main__":
     if not refload.available():
         raise SystemExit("needs /root/reference (dev container)")
     metrics_kat()
+    metrics_kat_edge()
     depthcrafter_post()
     stablenormal_post()
     oracle_tiny()
