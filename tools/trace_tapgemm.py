@@ -8,7 +8,7 @@ the given shape and prints, averaged over CTAs and steady-state tiles (tile inde
   epilogue g0|g1  wait for the accumulator / accumulator ready -> TMEM drained / drained -> tile's stores issued
 
     python tools/trace_tapgemm.py build                     # here (no GPU needed): compile the trace variant
-    python tools/trace_tapgemm.py linear M K N [res]        # on the GPU box
+    python tools/trace_tapgemm.py linear M K N [res|geglu]  # on the GPU box
     python tools/trace_tapgemm.py conv T H W C Cout
 Development aid; nothing in the product or the tests loads the trace library."""
 import os
@@ -50,7 +50,11 @@ def main():
         x, W = rnd(M, K), rnd(N, K, sc=1 / math.sqrt(K))
         res = rnd(M, N) if "res" in sys.argv else None
         b = torch.zeros(N, device=dev)
-        run = lambda: ops.linear(x, W, bias=b, res=res)
+        if "geglu" in sys.argv:                     # N = 2 x hidden, rows interleaved like ug_ctx_finalize does
+            W, b = ops.geglu_interleave(W, b)
+            run = lambda: ops.linear(x, W, bias=b, geglu=True)
+        else:
+            run = lambda: ops.linear(x, W, bias=b, res=res)
     elif kind == "conv":
         T, H, Wd, Cc, Co = dims[:5]
         x, W = rnd(T, H, Wd, Cc), rnd(9, Co, Cc, sc=1 / math.sqrt(9 * Cc))
