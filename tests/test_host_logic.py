@@ -192,6 +192,34 @@ def test_sharding_assignment_and_stitch_single_process():
     assert torch.allclose(video, scene, atol=1e-4)
 
 
+def test_metric_table_matches_reference_export(tmp_path):
+    """sharding.export_metric_csv / average_row against the reference's MetricsManager (metrics/save_utils.py) when it
+    is mounted, and against the format it is known to write otherwise: NaN-skipping 'Average' line, %.5f."""
+    from unigeo_b200 import sharding as sh
+    names = ["Abs Rel", "delta < 1.25", "normal mean"]
+    rows = torch.tensor([[0.123456789, 0.9, 30.5], [0.2, float("nan"), 12.25], [0.05, 0.5, float("nan")]],
+                        dtype=torch.float64)
+    seqs = ["scene_a", "scene_b", "scene_c"]
+    avg = sh.average_row(rows)
+    assert abs(avg[0].item() - (0.123456789 + 0.2 + 0.05) / 3) < 1e-12 and abs(avg[1].item() - 0.7) < 1e-12
+    assert abs(avg[2].item() - 21.375) < 1e-12
+    mine = tmp_path / "mine" / "metrics.csv"
+    sh.export_metric_csv(str(mine), seqs, rows, names)
+    text = mine.read_text()
+    assert text.splitlines()[0] == ",Abs Rel,delta < 1.25,normal mean"
+    assert text.splitlines()[1] == "scene_a,0.12346,0.90000,30.50000"
+    assert text.splitlines()[2] == "scene_b,0.20000,,12.25000"
+    assert text.splitlines()[4] == "Average,0.12449,0.70000,21.37500"
+    from harness import refload
+    if refload.available():
+        mm = refload._load("metrics", "save_utils").MetricsManager(metric_names=names)
+        for s, r in zip(seqs, rows.tolist()):
+            mm.update_metrics({"seq_name": s, **dict(zip(names, r))})
+        ref = tmp_path / "ref" / "metrics.csv"
+        mm.export_to_csv(str(ref))
+        assert ref.read_text() == text
+
+
 def test_fit_scale_shift_exact():
     from unigeo_b200.sharding import fit_scale_shift
     x = torch.rand(100, dtype=torch.float64)

@@ -32,6 +32,7 @@ ap.add_argument("--height", type=int, default=384)
 ap.add_argument("--width", type=int, default=512)
 ap.add_argument("--steps", type=int, default=5)           # the reference hard-codes 5 (model/depthcrafter.py:86)
 ap.add_argument("--config", default="full")
+ap.add_argument("--csv", default=None)                    # the per-clip metric table + 'Average' line (save_utils format)
 a = ap.parse_args()
 
 rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -96,6 +97,9 @@ table = sh.gather_metric_rows(mine, torch.tensor(local_rows, dtype=torch.float64
 torch.cuda.synchronize()
 t_metrics = time.perf_counter() - t1
 avg = sh.average_row(table)
+if rank == 0 and a.csv:
+    sh.export_metric_csv(a.csv, [f"synthetic_scene_clip{k}" for k in range(a.clips)], table,
+                         list(DM.DEPTH_KEYS + DM.NORMAL_KEYS))
 rows = [(k, float(table[k, 0])) for k in range(a.clips)]
 t = torch.tensor([t_clips, t_total, stitch_ms, t_metrics], device=plug.device, dtype=torch.float64)
 if world > 1:

@@ -112,5 +112,22 @@ def gather_metric_rows(local_ids: Sequence[int], local_rows: torch.Tensor, num_c
 
 
 def average_row(rows: torch.Tensor) -> torch.Tensor:
-    """The 'Average' line metrics/save_utils.py:64-90 appends: column means over the clips."""
-    return rows.mean(dim=0)
+    """The 'Average' line metrics/save_utils.py:51-63 computes: column means over the clips, NaNs skipped
+    (``mean(skipna=True)``; a column of NaNs only stays NaN)."""
+    return torch.nanmean(rows, dim=0)
+
+
+def export_metric_csv(path: str, seq_names: Sequence[str], rows: torch.Tensor, metric_names: Sequence[str]) -> None:
+    """The table metrics/save_utils.py:65-90 writes (``MetricsManager.export_to_csv``): one line per sequence, an
+    'Average' line, floats as %.5f, NaN as an empty field, header ',<metric>,...'.  Plain text, no pandas."""
+    import os
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    body = torch.cat([rows.to(torch.float64).cpu(), average_row(rows.to(torch.float64).cpu())[None]], 0)
+
+    def fmt(v: float) -> str:
+        return "" if v != v else "%.5f" % v
+
+    with open(path, "w") as f:
+        f.write("," + ",".join(metric_names) + "\n")
+        for name, row in zip(list(seq_names) + ["Average"], body.tolist()):
+            f.write(str(name) + "," + ",".join(fmt(v) for v in row) + "\n")
