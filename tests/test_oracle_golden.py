@@ -134,3 +134,18 @@ def test_reference_metrics_match_when_mounted():
     ref = refload.metrics_eval_normal().normal_evaluation(a.clone(), b.clone(), custom_mask=mask)
     mine = normal_evaluation(a, b, mask)
     assert all(float(ref[k]) == float(mine[k]) for k in ref)
+
+
+def test_harness_gt_label_matches_reference_when_mounted():
+    """harness.synthetic.gt_label (what the GPU parity tests and the scene tool score against) equals the reference's
+    utils/io_utils.py::prepare_gt_label on the three keys eval.py:49-54 reads -- run against the unmodified file."""
+    from harness import refload
+    from harness.synthetic import gt_label, make_clip
+    if not refload.available():
+        import pytest
+        pytest.skip("needs /root/reference (dev container)")
+    data = make_clip(3, 64, 96, seed=5)
+    ref = refload.utils_io().prepare_gt_label(data)
+    mine = gt_label(data)
+    for key in ("gt_depths", "gt_normals", "gt_masks"):
+        assert mine[key].dtype == ref[key].dtype and torch.equal(mine[key], ref[key]), key
