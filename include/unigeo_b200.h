@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define UG_VERSION 101
+#define UG_VERSION 102
 
 typedef struct ug_ctx ug_ctx;
 
@@ -55,7 +55,7 @@ typedef struct ug_model_cfg {
   int32_t addition_time_embed_dim;
   int32_t num_added_ids;
   int32_t norm_groups;
-  float eps_cross_attn_block, eps_plain_block, eps_transformer_norm, eps_out_norm, ln_eps;
+  float eps_cross_attn_block, eps_plain_block, eps_plain_up_block, eps_transformer_norm, eps_out_norm, ln_eps;
   /* temporal-decoder VAE */
   int32_t vae_in_channels, vae_latent_channels;
   int32_t vae_num_blocks;
@@ -101,6 +101,11 @@ int ug_ctx_destroy(ug_ctx* ctx);
  * original diffusers shape.  Copied and re-laid-out into library storage. */
 int ug_ctx_load_weight(ug_ctx* ctx, const char* key, const void* dev_ptr, int dtype, const int64_t* shape,
                        int rank, void* stream);
+/* Storage / compute type of the VAE ENCODER alone (UG_F16, UG_BF16, or -1 = the context's dtype; call before the
+ * "vae.encoder." / "vae.quant_conv." (and "vae2d." ditto) weights are loaded).  [UPSTREAM] encode_vae_video upcasts the VAE to fp32
+ * (force_upcast) because SVD's encoder activations leave the fp16 range; UG_BF16 keeps the
+ * fp32 exponent range on the 16-bit tensor-core path while the rest of an fp16 context stays fp16. */
+int ug_ctx_set_vae_encode_dtype(ug_ctx* ctx, int dtype);
 /* Build fused matrices (QKV, GEGLU-interleaved FF, stacked time-embedding projections). */
 int ug_ctx_finalize(ug_ctx* ctx, void* stream);
 /* Size the workspace for clips of T frames with h x w latents (H = 8h, W = 8w) and precompute
@@ -181,6 +186,23 @@ int ug_vae_decode_frames(ug_ctx* ctx, const float* lat, int T, int h, int w, int
  * intrinsics fp32 [T][3][3] (device) -> depths fp32 [T][H][W], normals fp32 [T][H][W][3]. */
 int ug_depth_postprocess(ug_ctx* ctx, const float* frames, const float* intrinsics, int T, int H, int W,
                          float* depths, float* normals, void* stream);
+
+/* ---- scene stitch (BASELINE cfg4): the one exchange step of the clip-sharded path.  Clips of a scene
+ * (dataset/scannetpp/scannetpp.py:42-48, clip_overlap shared frames) are min-max normalised one by one
+ * (model/depthcrafter.py:95), so consecutive clips disagree by a 2-parameter map on their shared frames.  After ONE
+ * all-gather of every clip's first / last `overlap` frames (NCCL; unigeo_b200/sharding.py) every rank calls
+ * ug_stitch_fit: overlap_frames fp32 [world][per_rank][2 (head, tail)][n] as gathered (clip k on rank k % world, slot
+ * k / world), n = overlap * H * W; space 1 fits on x = 1 / depth - offset (the normalised disparity of
+ * model/depthcrafter.py:96, where the map IS affine), 0 on the values as given; chain_dev (device) receives
+ * [num_clips][2] doubles (S, T) mapping clip k into clip 0's frame (fp64 fixed-order sums, a constant overlap keeps
+ * the scale and matches the means).  ug_stitch_apply maps one clip (elems = T * H * W values) and ramps its first
+ * `overlap` frames from prev_tail (the previous clip's last frames, NULL for clip 0) with linspace(0, 1, overlap).
+ * Not in the reference (it never stitches: window_size = len(frames), model/depthcrafter.py:87): an ADDITIONAL output. */
+int ug_stitch_fit(ug_ctx* ctx, const float* overlap_frames, int world, int per_rank, int num_clips, long long n,
+                  int space, float offset, double* chain_dev, void* stream);
+int ug_stitch_apply(ug_ctx* ctx, const float* clip, long long elems, const float* prev_tail, long long n_overlap,
+                    long long frame_elems, int overlap, const double* chain_dev, int k, int space, float offset,
+                    float* out, void* stream);
 
 /* ---- consumer side of the plugin boundary: the two metric functions eval.py applies to the outputs, on the device
  * (SURVEY.md 8(f)-3), so that depths / normals can be scored where they were produced.

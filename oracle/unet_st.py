@@ -208,7 +208,7 @@ def unet_forward(sd: SD, cfg, sample: torch.Tensor, timestep: float, enc: torch.
     rev_heads = tuple(reversed(cfg.num_attention_heads))
     for i in range(nb):
         has_attn = i > 0
-        eps = cfg.eps_cross_attn_block if has_attn else cfg.eps_plain_block
+        eps = cfg.eps_cross_attn_block if has_attn else cfg.eps_plain_up_block
         for j in range(cfg.layers_per_block + 1):
             x = torch.cat([x, skips.pop()], dim=1)
             x = st_res_block(sd, f"up_blocks.{i}.resnets.{j}", x, emb, t, g, eps)

@@ -112,11 +112,31 @@ def test_stablenormal_needs_gpu_or_predictor():
         pytest.skip("GPU present")
     from unigeo_b200.model import StableNormal
     with pytest.raises(RuntimeError):
-        StableNormal(config="tiny")
+        StableNormal(config="tiny", weights="synthetic")
     s = StableNormal(predictor=lambda im: im)          # hub-style PIL -> PIL predictor still injectable
     out = s.forward({"images": [np.full((3, 4, 4), 200.0, dtype=np.float32)]})
     assert out["pred_normals"].shape == (1, 4, 4, 3) and not out["pred_depths"].any()
     assert abs(out["pred_normals"][0, 0, 0, 0].item() - (56 / 255 * 2 - 1)) < 1e-6     # uint8 wraparound, App. B.10
+
+
+def test_adapters_refuse_missing_checkpoints(tmp_path):
+    """The reference adapters raise when the checkpoint is missing (from_pretrained, model/depthcrafter.py:18-29; hub
+    load, model/stablenormal.py:16); random weights must be asked for explicitly (weights="synthetic"), never a silent
+    fallback that writes meaningless numbers into metrics.csv.  Raised before any device work: runs without a GPU."""
+    from unigeo_b200.model import DepthCrafter, StableNormal
+    with pytest.raises(FileNotFoundError):
+        DepthCrafter(model_dir="x", unet_path=str(tmp_path / "no_such_unet"), pre_train_path=str(tmp_path))
+    with pytest.raises(FileNotFoundError):
+        DepthCrafter(config="tiny")                                   # no paths at all
+    (tmp_path / "unet").mkdir()
+    with pytest.raises(FileNotFoundError):                            # pre_train_path lacks vae/
+        DepthCrafter(unet_path=str(tmp_path / "unet"), pre_train_path=str(tmp_path))
+    with pytest.raises(ValueError):
+        DepthCrafter(config="tiny", weights="random")
+    with pytest.raises(FileNotFoundError):
+        StableNormal(model_dir=str(tmp_path / "no_such_dir"))        # the reference yaml's only key
+    with pytest.raises(FileNotFoundError):
+        StableNormal(config="tiny")
 
 
 def test_2d_param_inventory_matches_published_sizes():
@@ -186,7 +206,7 @@ def test_sharding_assignment_and_stitch_single_process():
     N = starts[-1] + T
     scene = torch.linspace(1, 5, N).view(N, 1, 1) + torch.rand(N, 6, 8) * 0.5
     clips = [scene[s:s + T] * (1.0 + 0.3 * k) - 0.2 * k for k, s in enumerate(starts)]
-    st = sh.stitch_scene(clips, list(range(n)), n, ov)
+    st = sh.stitch_scene(clips, list(range(n)), n, ov, space="depth")   # clips affine IN DEPTH here
     video = sh.assemble_scene(st, starts, N, ov)
     assert video.shape == scene.shape
     assert torch.allclose(video, scene, atol=1e-4)
@@ -236,7 +256,7 @@ def test_abi_header_and_library_agree():
     assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.ug_version() == 101
+    assert lib.ug_version() == 102
 
 
 def test_abi_fails_cleanly_without_gpu():
@@ -331,3 +351,11 @@ def test_tile_schedule_is_a_balanced_partition_without_gpu():
     assert lib.ug_tile_schedule(10, 320, 100, 1, 0, 2, 74, 5, None, 0, None, None) < 0
     tab = (C.c_int * 4)()
     assert lib.ug_tile_schedule(300, 320, 192, 1, 0, 2, 74, 5, tab, 4, None, None) < 0
+
+
+def test_top_level_model_package_is_the_plugin_surface():
+    """configs/config_utils.py:3-6 does getattr(importlib.import_module("model"), model_name) (eval.py:21)."""
+    import importlib
+    m = importlib.import_module("model")
+    from unigeo_b200.model import DepthCrafter, StableNormal
+    assert getattr(m, "DepthCrafter") is DepthCrafter and getattr(m, "StableNormal") is StableNormal

@@ -161,3 +161,35 @@ def test_plugin_scored_on_device(cuda):
     nres = normal_evaluation(dev["pred_normals"], gt["gt_normals"], custom_mask=gt["gt_masks"], engine=plug.engine)
     _check_normal(nres, OM.normal_evaluation(cpu["pred_normals"], gt["gt_normals"], gt["gt_masks"]),
                   int(torch.as_tensor(gt["gt_masks"]).sum()))
+
+
+def test_edge_fixture_recorded_from_the_reference(cuda):
+    """metrics_kat_edge.npz (recorded from the UNMODIFIED reference functions, tests/golden/make_golden.py) against the
+    device kernels: aligned predictions below zero (the clamp(1e-5) / log branch of eval_depth.py:141-164), sparse masks
+    with even and odd survivor counts (torch.median's lower-middle rule), custom_mask=None, and the three full-size maps.
+    Same tolerances as above; valid_pixels and the gt_valid map exact, the error / aligned maps within the fp32 rounding
+    of (s, t) (closed-form fp64 solve here, SVD lstsq in the reference)."""
+    from unigeo_b200.metrics import depth_evaluation, normal_evaluation
+    k = np.load(os.path.join(G, "metrics_kat_edge.npz"))
+    for name in [str(c) for c in k["cases"]]:
+        use_mask = bool(k[f"{name}_use_mask"])
+        mask = k[f"{name}_mask"] if use_mask else None
+        res, err, aligned, gtv = depth_evaluation(k[f"{name}_pred"], k[f"{name}_gt"], custom_mask=mask,
+                                                  align_with_lstsq=True)
+        ref = {str(a): float(b) for a, b in zip(k["depth_keys"], k[f"{name}_depth_vals"])}
+        ref["valid_pixels"] = int(ref["valid_pixels"])
+        _check_depth(res, ref, ref["valid_pixels"])
+        nm = k[f"{name}_mask"] if use_mask else np.ones_like(k[f"{name}_mask"])
+        nres = normal_evaluation(k[f"{name}_pn"], k[f"{name}_gn"], custom_mask=nm)
+        nref = {str(a): float(b) for a, b in zip(k["normal_keys"], k[f"{name}_normal_vals"])}
+        _check_normal(nres, nref, int(nm.sum()))
+        if not use_mask:
+            assert normal_evaluation(k[f"{name}_pn"], k[f"{name}_gn"], custom_mask=None) == nres
+        if name == "neg":
+            assert (k["neg_pred_aligned"] < 0).any()              # the case does exercise the clamp branch
+            assert np.array_equal(gtv.cpu().numpy(), k["neg_gt_valid"])
+            a, e = aligned.cpu().numpy(), err.cpu().numpy()
+            assert a.shape == k["neg_pred_aligned"].shape
+            assert np.abs(a - k["neg_pred_aligned"]).max() <= 2e-5 * max(1.0, np.abs(k["neg_pred_aligned"]).max())
+            assert np.abs(e - k["neg_err_map"]).max() <= 2e-5 * max(1.0, np.abs(k["neg_err_map"]).max())
+            assert (e[k["neg_gt_valid"] == 0] == 0).all()          # invalid pixels carry no error

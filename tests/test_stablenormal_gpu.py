@@ -164,7 +164,7 @@ def test_plugin_end_to_end(bundle):
     from unigeo_b200.weights import (controlnet_param_shapes, synthetic_state_dict, unet2d_param_shapes,
                                      vae2d_param_shapes)
     cfg, sn, _, _, _, d = bundle
-    plug = StableNormal(config="tiny", num_inference_steps=2, weight_seed=0)
+    plug = StableNormal(config="tiny", weights="synthetic", num_inference_steps=2, weight_seed=0)
     data = {"images": [f.transpose(2, 0, 1).astype(np.float32) for f in d["u8"]]}
     noise = torch.randn(Fr, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(9))
     out = plug.forward(data, init_noise=noise)
@@ -232,7 +232,7 @@ def test_plugin_with_yoso_start_and_checkpoint_directory(bundle, tmp_path):
     cfg, sn, _, _, _, d = bundle
     data = {"images": [f.transpose(2, 0, 1).astype(np.float32) for f in d["u8"]]}
     noise = torch.randn(Fr, 4, H // 8, W // 8, generator=torch.Generator().manual_seed(10))
-    plug = StableNormal(config="tiny", num_inference_steps=2, weight_seed=0, yoso=True)
+    plug = StableNormal(config="tiny", weights="synthetic", num_inference_steps=2, weight_seed=0, yoso=True)
     out = plug.forward(data, init_noise=noise)
     sds = {"unet2d": synthetic_state_dict(unet2d_param_shapes(sn.unet2d), 3000),
            "controlnet": synthetic_state_dict(controlnet_param_shapes(sn.unet2d), 3010),
@@ -246,7 +246,7 @@ def test_plugin_with_yoso_start_and_checkpoint_directory(bundle, tmp_path):
                                       yoso_unet_sd=sds["yoso_unet"], yoso_ctrl_sd=sds["yoso_controlnet"])
     ref = StableNormal.postprocess(list(ref_u8))["pred_normals"]
     assert angular_deg(out["pred_normals"], ref).mean().item() <= 1.0
-    plain = StableNormal(config="tiny", num_inference_steps=2, weight_seed=0).forward(data, init_noise=noise)
+    plain = StableNormal(config="tiny", weights="synthetic", num_inference_steps=2, weight_seed=0).forward(data, init_noise=noise)
     assert angular_deg(plain["pred_normals"], out["pred_normals"]).mean().item() > 1.0     # the start latent matters
     root = str(tmp_path)
     for net, sd in sds.items():

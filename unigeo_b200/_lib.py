@@ -34,7 +34,7 @@ class ModelCfg(C.Structure):
         ("addition_time_embed_dim", C.c_int32),
         ("num_added_ids", C.c_int32),
         ("norm_groups", C.c_int32),
-        ("eps_cross_attn_block", C.c_float), ("eps_plain_block", C.c_float),
+        ("eps_cross_attn_block", C.c_float), ("eps_plain_block", C.c_float), ("eps_plain_up_block", C.c_float),
         ("eps_transformer_norm", C.c_float), ("eps_out_norm", C.c_float), ("ln_eps", C.c_float),
         ("vae_in_channels", C.c_int32), ("vae_latent_channels", C.c_int32),
         ("vae_num_blocks", C.c_int32),
@@ -73,6 +73,7 @@ _SIGNATURES = {
     "ug_ctx_create": ([C.POINTER(_P), _I, C.POINTER(ModelCfg)], C.c_int),
     "ug_ctx_destroy": ([_P], C.c_int),
     "ug_ctx_load_weight": ([_P, C.c_char_p, _P, _I, C.POINTER(C.c_int64), _I, _P], C.c_int),
+    "ug_ctx_set_vae_encode_dtype": ([_P, _I], C.c_int),
     "ug_ctx_finalize": ([_P, _P], C.c_int),
     "ug_ctx_prepare": ([_P, _I, _I, _I, _P], C.c_int),
     "ug_set_clip_context": ([_P, _P, _P], C.c_int),
@@ -94,6 +95,8 @@ _SIGNATURES = {
     "ug_depth_postprocess": ([_P, _P, _P, _I, _I, _I, _P, _P, _P], C.c_int),
     "ug_depth_metrics": ([_P, _P, _P, _P, _L, _F, C.POINTER(C.c_double), _P, _P, _P, _P], C.c_int),
     "ug_normal_metrics": ([_P, _P, _P, _P, _L, C.POINTER(C.c_double), _P, _P], C.c_int),
+    "ug_stitch_fit": ([_P, _P, _I, _I, _I, _L, _I, _F, _P, _P], C.c_int),
+    "ug_stitch_apply": ([_P, _P, _L, _P, _L, _L, _I, _P, _I, _I, _F, _P, _P], C.c_int),
     "ug_karras_schedule": ([C.POINTER(ModelCfg), _I, C.POINTER(C.c_double), C.POINTER(C.c_double),
                             C.POINTER(C.c_double)], C.c_int),
     "ug_ddim_schedule": ([C.POINTER(UNet2DCfg), _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_double),
@@ -161,6 +164,7 @@ def cfg_struct(cfg, dtype: int) -> ModelCfg:
     m.num_added_ids = u.num_added_ids
     m.norm_groups = u.norm_groups
     m.eps_cross_attn_block, m.eps_plain_block = u.eps_cross_attn_block, u.eps_plain_block
+    m.eps_plain_up_block = u.eps_plain_up_block
     m.eps_transformer_norm, m.eps_out_norm, m.ln_eps = u.eps_transformer_norm, u.eps_out_norm, u.ln_eps
     m.vae_in_channels, m.vae_latent_channels = v.in_channels, v.latent_channels
     m.vae_num_blocks = len(v.block_out_channels)

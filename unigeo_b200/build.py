@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "build")
 LIB = os.path.join(HERE, "libunigeo_b200.so")
-SOURCES = ["tapgemm.cu", "fmha.cu", "kernels.cu", "ops.cu", "unet.cu", "unet2d.cu", "vae.cu", "clip.cu", "post.cu", "metrics.cu", "api.cu"]
+SOURCES = ["tapgemm.cu", "fmha.cu", "kernels.cu", "ops.cu", "unet.cu", "unet2d.cu", "vae.cu", "clip.cu", "post.cu", "metrics.cu", "stitch.cu", "api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",

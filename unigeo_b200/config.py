@@ -30,7 +30,8 @@ class UNetSTConfig:
     # [UPSTREAM] eps values (unet_3d_blocks.py): cross-attn blocks build their
     # SpatioTemporalResBlocks with 1e-6, plain down/up/mid blocks with 1e-5.
     eps_cross_attn_block: float = 1e-6
-    eps_plain_block: float = 1e-5
+    eps_plain_block: float = 1e-5            # DownBlockSpatioTemporal / mid block: hard-coded 1e-5 upstream
+    eps_plain_up_block: float = 1e-6         # UpBlockSpatioTemporal: resnet_eps default 1e-6, not overridden by get_up_block
     eps_transformer_norm: float = 1e-6
     eps_out_norm: float = 1e-5
     ln_eps: float = 1e-5

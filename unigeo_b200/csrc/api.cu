@@ -159,6 +159,21 @@ std::vector<int> ddim_timesteps(int NT, int steps, int t_start) {
   return ts;
 }
 
+// matrices of the VAE encoder live in the encoder's own format (ug_ctx_set_vae_encode_dtype)
+bool is_vae_encoder_key(const char* key) {
+  return std::strncmp(key, "vae.encoder.", 12) == 0 || std::strncmp(key, "vae.quant_conv.", 15) == 0 ||
+         std::strncmp(key, "vae2d.encoder.", 14) == 0 || std::strncmp(key, "vae2d.quant_conv.", 17) == 0;
+}
+int weight_fmt(const Ctx& c, const char* key) { return (c.enc_fmt >= 0 && is_vae_encoder_key(key)) ? c.enc_fmt : c.fmt; }
+
+// the VAE encoder graph runs with the encoder's format as the context format
+struct FmtScope {
+  Ctx& c;
+  int saved;
+  FmtScope(Ctx& ctx, int fmt) : c(ctx), saved(ctx.fmt) { if (fmt >= 0) c.fmt = fmt; }
+  ~FmtScope() { c.fmt = saved; }
+};
+
 thread_local ug_ctx* g_scratch[2] = {nullptr, nullptr};
 ug_ctx* scratch_ctx(int dtype) {
   UG_CHECK(dtype == UG_F16 || dtype == UG_BF16, UG_ERR_INVALID, "dtype must be UG_F16 or UG_BF16");
@@ -249,12 +264,23 @@ int ug_ctx_load_weight(ug_ctx* u, const char* key, const void* dev_ptr, int dtyp
       const size_t bytes = (size_t)w.taps * w.cout * w.cin_pad * 2;
       w.p = c.dmalloc(bytes);
       if (w.cin_pad != w.cin) UG_CUDA(cudaMemsetAsync(w.p, 0, bytes, st));
-      UG_CUDA(launch_convert_weight(dev_ptr, dtype, w.p, w.cout, w.cin, w.cin_pad, w.taps, c.fmt, st));
+      UG_CUDA(launch_convert_weight(dev_ptr, dtype, w.p, w.cout, w.cin, w.cin_pad, w.taps, weight_fmt(c, key), st));
       w.cin = w.cin_pad;
     }
     c.weights[key] = w;
     c.finalized = false;
     ++c.ptr_epoch;
+  });
+}
+
+int ug_ctx_set_vae_encode_dtype(ug_ctx* u, int dtype) {
+  return guard([&] {
+    UG_CHECK(u, UG_ERR_INVALID, "null ctx");
+    UG_CHECK(dtype == -1 || dtype == UG_F16 || dtype == UG_BF16, UG_ERR_INVALID, "dtype must be -1, UG_F16 or UG_BF16");
+    for (const auto& kv : u->c.weights)
+      UG_CHECK(kv.second.is_f32 || !is_vae_encoder_key(kv.first.c_str()), UG_ERR_STATE,
+               "ug_ctx_set_vae_encode_dtype must precede the encoder's weights");
+    u->c.enc_fmt = dtype == u->c.fmt ? -1 : dtype;
   });
 }
 
@@ -366,6 +392,7 @@ int ug_vae_encode(ug_ctx* u, const float* img, const float* noise, float noise_s
     UG_CHECK(N >= 1 && H % 8 == 0 && W % 8 == 0, UG_ERR_INVALID, "H and W must be multiples of 8");
     const std::string sig = "enc:" + std::to_string(N) + "x" + std::to_string(H) + "x" + std::to_string(W);
     run_sized(u, sig, stream, [&](Ctx& c) {
+      FmtScope fs(c, c.enc_fmt);
       void* img16 = c.alloc16((long long)N * H * W * 8);
       if (!c.dry)
         op_check(c, launch_nchw_to_nhwc(img, noise, noise_strength, 1.f, 0.f, N, c.cfg.vae_in_channels, H, W, 8,
@@ -416,6 +443,7 @@ int ug_vae_encode_frames(ug_ctx* u, const float* frames, const float* noise, flo
     UG_CHECK(u->c.cfg.vae_in_channels == 3, UG_ERR_INVALID, "frames are RGB");
     const std::string sig = "enc:" + std::to_string(T) + "x" + std::to_string(H) + "x" + std::to_string(W);
     run_sized(u, sig, stream, [&](Ctx& c) {
+      FmtScope fs(c, c.enc_fmt);
       void* img16 = c.alloc16((long long)T * H * W * 8);
       if (!c.dry)
         op_check(c, launch_frames_in(frames, noise, noise_strength, T, (long long)H * W, img16, video_nchw, c.fmt,
@@ -519,6 +547,40 @@ int ug_normal_metrics(ug_ctx* u, const float* pred, const float* gt, const unsig
         c.launches += 9;   // errors, fold, 4 x (histogram, step) behind one launcher
       }
     });
+  });
+}
+
+int ug_stitch_fit(ug_ctx* u, const float* overlap_frames, int world, int per_rank, int num_clips, long long n, int space,
+                  float offset, double* chain_dev, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && overlap_frames && chain_dev, UG_ERR_INVALID, "null argument");
+    UG_CHECK(world >= 1 && per_rank >= 1 && num_clips >= 1 && num_clips <= world * per_rank && n >= 1, UG_ERR_INVALID,
+             "bad extents");
+    UG_CHECK(space == 0 || space == 1, UG_ERR_INVALID, "space must be 0 (as given) or 1 (1 / v - offset)");
+    run_sized(u, "stitch:" + std::to_string(num_clips), stream, [&](Ctx& c) {
+      void* ws = c.ws.alloc((size_t)stitch_workspace_bytes(num_clips));
+      if (!c.dry) {
+        op_check(c, launch_stitch_fit(overlap_frames, world, per_rank, num_clips, n, space, offset, ws, chain_dev, c.stream),
+                 "stitch_fit", 0.0, 8.0 * n * (num_clips - 1));
+        if (num_clips > 1) c.launches += 1;   // fit + chain behind one launcher
+      }
+    });
+  });
+}
+
+int ug_stitch_apply(ug_ctx* u, const float* clip, long long elems, const float* prev_tail, long long n_overlap,
+                    long long frame_elems, int overlap, const double* chain_dev, int k, int space, float offset, float* out,
+                    void* stream) {
+  return guard([&] {
+    UG_CHECK(u && clip && chain_dev && out, UG_ERR_INVALID, "null argument");
+    UG_CHECK(elems >= 1 && k >= 0 && frame_elems >= 1 && overlap >= 0 && n_overlap == (long long)overlap * frame_elems &&
+                 n_overlap <= elems, UG_ERR_INVALID, "bad extents");
+    UG_CHECK(k > 0 || prev_tail == nullptr, UG_ERR_INVALID, "clip 0 has no predecessor");
+    Ctx& c = u->c;
+    UG_CUDA(cudaSetDevice(c.device));
+    c.stream = reinterpret_cast<cudaStream_t>(stream);
+    op_check(c, launch_stitch_apply(clip, elems, prev_tail, n_overlap, frame_elems, overlap, chain_dev, k, space, offset,
+                                    out, c.stream), "stitch_apply", 0.0, 8.0 * elems);
   });
 }
 
@@ -647,6 +709,7 @@ int ug_vae2d_encode(ug_ctx* u, const float* img, int N, int H, int W, float out_
     UG_CHECK(N >= 1 && H % 8 == 0 && W % 8 == 0, UG_ERR_INVALID, "H and W must be multiples of 8");
     const std::string sig = "enc2d:" + std::to_string(N) + "x" + std::to_string(H) + "x" + std::to_string(W);
     run_sized(u, sig, stream, [&](Ctx& c) {
+      FmtScope fs(c, c.enc_fmt);
       void* img16 = c.alloc16((long long)N * H * W * 8);
       if (!c.dry)
         op_check(c, launch_nchw_to_nhwc(img, nullptr, 0.f, 1.f, 0.f, N, c.cfg.vae_in_channels, H, W, 8, img16, c.fmt,

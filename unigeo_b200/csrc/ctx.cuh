@@ -87,6 +87,8 @@ struct Nets2D;
 struct Ctx {
   int device = 0;
   int fmt = 1;                   // 0 fp16, 1 bf16
+  int enc_fmt = -1;              // storage / compute format of the VAE ENCODER ("vae.encoder.", "vae.quant_conv."
+                                 // matrices and its activations); -1 = same as fmt (ug_ctx_set_vae_encode_dtype)
   ug_model_cfg cfg{};
   std::unordered_map<std::string, Weight> weights;
   Arena ws;                      // activations / temporaries

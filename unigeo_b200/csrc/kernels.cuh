@@ -97,6 +97,13 @@ int launch_euler_step(float* latents, const float* v, float sigma, float sigma_n
 long long post_workspace_floats(long long pixels);
 int launch_depth_postprocess(const float* frames, const float* K, int T, int H, int W, float* depth, float* normals,
                              float* ws, cudaStream_t st);
+// ---- scene stitch (stitch.cu): 2-parameter maps between consecutive clips on their shared frames, chained into clip 0's
+// frame; buf = all-gathered overlap frames [world][per_rank][2 (head, tail)][n] fp32; chain = [num_clips][2] doubles (S, T)
+long long stitch_workspace_bytes(int num_clips);
+int launch_stitch_fit(const float* buf, int world, int per_rank, int num_clips, long long n, int space, float offset,
+                      void* ws, double* chain, cudaStream_t st);
+int launch_stitch_apply(const float* clip, long long elems, const float* prev_tail, long long n_ov, long long frame_elems,
+                        int overlap, const double* chain, int k, int space, float offset, float* out, cudaStream_t st);
 // ---- metric kernels (metrics.cu): eval.py:49 / :54 on the device; results land in host doubles (the launchers
 // synchronise `st`).  ws: metrics_workspace_bytes(n) bytes.  mask nullable (uint8, 0 = excluded).
 long long metrics_workspace_bytes(long long n);

@@ -427,7 +427,7 @@ void unet_forward(Ctx& c, const void* x16, float timestep, const float ids[3], f
 
   for (int i = 0; i < nb; ++i) {
     const bool attn = i > 0;
-    const float eps = attn ? g.eps_cross_attn_block : g.eps_plain_block;
+    const float eps = attn ? g.eps_cross_attn_block : g.eps_plain_up_block;
     const int co = g.unet_block_out[nb - 1 - i];
     const std::string b = U + "up_blocks." + std::to_string(i);
     for (int j = 0; j < L + 1; ++j) {

@@ -30,7 +30,8 @@ def _f32(t: torch.Tensor, device) -> torch.Tensor:
 class Engine:
     """One context = one GPU = one model replica (clip-sharded data parallelism above it)."""
 
-    def __init__(self, cfg: PipelineConfig, dtype: str = "fp16", device: int = 0, sn_cfg=None):
+    def __init__(self, cfg: PipelineConfig, dtype: str = "fp16", device: int = 0, sn_cfg=None,
+                 vae_encode_dtype: str | None = None):
         if not torch.cuda.is_available():
             raise RuntimeError("unigeo_b200.Engine needs a CUDA device (B200, sm_100a); there is no CPU path")
         if dtype not in _DTYPES:
@@ -42,6 +43,11 @@ class Engine:
         self._cfg_struct = _lib.cfg_struct(cfg, _DTYPES[dtype])
         self._ctx = C.c_void_p()
         _lib.check(self.lib.ug_ctx_create(C.byref(self._ctx), device, C.byref(self._cfg_struct)))
+        if vae_encode_dtype is not None:   # the encoder alone in bf16 (upstream upcasts it to fp32: fp16 range)
+            if vae_encode_dtype not in _DTYPES:
+                raise ValueError(f"vae_encode_dtype must be one of {sorted(_DTYPES)}")
+            _lib.check(self.lib.ug_ctx_set_vae_encode_dtype(self._ctx, _DTYPES[vae_encode_dtype]))
+        self.vae_encode_dtype = vae_encode_dtype or dtype
         self._shape: Tuple[int, int, int] | None = None
         self._finalized = False
         self.sn_cfg = sn_cfg
@@ -261,6 +267,32 @@ class Engine:
                                                   m.data_ptr() if m is not None else None, n, out,
                                                   err.data_ptr() if with_map else None, _stream()))
         return (list(out), err) if with_map else list(out)
+
+    # ------------------------------------------------------------------ scene stitch (sharding.stitch_scene)
+    def stitch_fit(self, gathered: torch.Tensor, num_clips: int, disparity: bool = True, offset: float = 0.1):
+        """gathered [world, per_rank, 2, overlap, H, W] fp32 CUDA (all-gathered heads / tails) -> chain [num_clips, 2]
+        float64 CUDA: (S, T) of every clip into clip 0's frame (ug_stitch_fit)."""
+        g = _f32(gathered, self.device)
+        world, per_rank = g.shape[0], g.shape[1]
+        n = g[0, 0, 0].numel()
+        chain = torch.empty((num_clips, 2), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_stitch_fit(self._ctx, g.data_ptr(), world, per_rank, int(num_clips), n,
+                                              1 if disparity else 0, float(offset), chain.data_ptr(), _stream()))
+        return chain
+
+    def stitch_apply(self, clip: torch.Tensor, prev_tail, chain: torch.Tensor, k: int, overlap: int,
+                     disparity: bool = True, offset: float = 0.1) -> torch.Tensor:
+        """clip [T,H,W] (clip k of the scene), prev_tail [overlap,H,W] | None -> clip k in clip 0's frame, head ramped."""
+        d = _f32(clip, self.device)
+        frame = d[0].numel()
+        pt = _f32(prev_tail, self.device) if prev_tail is not None else None
+        out = torch.empty_like(d)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.ug_stitch_apply(self._ctx, d.data_ptr(), d.numel(), pt.data_ptr() if pt is not None else None,
+                                                overlap * frame, frame, int(overlap), chain.data_ptr(), int(k),
+                                                1 if disparity else 0, float(offset), out.data_ptr(), _stream()))
+        return out
 
     # ------------------------------------------------------------------ StableNormal path (2-D UNet)
     def set_text_context(self, net: str, tokens: torch.Tensor) -> None:

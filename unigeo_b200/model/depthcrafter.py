@@ -7,7 +7,10 @@ Same contract as the reference adapter (/root/reference/model/depthcrafter.py):
          data['intrinsics'] list of [3,3]                                          :49
 Extra, optional ``model_params`` (ride in **kwargs like the reference tolerates):
   config="full"|"tiny", dtype="fp16"|"bf16", num_inference_steps=5, seed=None,
-  weights="synthetic"|"pretrained", device=0, clip="random"|"none".
+  weights="pretrained" (default) | "synthetic", device=0, clip="random"|"none",
+  vae_encode_dtype="bf16" (the VAE encoder alone in bf16: upstream upcasts it to fp32 for range).
+Like the reference (from_pretrained at :18-29 raises on a missing checkpoint), a missing ``unet_path`` /
+``pre_train_path`` raises FileNotFoundError; seeded random weights load ONLY on an explicit weights="synthetic".
 There is no CPU path: constructing this class without a B200 raises.
 """
 from __future__ import annotations
@@ -34,10 +37,17 @@ class DepthCrafter:
         self.dtype = kwargs.get("dtype", "fp16")                 # reference: torch_dtype=float16 (:21,:27)
         self.num_inference_steps = int(kwargs.get("num_inference_steps", 5))   # reference hard-codes 5 (:86)
         self.seed = kwargs.get("seed")
-        weights = kwargs.get("weights")
-        if weights is None:
-            weights = "pretrained" if unet_path and os.path.isdir(unet_path) else "synthetic"
-        self.engine = Engine(self.cfg, dtype=self.dtype, device=self.device.index)
+        weights = kwargs.get("weights", "pretrained")
+        if weights not in ("pretrained", "synthetic"):
+            raise ValueError(f"weights must be 'pretrained' or 'synthetic', got {weights!r}")
+        if weights == "pretrained":              # never fall back to random weights silently (garbage metrics.csv)
+            for what, pth, sub in (("unet_path", unet_path, ""), ("pre_train_path", pre_train_path, "vae")):
+                if not pth or not os.path.isdir(os.path.join(pth, sub)):
+                    raise FileNotFoundError(f"DepthCrafter: {what}={pth!r} is not a checkpoint directory"
+                                            f"{' with a ' + sub + '/ sub-directory' if sub else ''} "
+                                            "(pass weights='synthetic' for seeded random weights)")
+        self.engine = Engine(self.cfg, dtype=self.dtype, device=self.device.index,
+                             vae_encode_dtype=kwargs.get("vae_encode_dtype"))
         self._stage = None                                       # pinned staging buffer of prepare_input_device
         clip_dir = None
         if weights == "pretrained":
@@ -57,7 +67,9 @@ class DepthCrafter:
                                 device_weights=bool(kwargs.get("device_weights")))
         self.engine.finalize()
         self.pipeline = DepthCrafterPipelineB200(self.cfg, self.engine, clip)
-        print(f"Using device: {self.device}")
+        self.weight_source = (f"pretrained: unet {unet_path}, vae/image_encoder {pre_train_path}" if weights == "pretrained"
+                              else f"synthetic (seeded random, weight_seed={int(kwargs.get('weight_seed', 0))})")
+        print(f"Using device: {self.device}; weights: {self.weight_source}")
 
     def prepare_input(self, data):
         """reference :39-45 -- uint8 TRUNCATION (astype), then /255."""

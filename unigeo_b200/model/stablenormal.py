@@ -7,8 +7,11 @@ The reference pulls ``Stable-X/StableNormal`` through ``torch.hub.load`` (:16, n
 in one batch).  The adapter-side contract is reproduced exactly: per-frame 8-bit predictor output, the
 uint8 x-flip wraparound (:43, App. B.10), ``/255*2-1`` (:45) and zero depths (:49).
 ``model_params`` (ride in **kwargs like the reference tolerates): ``config="full"|"tiny"``,
-``dtype``, ``num_inference_steps=10``, ``seed``, ``weights="synthetic"|<dir>``, ``controlnet=True``,
+``dtype``, ``num_inference_steps=10``, ``seed``, ``weights=<dir>|"synthetic"``, ``controlnet=True``,
 ``yoso=False``, ``device=0``; or ``predictor=<callable PIL -> PIL>`` to inject one (the hub signature).
+``weights`` defaults to ``model_dir`` (the reference's only key, configs/stablenormal_scannetpp.yaml:10-11); a missing
+checkpoint directory raises FileNotFoundError like the reference's hub load does -- seeded random weights load ONLY on
+an explicit ``weights="synthetic"``.
 There is no CPU path: constructing this class without a B200 (and without ``predictor``) raises.
 """
 from __future__ import annotations
@@ -25,6 +28,10 @@ class StableNormal:
         self.pipeline = None
         if predictor is not None:
             return
+        weights = kwargs.get("weights", model_dir)
+        if weights != "synthetic" and not (weights and os.path.isdir(str(weights))):
+            raise FileNotFoundError(f"StableNormal: weights={weights!r} is not a checkpoint directory "
+                                    "(pass weights='synthetic' for seeded random weights)")
         from ..config import get_config, stablenormal_config
         from ..engine import Engine
         from ..pipeline_stablenormal import StableNormalPipelineB200 as P
@@ -41,7 +48,6 @@ class StableNormal:
         nets = [(P.UNET, unet2d_param_shapes)] + ([(P.CONTROLNET, controlnet_param_shapes)] if use_ctrl else [])
         if use_yoso:
             nets += [(P.YOSO_UNET, unet2d_param_shapes)] + ([(P.YOSO_CONTROLNET, controlnet_param_shapes)] if use_ctrl else [])
-        weights = kwargs.get("weights", "synthetic")
         u = self.sn_cfg.unet2d
         if weights == "synthetic":
             s = int(kwargs.get("weight_seed", 0))
@@ -60,7 +66,8 @@ class StableNormal:
             prompt = torch.load(os.path.join(weights, "prompt_embeds.pt")).float().reshape(-1, u.cross_attention_dim)
         self.engine.finalize()
         self.pipeline = P(self.sn_cfg, self.engine, prompt, controlnet=use_ctrl, yoso=use_yoso)
-        print(f"Using device: {self.device}")
+        self.weight_source = "synthetic (seeded random)" if weights == "synthetic" else f"checkpoint directory {weights}"
+        print(f"Using device: {self.device}; weights: {self.weight_source}")
 
     def prepare_input(self, data):
         frames = [np.asarray(x).transpose(1, 2, 0).astype(np.uint8) for x in data["images"]]
