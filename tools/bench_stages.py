@@ -33,8 +33,18 @@ if which in ("all", "vae"):
     T, H, W = 25, 384, 512
     img = torch.rand(T, 3, H, W, device=dev) * 2 - 1
     lat = torch.randn(T, 4, H // 8, W // 8, device=dev) * 0.5
+    eng.vae_encode(img)
+    eng.profile(True, by_shape=True)
+    timed(lambda: eng.vae_encode(img), iters=1)
+    erows = sorted(eng.profile_read(), key=lambda r: -r["ms"])
+    eng.profile(False)
     ms = timed(lambda: eng.vae_encode(img))
     print(json.dumps({"stage": "vae_encode 25x384x512", "ms": ms, "tflops": 20.8 / ms * 1e3, "gbs_alg": 23.3 / ms * 1e3}))
+    for r in erows[:40]:
+        tf = r["flops"] / (r["ms"] / 2) / 1e9 if r["ms"] else 0
+        gb = r["bytes"] / (r["ms"] / 2) / 1e6 if r["ms"] else 0
+        print(f"   {r['ms']/2:8.3f} ms n={r['launches']//2:3d} {tf/2:7.0f} TF/s {gb/2:7.0f} GB/s  {r['name']}")
+    json.dump(erows, open("gpurun_out/vae_encode_by_shape.json", "w"), indent=1)
     eng.profile(True, by_shape=True)
     ms = timed(lambda: eng.vae_decode(lat, 8), iters=1)
     rows = sorted(eng.profile_read(), key=lambda r: -r["ms"])
@@ -43,8 +53,11 @@ if which in ("all", "vae"):
     print(json.dumps({"stage": "vae_decode 25x384x512 chunk 8", "ms": ms, "tflops": 56.9 / ms * 1e3, "gbs_alg": 68.5 / ms * 1e3,
                       "workspace_gb": eng.workspace_bytes() / 2 ** 30}))
     tot = sum(r["ms"] for r in rows) / 2
-    for r in rows[:14]:
-        print(f"   {r['ms']/2:8.3f} ms n={r['launches']//2:3d} {r['name']}")
+    for r in rows[:60]:
+        tf = r["flops"] / (r["ms"] / 2) / 1e9 if r["ms"] else 0
+        gb = r["bytes"] / (r["ms"] / 2) / 1e6 if r["ms"] else 0
+        print(f"   {r['ms']/2:8.3f} ms n={r['launches']//2:3d} {tf/2:7.0f} TF/s {gb/2:7.0f} GB/s  {r['name']}")
+    json.dump(rows, open("gpurun_out/vae_decode_by_shape.json", "w"), indent=1)
     eng.close()
     del eng
     torch.cuda.empty_cache()

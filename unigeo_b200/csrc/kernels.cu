@@ -2,7 +2,9 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 
+#include <atomic>
 #include <map>
+#include <mutex>
 
 namespace ug {
 namespace {
@@ -1302,25 +1304,37 @@ int launch_gn_fused(const void* x1, int C1, const void* x2, int C2, long long ro
   if (smem < smem_fin) smem = smem_fin;
   if (smem < smem_apply) smem = smem_apply;
   if (sets > kGnMaxSets || g.threads < 2 * G || g.threads > 320) return (int)cudaErrorInvalidValue;
-  // co-residency: CTAs per SM for this block shape (cached) x SM count
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  }
+  // co-residency: CTAs per SM for this block shape x SM count, cached per DEVICE under a mutex (contexts of several
+  // devices / threads share these statics)
+  static std::mutex mu;
+  static std::map<int, int> sms_of;
   static std::map<unsigned long long, int> occ_cache;
-  const unsigned long long key = ((unsigned long long)fmt << 40) | ((unsigned long long)g.threads << 24) | (unsigned long long)smem;
-  auto it = occ_cache.find(key);
-  if (it == occ_cache.end()) {
-    int nb = 0;
-    cudaError_t e;
-    if (fmt == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gn_fused_kernel<__nv_bfloat16>, g.threads, smem);
-    else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gn_fused_kernel<__half>, g.threads, smem);
-    if (e != cudaSuccess) return (int)e;
-    it = occ_cache.emplace(key, nb).first;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int sms = 0, occ = 0;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto sit = sms_of.find(dev);
+    if (sit == sms_of.end()) {
+      int n = 0;
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      sit = sms_of.emplace(dev, n).first;
+    }
+    sms = sit->second;
+    const unsigned long long key = ((unsigned long long)dev << 48) | ((unsigned long long)fmt << 40) |
+                                   ((unsigned long long)g.threads << 24) | (unsigned long long)smem;
+    auto it = occ_cache.find(key);
+    if (it == occ_cache.end()) {
+      int nb = 0;
+      cudaError_t e;
+      if (fmt == 1) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gn_fused_kernel<__nv_bfloat16>, g.threads, smem);
+      else e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gn_fused_kernel<__half>, g.threads, smem);
+      if (e != cudaSuccess) return (int)e;
+      it = occ_cache.emplace(key, nb).first;
+    }
+    occ = it->second;
   }
-  const long long resident = (long long)it->second * sms;
+  const long long resident = (long long)occ * sms;
   if (resident < sets) return (int)cudaErrorNotSupported;
   long long chunks = resident / sets;
   if (chunks > g.chunks) chunks = g.chunks;
@@ -1329,7 +1343,36 @@ int launch_gn_fused(const void* x1, int C1, const void* x2, int C2, long long ro
   dim3 grid((unsigned)chunks, (unsigned)sets);
   float* mr = stats + sets * chunks * G * 2;
   const float inv_cnt = 1.0f / ((float)rows_per_set * (float)(C / G));
-  cudaError_t err;
+  // The kernel's CTAs wait for each other (grid-wide flag), so they must all be resident.  A COOPERATIVE launch makes the
+  // driver guarantee that (or fail the launch) even when other streams / processes share the GPU; a plain launch sized
+  // from the occupancy query only assumes it.  UG_GN_COOP=0 selects the plain launch; a cooperative launch that the
+  // driver refuses (e.g. in combination with programmatic dependent launch) falls back to it once and for all.
+  static std::atomic<int> coop{[] { const char* e = getenv("UG_GN_COOP"); return e ? atoi(e) : 1; }()};
+  cudaError_t err = cudaSuccess;
+  if (coop.load() != 0) {
+    static const bool no_pdl = getenv("UG_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(g.threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = (no_pdl || coop.load() == 2) ? 1 : 2;       // 2: cooperative without the PDL attribute
+    UG_DISPATCH_FMT(fmt, (err = cudaLaunchKernelEx(&cfg, gn_fused_kernel<T>, x1, C1 / 8, x2, C2 / 8, rows_per_set,
+                                                   chunk_rows, G, C / G, stats, mr, counters, inv_cnt, eps, gamma, beta,
+                                                   silu, y)));
+    if (err == cudaSuccess) return 0;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return (int)err;   // never retry inside a capture: surface the error
+    cudaGetLastError();
+    coop.store(0);
+  }
   UG_DISPATCH_FMT(fmt, (err = launch_pdl(gn_fused_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
                                          rows_per_set, chunk_rows, G, C / G, stats, mr, counters, inv_cnt, eps, gamma,
                                          beta, silu, y)));
