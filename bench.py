@@ -29,10 +29,21 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-UNET_TFLOP_PER_STEP = {(25, 384, 512): 23.16}       # SURVEY.md §8(d) algorithmic count
+UNET_TFLOP_PER_STEP = {(25, 384, 512): 23.16, (49, 576, 1024): 156.6}       # SURVEY.md §8(d) algorithmic counts
 # algorithmic work of the VAE stages per clip (TFLOP, GB of minimal 16-bit traffic)
-VAE_WORK = {(25, 384, 512): {"decode": (56.9, 68.5), "encode": (20.8, 23.3)}}
-TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")   # per-launch DRAM bytes from the ncu capture
+VAE_WORK = {(25, 384, 512): {"decode": (56.9, 68.5), "encode": (20.8, 23.3)},
+            (49, 576, 1024): {"decode": (340.0, 402.8), "encode": (128.0, 137.1)}}
+# per-launch DRAM bytes from an ncu launch list of THIS build (tools/ncu_traffic.py stamps the source digest; a stale
+# file -- kernels changed since the capture -- is reported as traffic: null)
+TRAFFIC_JSON = os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")
+
+
+def source_digest():
+    """sha256 over the CUDA sources + nvcc flags: the same digest unigeo_b200/build.py stamps the library with."""
+    from unigeo_b200 import build as B
+    deps = [os.path.join(B.CSRC, f) for f in os.listdir(B.CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    deps.append(os.path.join(B.HERE, "..", "include", "unigeo_b200.h"))
+    return B._digest(deps)
 
 
 def parse():
@@ -48,6 +59,12 @@ def parse():
     ap.add_argument("--width", type=int, default=512)
     ap.add_argument("--e2e-steps", type=int, default=25, help="num_inference_steps of the e2e plugin call (cfg2: 25)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (fp32 oracle on the GPU, rank 0)")
+    ap.add_argument("--no-library-baseline", action="store_true", help="skip the torch-eager fp16 arm on the same GPU")
+    ap.add_argument("--no-scene", action="store_true", help="skip the cfg4 scene (8 overlapping clips, stitch all-gather)")
+    ap.add_argument("--scene-clips", type=int, default=8)
+    ap.add_argument("--scene-overlap", type=int, default=5)
+    ap.add_argument("--scene-steps", type=int, default=5, help="the reference's shipped num_inference_steps")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-frames", type=int, default=2)
     ap.add_argument("--profile-out", default=None, help="write the per-kernel launch table (json) here")
@@ -142,7 +159,9 @@ def run_reference(a):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(a), "frames": a.frames, "height": a.height, "width": a.width},
         "cpu_baseline": {"value": val, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e": {"value": val, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                "extrapolated": f"UNet step on {min(a.cpu_sample_frames, a.frames)} of {a.frames} frames x "
+                                f"{a.frames / max(1, min(a.cpu_sample_frames, a.frames)):g}; CLIP / VAE stages not included"},
         "note": "the reference's own diffusers path is not installable offline (no diffusers/weights); "
                 "this is the oracle port of the same algorithm (parity unpinned, see DESIGN.md)",
     }))
@@ -242,6 +261,9 @@ def run_b200(a):
         traffic = {}
         try:
             traffic = json.load(open(TRAFFIC_JSON))
+            if traffic.get("source_digest") != source_digest():
+                traffic = {"source": f"{os.path.basename(TRAFFIC_JSON)} is STALE (kernels changed since that ncu "
+                                     "capture): traffic not reported"}
         except (OSError, ValueError):
             pass
         roof = {"bound": "tensor", "kernel": "tapgemm_kernel<BN> (tcgen05 implicit GEMM: conv3x3 / temporal conv / linear / attention GEMMs)",
@@ -284,6 +306,16 @@ def run_b200(a):
     if not a.no_e2e:
         e2e = run_e2e(a, eng, cfg, world, rank, dev)
 
+    scene = None
+    if not a.no_scene and not a.no_e2e and a.config == "full":
+        scene = run_scene(a, eng, cfg, world, rank, dev)
+    parity = lib_base = None
+    if rank == 0 and world == 1 and a.config == "full":
+        if not a.no_parity and not a.no_e2e:
+            parity = run_parity(a, eng, cfg, dev)
+        if not a.no_library_baseline:
+            lib_base = run_library_baseline(a, eng, cfg, dev)
+
     cpu = None
     if rank == 0 and not a.no_cpu_baseline:
         del eng
@@ -301,6 +333,7 @@ def run_b200(a):
                        "weights": "seeded random-init, SVD-XT architecture (1.52 B params)",
                        "launch": "CUDA graph replay of the K-step loop" if graph_warm else "eager launches"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "scene": scene, "parity": parity, "library_baseline": lib_base,
         }
         print(json.dumps(line))
     if world > 1:
@@ -346,11 +379,7 @@ def run_e2e(a, eng, cfg, world, rank, dev):
     from unigeo_b200.clip_embed import ClipEmbedder
     from unigeo_b200.model.depthcrafter import DepthCrafter
     from unigeo_b200.pipeline import DepthCrafterPipelineB200
-    plug = object.__new__(DepthCrafter)                       # reuse the already-loaded engine (one copy of weights)
-    plug.device, plug.cfg, plug.dtype, plug.engine = dev, cfg, a.dtype, eng
-    plug.num_inference_steps, plug.seed, plug._stage = a.e2e_steps, 1234 + rank, None
-    plug.pipeline = DepthCrafterPipelineB200(cfg, eng, ClipEmbedder.__new__(ClipEmbedder))
-    plug.pipeline.clip.engine = eng                           # CLIP weights were loaded with the rest (run_b200)
+    plug = _plugin(a, eng, cfg, dev, a.e2e_steps, 1234 + rank)
     data = make_clip(a.frames, a.height, a.width, seed=1234 + rank)
     for _ in range(2):                                         # warm-up: workspace sizing, then the CUDA-graph capture
         plug.forward(data)                                     # of the denoising loop (2nd call with one signature)
@@ -371,6 +400,177 @@ def run_e2e(a, eng, cfg, world, rank, dev):
             "d2h_bytes_per_step": d2h / a.e2e_steps, "clip_seconds": dt, "num_inference_steps": a.e2e_steps,
             "call": "unigeo_b200.model.DepthCrafter.forward(data) (H2D images + prepare_input + CLIP ViT-H + VAE encode + denoise + "
                     "VAE decode + depth/normal post-processing + D2H)"}
+
+
+def _plugin(a, eng, cfg, dev, steps, seed):
+    from unigeo_b200.clip_embed import ClipEmbedder
+    from unigeo_b200.model.depthcrafter import DepthCrafter
+    from unigeo_b200.pipeline import DepthCrafterPipelineB200
+    plug = object.__new__(DepthCrafter)                       # reuse the already-loaded engine (one copy of weights)
+    plug.device, plug.cfg, plug.dtype, plug.engine = dev, cfg, a.dtype, eng
+    plug.num_inference_steps, plug.seed, plug._stage = steps, seed, None
+    plug.pipeline = DepthCrafterPipelineB200(cfg, eng, ClipEmbedder.__new__(ClipEmbedder))
+    plug.pipeline.clip.engine = eng
+    return plug
+
+
+def run_scene(a, eng, cfg, world, rank, dev):
+    """BASELINE cfg4 on a measured path: ONE scene = `scene_clips` overlapping clips (stride frames - overlap, as
+    dataset/scannetpp/scannetpp.py:44 builds them) sharded clip i -> rank i % world; every rank runs the plugin call on
+    its clips (no communication), then the ONE exchange of the path -- an all-gather of every clip's first / last
+    `overlap` depth frames (NCCL over NVLink) -- feeds the stitch kernels (ug_stitch_fit / ug_stitch_apply), the
+    metric kernels score the device-resident outputs and one all-gather collects the 17-float rows.  Total work is
+    fixed (strong scaling over N); timed on the host clock of the slowest rank around barriers (the plugin call is
+    synchronous), stitch + gathers also with CUDA events."""
+    import torch
+    import torch.distributed as dist
+    from harness.synthetic import gt_label, make_clip
+    from unigeo_b200 import metrics as DM
+    from unigeo_b200 import sharding as sh
+    K, ov, T = a.scene_clips, a.scene_overlap, a.frames
+    stride = T - ov
+    n_frames = stride * (K - 1) + T
+    sc = make_clip(n_frames, a.height, a.width, seed=4321, scene_name="synthetic_scene")
+    clip_of = lambda k: {key: (v[k * stride:k * stride + T] if isinstance(v, list) else v) for key, v in sc.items()}
+    plug = _plugin(a, eng, cfg, dev, a.scene_steps, 99)
+    mine = sh.clips_of_rank(K, rank, world)
+    gts = {k: gt_label(clip_of(k)) for k in mine}             # host-side GT shaping is dataset work, not the path
+    plug.forward_device(clip_of(mine[0] if mine else 0))      # warm-up: workspace / graph of this step count
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sync()
+    t0 = time.perf_counter()
+    outs = [plug.forward_device(clip_of(k)) for k in mine]
+    torch.cuda.synchronize()
+    t_clips = time.perf_counter() - t0
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record()
+    stitched = sh.stitch_scene([o["pred_depths"] for o in outs], mine, K, ov, rank, world, engine=eng, device=dev)
+    e1.record()
+    rows = []
+    for k, o in zip(mine, outs):
+        d = DM.depth_evaluation(o["pred_depths"], gts[k]["gt_depths"], custom_mask=gts[k]["gt_masks"],
+                                align_with_lstsq=True, engine=eng, with_maps=False)[0]
+        n = DM.normal_evaluation(o["pred_normals"], gts[k]["gt_normals"], custom_mask=gts[k]["gt_masks"], engine=eng)
+        rows.append([float(d[key]) for key in DM.DEPTH_KEYS] + [float(n[key]) for key in DM.NORMAL_KEYS])
+    table = sh.gather_metric_rows(mine, torch.tensor(rows, dtype=torch.float64, device=dev), K, rank, world)
+    e2.record()
+    sync()
+    t_total = time.perf_counter() - t0
+    t = torch.tensor([t_clips, t_total, e0.elapsed_time(e1), e1.elapsed_time(e2)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    tc, tt, stitch_ms, score_ms = t.tolist()
+    assert all(torch.isfinite(s_).all() for s_ in stitched)
+    return {"workload": f"scene of {K} clips x {T} frames (overlap {ov}, {n_frames} distinct frames) at {a.height}x{a.width}, "
+                        f"{a.scene_steps} denoising steps per clip, clips sharded over {world} GPU(s)",
+            "scaling": "strong (fixed scene)", "value": K * a.scene_steps / tt, "unit": "steps/s", "clips_per_s": K / tt,
+            "seconds_total": tt, "seconds_clips": tc, "stitch_ms": stitch_ms, "score_and_gather_ms": score_ms,
+            "collective": ("all_gather of [clips/rank, 2, overlap, H, W] fp32 overlap frames + all_gather of the metric rows (NCCL)"
+                           if world > 1 else "none (1 rank)"),
+            "stitch": "ug_stitch_fit / ug_stitch_apply (fp64 normal equations in disparity space, chained, ramped)",
+            "abs_rel_per_clip": [round(float(v), 5) for v in table[:, 0].tolist()]}
+
+
+def run_parity(a, eng, cfg, dev):
+    """Outside every timed region: the reference's shipped call (5 steps) through the plugin adapter against the fp32
+    oracle run on this GPU (torch eager, TF32 off, cuDNN off -- see tests/test_parity_cfg2_gpu.py) on the SAME weights
+    (the engine's fp16 values, upcast) and the same noise draws / CLIP embeddings; both scored by the reference metric
+    restatement (oracle/metrics.py, bit-exact against /root/reference/metrics/eval_depth.py on the golden fixtures)."""
+    import numpy as np
+    import torch
+    from harness.synthetic import gt_label, make_clip
+    from oracle import metrics as OM
+    from oracle import postprocess as OP
+    from oracle.pipeline import depthcrafter_pipeline
+    from unigeo_b200.weights import synthetic_state_dict, unet_param_shapes, vae_param_shapes
+    T, H, W = a.frames, a.height, a.width
+    if T * H * W > 25 * 384 * 512:
+        return {"skipped": "parity block runs at cfg2 size or smaller (the fp32 oracle needs minutes beyond it)"}
+    steps = 5
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.enabled)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.enabled = False
+    try:
+        usd = {k: v.float() for k, v in synthetic_state_dict(unet_param_shapes(cfg.unet), 1000, torch.float16, dev).items()}
+        vsd = {k: v.float() for k, v in synthetic_state_dict(vae_param_shapes(cfg.vae), 2000, torch.float16, dev).items()}
+        data = make_clip(T, H, W, seed=77)
+        plug = _plugin(a, eng, cfg, dev, steps, None)
+        g = torch.Generator(device=dev).manual_seed(5)
+        enc = torch.randn(T, cfg.clip_embed_dim, generator=g, device=dev)
+        aug = torch.randn(T, 3, H, W, generator=g, device=dev)
+        init = torch.randn(T, 4, H // 8, W // 8, generator=g, device=dev)
+        out = plug.forward(data, enc=enc, aug_noise=aug, init_noise=init)
+        frames = torch.from_numpy(OP.prepare_input(data["images"])).to(dev)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ref_frames = depthcrafter_pipeline(usd, vsd, cfg, frames, enc[None], aug, init[None], steps).cpu().numpy()
+        t_oracle = time.perf_counter() - t0
+        ref_depth = torch.from_numpy(np.asarray(OP.disparity_to_depth(ref_frames), dtype=np.float32))
+        gt = gt_label(data)
+        m_ref = OM.depth_evaluation(ref_depth, gt["gt_depths"], gt["gt_masks"])
+        m_got = OM.depth_evaluation(out["pred_depths"], gt["gt_depths"], gt["gt_masks"])
+        keys = ("Abs Rel", "delta < 1.25", "delta < 1.25^2", "delta < 1.25^3")
+        return {"what": f"DepthCrafter.forward, {steps} steps, {T}x{H}x{W}, {a.dtype} kernels vs fp32 oracle on the same GPU",
+                "abs_rel": {"b200": m_got["Abs Rel"], "oracle": m_ref["Abs Rel"], "abs_diff": abs(m_got["Abs Rel"] - m_ref["Abs Rel"])},
+                "delta_abs_diff": {k: abs(m_got[k] - m_ref[k]) for k in keys[1:]},
+                "valid_pixels_equal": m_got["valid_pixels"] == m_ref["valid_pixels"],
+                "max_abs_depth_diff": float((out["pred_depths"] - ref_depth).abs().max()),
+                "tolerance": {"abs_rel": 1e-3, "delta": 2e-3}, "oracle_seconds": t_oracle,
+                "pass": bool(abs(m_got["Abs Rel"] - m_ref["Abs Rel"]) <= 1e-3 and
+                             all(abs(m_got[k] - m_ref[k]) <= 2e-3 for k in keys[1:]))}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.enabled = tf32
+        torch.cuda.empty_cache()
+
+
+def run_library_baseline(a, eng, cfg, dev):
+    """The stack the reference actually dispatches to, on this same B200 ("the practical bar to beat"):
+    the oracle restatement of one denoising step in torch eager fp16 -- cuDNN convolutions, cuBLASLt linears, SDPA flash
+    attention -- on the bench's inputs and weights.  Timed with CUDA events (median of 3 after a warm-up); its output is
+    compared with the engine's for the same inputs so that a mis-computing library arm cannot pass as a baseline."""
+    import torch
+    from oracle import scheduler as S
+    from oracle import unet_st as U
+    from oracle.pipeline import added_time_ids
+    from unigeo_b200.weights import synthetic_state_dict, unet_param_shapes
+    T, h, w = a.frames, a.height // 8, a.width // 8
+    dt = torch.float16 if a.dtype == "fp16" else torch.bfloat16
+    sd = {k: v.to(dt) for k, v in synthetic_state_dict(unet_param_shapes(cfg.unet), 1000, torch.float16, dev).items()}
+    g = torch.Generator(device=dev).manual_seed(4321)
+    x = torch.randn(1, T, 8, h, w, generator=g, device=dev)
+    enc = torch.randn(1, T, cfg.clip_embed_dim, generator=g, device=dev)
+    ids = added_time_ids(cfg, dev)
+    U.USE_SDPA = True
+    try:
+        with torch.no_grad():
+            step = lambda: U.unet_forward(sd, cfg.unet, x.to(dt), 0.9, enc.to(dt), ids.to(dt))
+            ref = step()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(3):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); step(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+    finally:
+        U.USE_SDPA = False
+    ms = sorted(ts)[1]
+    eng.prepare(T, h, w)
+    eng.set_clip_context(enc[0])
+    ours = eng.unet_forward(x, 0.9, ids[0].tolist())
+    rel = ((ours.double() - ref.double()).norm() / ref.double().norm()).item()
+    del sd
+    torch.cuda.empty_cache()
+    return {"value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "dtype": a.dtype,
+            "what": "oracle restatement of one UNet denoising step in torch eager (cuDNN / cuBLASLt / SDPA flash), same GPU, "
+                    "same weights and inputs; Euler update excluded (negligible)",
+            "rel_l2_vs_b200_kernels": rel, "tflops": UNET_TFLOP_PER_STEP.get((a.frames, a.height, a.width), 0) / ms * 1e3}
 
 
 if __name__ == "__main__":

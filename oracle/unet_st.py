@@ -19,6 +19,11 @@ import torch.nn.functional as F
 
 SD = Dict[str, torch.Tensor]
 
+# bench.py's library-baseline arm only (torch eager fp16 on the GPU): route self-attention through
+# F.scaled_dot_product_attention (flash kernels) instead of materialising the scores, as the reference's
+# xformers / SDPA processors do (model/depthcrafter.py:33).  Parity tests keep the explicit softmax.
+USE_SDPA = False
+
 
 # ------------------------------------------------------------------ small pieces
 def sinusoid(t: torch.Tensor, dim: int) -> torch.Tensor:
@@ -68,6 +73,9 @@ def attention(sd: SD, key: str, x: torch.Tensor, ctx: torch.Tensor, heads: int) 
     q = q.view(b, n, heads, d).transpose(1, 2)
     k = k.view(b, -1, heads, d).transpose(1, 2)
     v = v.view(b, -1, heads, d).transpose(1, 2)
+    if USE_SDPA:
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(b, n, c)
+        return linear(sd, key + ".to_out.0", o)
     s = torch.matmul(q, k.transpose(-1, -2)) / math.sqrt(d)
     p = torch.softmax(s.float(), dim=-1).to(v.dtype)
     o = torch.matmul(p, v).transpose(1, 2).reshape(b, n, c)

@@ -1,9 +1,14 @@
 """Summarises an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv`
 launch list of one denoising step into per-kernel-family DRAM bytes per launch (bench.py `roofline.traffic`).
-usage: python tools/ncu_traffic.py gpurun_out/ncu_step_dram.csv profiles/r01_ncu_traffic.json"""
+The summary is stamped with the digest of the CUDA sources it was captured from; bench.py reports traffic only when
+that digest matches the build it runs (a stale file would silently describe other kernels).
+usage: python tools/ncu_traffic.py gpurun_out/ncu_step_dram.csv profiles/r02_ncu_traffic.json"""
 import csv
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 src, dst = sys.argv[1], sys.argv[2]
 rows = []
@@ -14,7 +19,7 @@ for r in csv.DictReader(lines):
 fam = {}
 for r in rows:
     name = r["Kernel Name"]
-    key = next((k for k in ("tapgemm", "fmha", "gn_fused", "gn_stats", "gn_apply", "layernorm", "temporal_attn", "concat",
+    key = next((k for k in ("tapgemm", "fmha", "gn_fused", "gn_cluster", "gn_stats", "gn_apply", "layernorm", "ln_stats", "temporal_attn", "concat",
                             "upsample2x") if k in name), None)
     if key is None:
         continue
@@ -32,6 +37,8 @@ for r in rows:
         d["us"] += v * scale
 out = {"source": f"ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum over one cfg2 "
                  f"denoising step ({src.split('/')[-1]}); cold-cache, serialised launches"}
+from bench import source_digest  # noqa: E402
+out["source_digest"] = source_digest()
 fam = {{"temporal_attn": "temporal_attention"}.get(k, k): v for k, v in fam.items()}
 for k, d in fam.items():
     n = len(d["ids"])
