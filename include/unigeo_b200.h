@@ -101,6 +101,10 @@ int ug_ctx_destroy(ug_ctx* ctx);
  * original diffusers shape.  Copied and re-laid-out into library storage. */
 int ug_ctx_load_weight(ug_ctx* ctx, const char* key, const void* dev_ptr, int dtype, const int64_t* shape,
                        int rank, void* stream);
+/* A whole state dict in one call and ONE conversion launch (n tensors; shapes holds 5 int64 per tensor, the first
+ * ranks[i] of them valid).  Same result as n ug_ctx_load_weight calls; the source tensors may be released on return. */
+int ug_ctx_load_weights(ug_ctx* ctx, int n, const char* const* keys, const void* const* dev_ptrs, const int* dtypes,
+                        const int64_t* shapes, const int* ranks, void* stream);
 /* Storage / compute type of the VAE ENCODER alone (UG_F16, UG_BF16, or -1 = the context's dtype; call before the
  * "vae.encoder." / "vae.quant_conv." (and "vae2d." ditto) weights are loaded).  [UPSTREAM] encode_vae_video upcasts the VAE to fp32
  * (force_upcast) because SVD's encoder activations leave the fp16 range; UG_BF16 keeps the

@@ -36,10 +36,25 @@ for _ in range(3):
 launches = eng.launch_count() // 3
 ms = sorted(ts)[1]
 assert torch.isfinite(out).all()
-eng.profile(True)
+eng.profile(True, by_shape=True)
 eng.refine_2d("unet2d", "controlnet", il, lat, 1)
-rows = eng.profile_read()
+rows = eng.profile_read(cap=2048)
 eng.profile(False)
+# per-kernel rooflines of the step (BASELINE cfg3): tensor-bound kernels against the measured cuBLAS peak, the rest
+# against the measured copy bandwidth; one frame of 64 x 64 latents is far too small to fill 148 SMs (M = 4096 ..
+# 64 rows per GEMM), so launch latency, not either roof, bounds most launches
+import os  # noqa: E402
+peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
+shape_rows = []
+for r in sorted(rows, key=lambda r: -r["ms"])[:25]:
+    tensor = r["name"].startswith(("tapgemm", "fmha"))
+    us = 1e3 * r["ms"] / max(r["launches"], 1)
+    ach = (r["flops"] / 1e12 if tensor else r["bytes"] / 1e9) / (r["ms"] * 1e-3) if r["ms"] else 0.0
+    peak = peaks["bf16_tflops_sustained"] if tensor else peaks["hbm_gbs"]
+    shape_rows.append({"kernel": r["name"], "launches": r["launches"], "us_per_launch": round(us, 2), "bound": "tensor" if tensor else "hbm",
+                       "achieved": round(ach, 1), "unit": "TFLOP/s" if tensor else "GB/s", "frac": round(ach / peak, 4)})
+for r in rows:
+    r["name"] = r["name"].split(" ")[0]
 fam = {}
 for r in rows:
     k = r["name"].split(".")[0]
@@ -60,4 +75,5 @@ print(json.dumps({
     "kernels": {k: {"ms": round(d["ms"], 3), "launches": d["launches"],
                     "tflops": round(d["flops"] / 1e9 / d["ms"], 1) if d["ms"] else 0} for k, d in
                 sorted(fam.items(), key=lambda kv: -kv[1]["ms"])},
+    "top_kernels_by_shape": shape_rows, "peaks": {"tensor_tflops": peaks["bf16_tflops_sustained"], "hbm_gbs": peaks["hbm_gbs"]},
     "plugin_forward_seconds": dt, "plugin_normals_shape": list(o["pred_normals"].shape)}))

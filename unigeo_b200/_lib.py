@@ -74,6 +74,8 @@ _SIGNATURES = {
     "ug_ctx_destroy": ([_P], C.c_int),
     "ug_ctx_load_weight": ([_P, C.c_char_p, _P, _I, C.POINTER(C.c_int64), _I, _P], C.c_int),
     "ug_ctx_set_vae_encode_dtype": ([_P, _I], C.c_int),
+    "ug_ctx_load_weights": ([_P, _I, C.POINTER(C.c_char_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int),
+                             C.POINTER(C.c_int64), C.POINTER(C.c_int), _P], C.c_int),
     "ug_ctx_finalize": ([_P, _P], C.c_int),
     "ug_ctx_prepare": ([_P, _I, _I, _I, _P], C.c_int),
     "ug_set_clip_context": ([_P, _P, _P], C.c_int),

@@ -273,6 +273,74 @@ int ug_ctx_load_weight(ug_ctx* u, const char* key, const void* dev_ptr, int dtyp
   });
 }
 
+int ug_ctx_load_weights(ug_ctx* u, int n, const char* const* keys, const void* const* dev_ptrs, const int* dtypes,
+                        const int64_t* shapes, const int* ranks, void* stream) {
+  return guard([&] {
+    UG_CHECK(u && keys && dev_ptrs && dtypes && shapes && ranks, UG_ERR_INVALID, "null argument");
+    UG_CHECK(n >= 0, UG_ERR_INVALID, "n must be non-negative");
+    if (n == 0) return;
+    Ctx& c = u->c;
+    UG_CUDA(cudaSetDevice(c.device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    std::vector<ConvertDesc> descs((size_t)n);
+    std::vector<Weight> ws((size_t)n);
+    long long blocks = 0;
+    for (int i = 0; i < n; ++i) {
+      const char* key = keys[i];
+      const int64_t* shape = shapes + (size_t)i * 5;
+      const int rank = ranks[i];
+      UG_CHECK(key && dev_ptrs[i], UG_ERR_INVALID, "null tensor");
+      UG_CHECK(rank >= 1 && rank <= 5, UG_ERR_WEIGHT, std::string("unsupported weight rank: ") + key);
+      UG_CHECK(dtypes[i] >= 0 && dtypes[i] <= 2, UG_ERR_INVALID, "bad dtype");
+      Weight& w = ws[i];
+      long long numel = 1;
+      for (int k = 0; k < rank; ++k) numel *= shape[k];
+      w.numel = numel;
+      ConvertDesc& d = descs[i];
+      d.src = dev_ptrs[i]; d.total = numel; d.src_dtype = dtypes[i]; d.first_block = blocks;
+      if (rank == 1) {
+        w.is_f32 = 1;
+        w.cout = (int)shape[0];
+        w.p = c.dmalloc((size_t)numel * 4);
+        d.dst_fmt = 2; d.cout = w.cout; d.cin = d.cin_pad = d.taps = 1;
+      } else {
+        w.cout = (int)shape[0];
+        w.cin = (int)shape[1];
+        w.taps = 1;
+        for (int k = 2; k < rank; ++k) w.taps *= (int)shape[k];
+        UG_CHECK(w.taps == 1 || w.taps == 3 || w.taps == 9, UG_ERR_WEIGHT, std::string("unsupported kernel size: ") + key);
+        w.cin_pad = (w.cin + 7) & ~7;
+        const size_t bytes = (size_t)w.taps * w.cout * w.cin_pad * 2;
+        w.p = c.dmalloc(bytes);
+        if (w.cin_pad != w.cin) UG_CUDA(cudaMemsetAsync(w.p, 0, bytes, st));
+        d.dst_fmt = weight_fmt(c, key); d.cout = w.cout; d.cin = w.cin; d.cin_pad = w.cin_pad; d.taps = w.taps;
+        w.cin = w.cin_pad;
+      }
+      d.dst = w.p;
+      long long nb = (numel + 256 * 16 - 1) / (256 * 16);       // 16 elements per thread, 1..2048 CTAs per tensor
+      blocks += nb < 1 ? 1 : (nb > 2048 ? 2048 : nb);
+    }
+    ConvertDesc* dd = nullptr;
+    UG_CUDA(cudaMalloc(&dd, descs.size() * sizeof(ConvertDesc)));
+    cudaError_t e = cudaMemcpyAsync(dd, descs.data(), descs.size() * sizeof(ConvertDesc), cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = (cudaError_t)launch_convert_batch(dd, n, blocks, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(dd);
+    UG_CUDA(e);
+    c.launches++;
+    for (int i = 0; i < n; ++i) {
+      Weight& w = ws[i];
+      if (w.is_f32 && w.numel <= 16) {
+        w.host.resize(w.numel);
+        UG_CUDA(cudaMemcpy(w.host.data(), w.p, (size_t)w.numel * 4, cudaMemcpyDeviceToHost));
+      }
+      c.weights[keys[i]] = w;
+    }
+    c.finalized = false;
+    ++c.ptr_epoch;
+  });
+}
+
 int ug_ctx_set_vae_encode_dtype(ug_ctx* u, int dtype) {
   return guard([&] {
     UG_CHECK(u, UG_ERR_INVALID, "null ctx");

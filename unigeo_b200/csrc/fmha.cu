@@ -40,8 +40,30 @@ constexpr int kOffBar = kOffP + 8 * kTile;
 constexpr int kSmem = kOffBar + 256;
 constexpr int kThreads = 320;
 constexpr uint32_t kColS = 0, kColO = 256;
+constexpr int kPolyDefault = 4;   // measured (L0, 25 x 3072 tokens): 508 us all-MUFU, 462 / 474 / 512 us with every 4th / 3rd / 2nd pair
 
-template <int FMT>
+// 2^x for a pair on the FMA / ALU pipes instead of the MUFU (4 ex2 per clock and SM partition is the kernel's
+// co-binding resource next to the TMEM read port): round-to-nearest split x = r + f by the 1.5 * 2^23 trick, degree-3
+// minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, below the 16-bit rounding P gets anyway: 4.9e-4 fp16,
+// 3.9e-3 bf16), r added into the exponent field.  x is clamped to [-120, 126]: below, 2^x is 0 in 16 bit anyway;
+// above, the result still exceeds the rescale threshold (256), which sends the block down the exact route.
+__device__ __forceinline__ float2 ex2_poly2(float2 x) {
+  x.x = fminf(fmaxf(x.x, -120.0f), 126.0f);
+  x.y = fminf(fmaxf(x.y, -120.0f), 126.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 j = __fadd2_rn(x, magic);                                   // low mantissa bits = round(x)
+  const float2 r = __fadd2_rn(j, make_float2(-12582912.0f, -12582912.0f));
+  const float2 f = __fadd2_rn(x, make_float2(-r.x, -r.y));
+  float2 p = __ffma2_rn(f, make_float2(0.05517132207751274f, 0.05517132207751274f),
+                        make_float2(0.24261054396629333f, 0.24261054396629333f));
+  p = __ffma2_rn(p, f, make_float2(0.6932609677314758f, 0.6932609677314758f));
+  p = __ffma2_rn(p, f, make_float2(0.9999281167984009f, 0.9999281167984009f));
+  return make_float2(__int_as_float(__float_as_int(p.x) + (__float_as_int(j.x) << 23)),
+                     __int_as_float(__float_as_int(p.y) + (__float_as_int(j.y) << 23)));
+}
+
+// POLY: every POLY-th pair of a chunk takes ex2_poly2 instead of two MUFU ex2 (0 = none)
+template <int FMT, int POLY>
 __global__ void __launch_bounds__(kThreads, 1)
 fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ FmhaArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -195,7 +217,9 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
         const float2 t = __ffma2_rn(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), sc2, nm2);
-        float2 pp = make_float2(ex2_approx(t.x), ex2_approx(t.y));
+        float2 pp;
+        if (POLY > 0 && ((i >> 1) % (POLY > 0 ? POLY : 1)) == (POLY > 1 ? 1 : 0)) pp = ex2_poly2(t);
+        else pp = make_float2(ex2_approx(t.x), ex2_approx(t.y));
         if constexpr (MASK) {
           if (c * 32 + i >= valid) pp.x = 0.f;
           if (c * 32 + i + 1 >= valid) pp.y = 0.f;
@@ -343,17 +367,25 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
 }  // namespace
 
 int launch_fmha_d64(const CUtensorMap& tm, const FmhaArgs& args, cudaStream_t stream) {
+  using Kern = void (*)(const CUtensorMap, const FmhaArgs);
+  // UG_FMHA_POLY = n: every n-th pair of exponentials on the FMA pipe (0 = all on the MUFU); default kPolyDefault
+  static const int poly = [] { const char* e = getenv("UG_FMHA_POLY"); return e ? atoi(e) : kPolyDefault; }();
+  static Kern table[2][5] = {{fmha_d64_kernel<0, 0>, nullptr, fmha_d64_kernel<0, 2>, fmha_d64_kernel<0, 3>, fmha_d64_kernel<0, 4>},
+                             {fmha_d64_kernel<1, 0>, nullptr, fmha_d64_kernel<1, 2>, fmha_d64_kernel<1, 3>, fmha_d64_kernel<1, 4>}};
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(fmha_d64_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(fmha_d64_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
-    if (e != cudaSuccess) return (int)e;
+    for (int f = 0; f < 2; ++f)
+      for (int q = 0; q < 5; ++q)
+        if (table[f][q] != nullptr) {
+          cudaError_t e = cudaFuncSetAttribute(table[f][q], cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+          if (e != cudaSuccess) return (int)e;
+        }
     configured = true;
   }
   if (args.C != args.heads * 64 || (args.C & 7)) return (int)cudaErrorInvalidValue;
+  const int pq = (poly >= 2 && poly <= 4) ? poly : 0;
   dim3 grid((args.N + 255) / 256, args.heads, args.F);
-  return (int)launch_pdl(args.fmt ? fmha_d64_kernel<1> : fmha_d64_kernel<0>, grid, dim3(kThreads), kSmem, stream, tm, args);
+  return (int)launch_pdl(table[args.fmt ? 1 : 0][pq], grid, dim3(kThreads), kSmem, stream, tm, args);
 }
 
 }  // namespace ug

@@ -1235,6 +1235,38 @@ __global__ void convert_f32_kernel(const void* __restrict__ src, int sd, float* 
                      : __half2float(reinterpret_cast<const __half*>(src)[i]);
 }
 
+// Whole state dicts in ONE launch (ug_ctx_load_weights): block b serves tensor t with first_block[t] <= b <
+// first_block[t + 1]; matrices go [cout][cin][taps] -> [tap][cout][cin_pad] 16-bit, vectors -> fp32.
+__global__ void __launch_bounds__(256) convert_batch_kernel(const ConvertDesc* __restrict__ d, int n) {
+  int lo = 0, hi = n - 1;
+  while (lo < hi) {                                   // last tensor whose first block is <= blockIdx.x
+    const int mid = (lo + hi + 1) >> 1;
+    if (d[mid].first_block <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
+  }
+  const ConvertDesc t = d[lo];
+  const long long nb = (lo + 1 < n ? d[lo + 1].first_block : (long long)gridDim.x) - t.first_block;
+  const long long start = ((long long)blockIdx.x - t.first_block) * 256 + threadIdx.x, step = nb * 256;
+  auto load = [&](long long s_) -> float {
+    return t.src_dtype == 2 ? reinterpret_cast<const float*>(t.src)[s_]
+         : t.src_dtype == 1 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(t.src)[s_])
+                            : __half2float(reinterpret_cast<const __half*>(t.src)[s_]);
+  };
+  if (t.dst_fmt == 2) {
+    for (long long i = start; i < t.total; i += step) reinterpret_cast<float*>(t.dst)[i] = load(i);
+    return;
+  }
+  for (long long i = start; i < t.total; i += step) {
+    const int ci = (int)(i % t.cin);
+    const long long r = i / t.cin;
+    const int co = (int)(r % t.cout);
+    const int tap = (int)(r / t.cout);
+    const float v = load(((long long)co * t.cin + ci) * t.taps + tap);
+    const long long o = ((long long)tap * t.cout + co) * t.cin_pad + ci;
+    if (t.dst_fmt == 1) reinterpret_cast<__nv_bfloat16*>(t.dst)[o] = __float2bfloat16_rn(v);
+    else reinterpret_cast<__half*>(t.dst)[o] = __float2half_rn(v);
+  }
+}
+
 inline int grid_for(long long total, int block, int cap = 148 * 16) {
   long long g = (total + block - 1) / block;
   if (g > cap) g = cap;
@@ -1664,6 +1696,12 @@ int launch_convert_weight(const void* src, int src_dtype, void* dst, int Cout, i
   const long long total = (long long)Cout * Cin * taps;
   UG_DISPATCH_FMT(fmt, (convert_weight_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
                            src, src_dtype, reinterpret_cast<T*>(dst), Cout, Cin, CinPad, taps)));
+  return last_err();
+}
+
+int launch_convert_batch(const ConvertDesc* dev_descs, int n, long long total_blocks, cudaStream_t st) {
+  if (n <= 0) return 0;
+  convert_batch_kernel<<<(unsigned)total_blocks, 256, 0, st>>>(dev_descs, n);
   return last_err();
 }
 

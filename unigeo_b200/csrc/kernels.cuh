@@ -127,6 +127,17 @@ int launch_frames_out(const void* x, long long pixels, float* y, int fmt, cudaSt
 // weights: src fp32/16-bit [Cout][Cin][taps] -> dst 16-bit [taps][Cout][CinPad] (dst pre-zeroed when padded)
 int launch_convert_weight(const void* src, int src_dtype /*0 f16,1 bf16,2 f32*/, void* dst, int Cout, int Cin,
                           int CinPad, int taps, int fmt, cudaStream_t st);
+// one launch for a whole state dict: descriptors (device memory) sorted by first_block; dst_fmt 0 fp16 / 1 bf16 matrix
+// ([cout][cin][taps] -> [tap][cout][cin_pad]), 2 fp32 vector copy
+struct ConvertDesc {
+  const void* src;
+  void* dst;
+  long long total;         // source elements
+  long long first_block;   // first CTA serving this tensor
+  int src_dtype, dst_fmt;
+  int cout, cin, cin_pad, taps;
+};
+int launch_convert_batch(const ConvertDesc* dev_descs, int n, long long total_blocks, cudaStream_t st);
 int launch_convert_f32(const void* src, int src_dtype, float* dst, long long n, cudaStream_t st);
 
 }  // namespace ug

@@ -67,6 +67,7 @@ class Engine:
     def load_state_dict(self, prefix: str, sd: Dict[str, torch.Tensor]) -> None:
         """``prefix`` is "unet" or "vae"; ``sd`` maps diffusers keys to tensors (any device/dtype)."""
         with torch.cuda.device(self.device):
+            keep, keys = [], []
             for key, t in sd.items():
                 if t.dtype not in _TORCH_TO_UG:
                     t = t.float()
@@ -75,10 +76,25 @@ class Engine:
                         t = t.reshape(t.shape[0], -1)
                     elif key.endswith("position_embedding.weight"):
                         t = t.reshape(-1)
-                t = t.to(self.device).contiguous()
-                shape = (C.c_int64 * t.dim())(*t.shape)
-                _lib.check(self.lib.ug_ctx_load_weight(self._ctx, f"{prefix}.{key}".encode(), t.data_ptr(),
-                                                       _TORCH_TO_UG[t.dtype], shape, t.dim(), _stream()))
+                keep.append(t.to(self.device).contiguous())
+                keys.append(f"{prefix}.{key}".encode())
+            # the whole dict in slices of <= 256 MB of staged source tensors: ONE conversion launch per slice
+            i0 = 0
+            while i0 < len(keep):
+                i1, nbytes = i0, 0
+                while i1 < len(keep) and (i1 == i0 or nbytes + keep[i1].numel() * keep[i1].element_size() <= (1 << 28)):
+                    nbytes += keep[i1].numel() * keep[i1].element_size()
+                    i1 += 1
+                n = i1 - i0
+                shapes = (C.c_int64 * (5 * n))()
+                for j, t in enumerate(keep[i0:i1]):
+                    for k, d in enumerate(t.shape):
+                        shapes[5 * j + k] = d
+                _lib.check(self.lib.ug_ctx_load_weights(
+                    self._ctx, n, (C.c_char_p * n)(*keys[i0:i1]), (C.c_void_p * n)(*[t.data_ptr() for t in keep[i0:i1]]),
+                    (C.c_int * n)(*[_TORCH_TO_UG[t.dtype] for t in keep[i0:i1]]), shapes,
+                    (C.c_int * n)(*[t.dim() for t in keep[i0:i1]]), _stream()))
+                i0 = i1
             torch.cuda.current_stream().synchronize()
         self._finalized = False
 
