@@ -64,9 +64,12 @@ def test_cfg5_denoising_step_is_finite_and_deterministic(engine, cuda):
     e.set_clip_context(torch.randn(T, cfg.clip_embed_dim, generator=g, device=cuda))
     ids = [cfg.fps_id, cfg.motion_bucket_id, cfg.noise_aug_strength]
     a = e.denoise(cond, noise, ids, 1).clone()
-    b = e.denoise(cond, noise, ids, 1).clone()
+    # eager call, graph capture, then replays: this size is where an intermittent (1 in 10) deviation under programmatic
+    # dependent launch showed up (profiles/r02_pdl_race.txt); 16 calls make a regression visible with p = 0.8
+    outs = [e.denoise(cond, noise, ids, 1).clone() for _ in range(15)]
     torch.cuda.synchronize()
-    assert torch.isfinite(a).all() and torch.equal(a, b)
+    assert torch.isfinite(a).all()
+    assert all(torch.equal(a, b) for b in outs), [float((a - b).abs().max()) for b in outs]
     assert e.workspace_bytes() < 60 * 2 ** 30                                   # one clip fits a fraction of 180 GB
 
 

@@ -902,11 +902,13 @@ int ug_op_linear(int dtype, const void* x, long long M, int K, const void* W, in
                  const void* res, int geglu, int out_fp32, void* y, void* stream) {
   return guard([&] {
     ug_ctx* u = scratch_ctx(dtype);
-    u->c.stream = reinterpret_cast<cudaStream_t>(stream);
     Epi e;
     const int nout = geglu ? N / 2 : N;
     e.out = y; e.ldc = nout; e.out_fp32 = out_fp32; e.bias = bias; e.res = res; e.ldr = nout; e.geglu = geglu;
-    op_linear(u->c, x, M, K, K, W, N, e);
+    // sized run: a launch the tile picker splits along K needs workspace for its fp32 partials
+    const std::string sig = "lin:" + std::to_string(M) + ":" + std::to_string(K) + ":" + std::to_string(N) + ":" +
+                            std::to_string(geglu) + std::to_string(out_fp32) + (res ? "r" : "");
+    run_sized(u, sig, stream, [&](Ctx& c) { op_linear(c, x, M, K, K, W, N, e); });
   });
 }
 
@@ -914,10 +916,11 @@ int ug_op_conv3x3(int dtype, const void* x, int Nf, int H, int W, int C, const v
                   int asym_pad, const float* bias, const void* res, void* y, void* stream) {
   return guard([&] {
     ug_ctx* u = scratch_ctx(dtype);
-    u->c.stream = reinterpret_cast<cudaStream_t>(stream);
     Epi e;
     e.out = y; e.ldc = Cout; e.bias = bias; e.res = res; e.ldr = Cout;
-    op_conv3x3(u->c, x, Nf, H, W, C, Wt, Cout, stride, asym_pad, e);
+    const std::string sig = "conv:" + std::to_string(Nf) + ":" + std::to_string(H) + ":" + std::to_string(W) + ":" +
+                            std::to_string(C) + ":" + std::to_string(Cout) + ":" + std::to_string(stride) + (res ? "r" : "");
+    run_sized(u, sig, stream, [&](Ctx& c) { op_conv3x3(c, x, Nf, H, W, C, Wt, Cout, stride, asym_pad, e); });
   });
 }
 
@@ -925,10 +928,11 @@ int ug_op_tconv3(int dtype, const void* x, int T, long long P, int C, const void
                  const float* bias, const void* res, const void* blend, float alpha, void* y, void* stream) {
   return guard([&] {
     ug_ctx* u = scratch_ctx(dtype);
-    u->c.stream = reinterpret_cast<cudaStream_t>(stream);
     Epi e;
     e.out = y; e.ldc = Cout; e.bias = bias; e.res = res; e.ldr = Cout; e.blend = blend; e.ldb = Cout; e.alpha = alpha;
-    op_tconv3(u->c, x, T, P, C, Wt, Cout, chunk, e);
+    const std::string sig = "tconv:" + std::to_string(T) + ":" + std::to_string(P) + ":" + std::to_string(C) + ":" +
+                            std::to_string(Cout) + ":" + std::to_string(chunk) + (res ? "r" : "") + (blend ? "b" : "");
+    run_sized(u, sig, stream, [&](Ctx& c) { op_tconv3(c, x, T, P, C, Wt, Cout, chunk, e); });
   });
 }
 

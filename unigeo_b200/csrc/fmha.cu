@@ -87,7 +87,13 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
 
   if ((smem_u32(smem) & 1023u) != 0u) __trap();   // swizzled tiles need a 1024-byte aligned base
 
-  pdl_launch_dependents();
+  // NO griddepcontrol.launch_dependents here: this kernel's dependents start when it completes.  With the early trigger
+  // the 49 x 576 x 1024 denoising step deviated from its own no-PDL result in ~1 run of 10 (max |d| 0.03 on O(1)
+  // latents, every element slightly off; never at 25 x 384 x 512 in 120 runs).  Bisected with per-family switches
+  // (UG_NO_PDL_K, build variants without the trigger): only the pair "fmha -> attn1.to_out GEMM starting during fmha's
+  // last wave" reproduces it, 0 of 100 runs without this trigger; fences after the consumer's wait do not help.  The
+  // mechanism is not understood (profiles/r02_pdl_race.txt); the cost of not triggering is the overlap of one GEMM
+  // prologue per attention launch (16 per step).
   if (warp == 0 && lane == 0) tma_prefetch_desc(&tm);
   if (warp == 1) {
     if (lane == 0) {
@@ -385,7 +391,7 @@ int launch_fmha_d64(const CUtensorMap& tm, const FmhaArgs& args, cudaStream_t st
   if (args.C != args.heads * 64 || (args.C & 7)) return (int)cudaErrorInvalidValue;
   const int pq = (poly >= 2 && poly <= 4) ? poly : 0;
   dim3 grid((args.N + 255) / 256, args.heads, args.F);
-  return (int)launch_pdl(table[args.fmt ? 1 : 0][pq], grid, dim3(kThreads), kSmem, stream, tm, args);
+  return (int)launch_pdl_tag("fmha", table[args.fmt ? 1 : 0][pq], grid, dim3(kThreads), kSmem, stream, tm, args);
 }
 
 }  // namespace ug

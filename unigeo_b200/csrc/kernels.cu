@@ -2,6 +2,29 @@
 #include "kernels.cuh"
 #include "ptx.cuh"
 
+// bisecting aid: -DUG_NOTRIG_GN / _LN / _ATT / _MISC build variants in which a kernel family never releases its
+// dependents early (they start when it completes)
+#ifdef UG_NOTRIG_GN
+#define UG_TRIGGER_GN() do {} while (0)
+#else
+#define UG_TRIGGER_GN() pdl_launch_dependents()
+#endif
+#ifdef UG_NOTRIG_LN
+#define UG_TRIGGER_LN() do {} while (0)
+#else
+#define UG_TRIGGER_LN() pdl_launch_dependents()
+#endif
+#ifdef UG_NOTRIG_ATT
+#define UG_TRIGGER_ATT() do {} while (0)
+#else
+#define UG_TRIGGER_ATT() pdl_launch_dependents()
+#endif
+#ifdef UG_NOTRIG_MISC
+#define UG_TRIGGER_MISC() do {} while (0)
+#else
+#define UG_TRIGGER_MISC() pdl_launch_dependents()
+#endif
+
 #include <atomic>
 #include <map>
 #include <mutex>
@@ -69,7 +92,7 @@ __global__ void __launch_bounds__(320, 3) gn_stats_kernel(const void* __restrict
                                 long long rows_per_set, long long chunk_rows, int G, int cs,
                                 float* __restrict__ part, float* __restrict__ mr, unsigned int* __restrict__ counters,
                                 float inv_cnt, float eps) {
-  pdl_launch_dependents();
+  UG_TRIGGER_GN();
   pdl_wait();
   extern __shared__ float s_part[];   // [rpb][C] sums, then [rpb][C] sumsq
   __shared__ int s_last;
@@ -94,7 +117,7 @@ __global__ void __launch_bounds__(320, 3) gn_stats_kernel(const void* __restrict
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const long long rk = r + (long long)k * rpb;
-        u[k] = rk < r_end ? __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
+        u[k] = rk < r_end ? ld_act(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
@@ -182,7 +205,7 @@ gn_fused_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x
                 long long chunk_rows, int G, int cs, float* __restrict__ part, float* __restrict__ mr,
                 unsigned int* __restrict__ counters, float inv_cnt, float eps, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int silu, void* __restrict__ y) {
-  pdl_launch_dependents();
+  UG_TRIGGER_GN();
   pdl_wait();
   extern __shared__ float s_dyn[];
   __shared__ int s_last;
@@ -207,7 +230,7 @@ gn_fused_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const long long rk = r + (long long)k * rpb;
-          u[k] = rk < r_end ? __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
+          u[k] = rk < r_end ? ld_act(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
@@ -338,7 +361,7 @@ gn_fused_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const long long rk = r + (long long)k * rpb;
-          u[k] = rk < r_end ? __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
+          u[k] = rk < r_end ? ld_act(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -378,7 +401,7 @@ __global__ void __launch_bounds__(320)
 gn_cluster_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2, long long rows_per_set,
                   int chunk_rows, int G, int cs, float inv_cnt, float eps, const float* __restrict__ gamma,
                   const float* __restrict__ beta, int silu, void* __restrict__ y) {
-  pdl_launch_dependents();
+  UG_TRIGGER_GN();
   extern __shared__ __align__(16) unsigned char s_cl[];
   const int nvec = nv1 + nv2;
   const int C = nvec * 8;
@@ -418,7 +441,7 @@ gn_cluster_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int rk = r + k * rpb;
-          u[k] = rk < nrows ? __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r_begin + rk, c8))
+          u[k] = rk < nrows ? ld_act(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + r_begin + rk, c8))
                             : make_uint4(0u, 0u, 0u, 0u);
         }
 #pragma unroll
@@ -553,7 +576,7 @@ __global__ void __launch_bounds__(320, 3) gn_apply_kernel(const void* __restrict
                                 const float* __restrict__ part /* [sets][G] (mean, rstd) */,
                                 const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
                                 void* __restrict__ y) {
-  pdl_launch_dependents();
+  UG_TRIGGER_GN();
   pdl_wait();
   extern __shared__ float s_ab[];   // [C] scale, [C] shift, [G] mean, [G] rstd
   const int nvec = nv1 + nv2;
@@ -564,8 +587,8 @@ __global__ void __launch_bounds__(320, 3) gn_apply_kernel(const void* __restrict
   float* s_rstd = s_mean + G;
   const long long set = blockIdx.y;
   if (threadIdx.x < G) {
-    s_mean[threadIdx.x] = part[(set * G + threadIdx.x) * 2 + 0];
-    s_rstd[threadIdx.x] = part[(set * G + threadIdx.x) * 2 + 1];
+    s_mean[threadIdx.x] = ld_act(part + (set * G + threadIdx.x) * 2 + 0);      // written by the previous kernel
+    s_rstd[threadIdx.x] = ld_act(part + (set * G + threadIdx.x) * 2 + 1);
   }
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -594,7 +617,7 @@ __global__ void __launch_bounds__(320, 3) gn_apply_kernel(const void* __restrict
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
       const long long rk = r + (long long)k * rpb;
-      u[k] = rk < r_end ? __ldg(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
+      u[k] = rk < r_end ? ld_act(cat_ptr(x1, nv1, x2, nv2, set * rows_per_set + rk, c8)) : make_uint4(0u, 0u, 0u, 0u);
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
@@ -622,7 +645,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, const float* __restrict__ add, int add_div,
                  void* __restrict__ y) {
-  pdl_launch_dependents();
+  UG_TRIGGER_LN();
   pdl_wait();
   constexpr int RPW = 32 / LPR;                       // rows per warp
   const int lane = threadIdx.x & 31;
@@ -636,7 +659,7 @@ layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float*
   for (int k = 0; k < VPL; ++k) {
     const int i = sub + LPR * k;
     raw[k] = make_uint4(0u, 0u, 0u, 0u);
-    if (rok && i < nvec) raw[k] = __ldg(xb + i);
+    if (rok && i < nvec) raw[k] = ld_act(xb + i);
   }
   float2 f[VPL][4];
   const float* addr = (add && rok) ? add + (row / add_div) * C : nullptr;
@@ -781,7 +804,7 @@ template <typename T, int TPAD>
 __global__ void __launch_bounds__(128)
 temporal_attn_kernel(const void* __restrict__ qkv, void* __restrict__ out, int Tn, long long P, int C,
                      float scale_log2e) {
-  pdl_launch_dependents();
+  UG_TRIGGER_ATT();
   pdl_wait();
   extern __shared__ __align__(128) uint8_t sm_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -909,7 +932,7 @@ template <typename T, int KPAD>
 __global__ void __launch_bounds__(128)
 cross_attn_kernel(const void* __restrict__ q, int ldq, const void* __restrict__ kv, void* __restrict__ out, int N,
                   int C, int Lk, long long kv_frame_rows, float scale_log2e) {
-  pdl_launch_dependents();
+  UG_TRIGGER_ATT();
   pdl_wait();
   extern __shared__ __align__(128) uint8_t sm_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1028,29 +1051,28 @@ cross_attn_kernel(const void* __restrict__ q, int ldq, const void* __restrict__ 
 // ------------------------------------------------------------------ 2-D (StableNormal) scheduler glue
 // DDIM step, prediction_type = "sample", eta = 0, in place on fp32 latents:
 //   x <- c_x0 * x0 + c_x * x   with  c_x = sqrt((1-a_prev)/(1-a_t)),  c_x0 = sqrt(a_prev) - sqrt(a_t) * c_x
-__global__ void axpby_kernel(float* __restrict__ x, const float* __restrict__ x0, float c_x0, float c_x,
-                             long long n) {
-  pdl_launch_dependents();
+__global__ void axpby_kernel(float* x, const float* x0, float c_x0, float c_x, long long n) {
+  UG_TRIGGER_MISC();
   pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    x[i] = c_x0 * x0[i] + c_x * x[i];
+    x[i] = c_x0 * ld_act(x0 + i) + c_x * x[i];
 }
 // fp32 [tokens][Cs] -> 16-bit [tokens][Cd] (Cd >= Cs, zero padded): the UNet input of the 2-D path
 template <typename T>
-__global__ void f32_to_tokens_kernel(const float* __restrict__ x, int Cs, int Cd, long long tokens, T* __restrict__ y) {
-  pdl_launch_dependents();
+__global__ void f32_to_tokens_kernel(const float* x, int Cs, int Cd, long long tokens, T* __restrict__ y) {
+  UG_TRIGGER_MISC();
   pdl_wait();
   const long long n = tokens * Cd;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const long long t = i / Cd;
     const int c = (int)(i % Cd);
-    y[i] = Elem<T>::from_f(c < Cs ? x[t * Cs + c] : 0.f);
+    y[i] = Elem<T>::from_f(c < Cs ? ld_act(x + t * Cs + c) : 0.f);
   }
 }
 // decoded normals: 16-bit NHWC [N][HW][Cs] (3 valid) -> unit vectors, clip, 8-bit HWC [N][HW][3]
 template <typename T>
-__global__ void normals_to_u8_kernel(const T* __restrict__ x, int Cs, long long pixels, uint8_t* __restrict__ y) {
-  pdl_launch_dependents();
+__global__ void normals_to_u8_kernel(const T* x, int Cs, long long pixels, uint8_t* y) {   // x: no read-only path (PDL)
+  UG_TRIGGER_MISC();
   pdl_wait();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
     const float a = Elem<T>::to_f(x[i * Cs]), b = Elem<T>::to_f(x[i * Cs + 1]), c = Elem<T>::to_f(x[i * Cs + 2]);
@@ -1072,18 +1094,18 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
     const int ox = (int)(r % (2 * W)); r /= (2 * W);
     const int oy = (int)(r % (2 * H));
     const long long n = r / (2 * H);
-    y[i] = __ldg(x + ((n * H + (oy >> 1)) * W + (ox >> 1)) * nvec + c8);
+    y[i] = ld_act(x + ((n * H + (oy >> 1)) * W + (ox >> 1)) * nvec + c8);
   }
 }
 __global__ void concat_kernel(const void* __restrict__ x1, int nv1, const void* __restrict__ x2, int nv2,
                               long long rows, uint4* __restrict__ y) {
-  pdl_launch_dependents();
+  UG_TRIGGER_MISC();
   pdl_wait();
   const int nvec = nv1 + nv2;
   const long long total = rows * nvec;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x)
-    y[i] = __ldg(cat_ptr(x1, nv1, x2, nv2, i / nvec, (int)(i % nvec)));
+    y[i] = ld_act(cat_ptr(x1, nv1, x2, nv2, i / nvec, (int)(i % nvec)));
 }
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, const float* __restrict__ noise, float ns,
@@ -1235,6 +1257,62 @@ __global__ void convert_f32_kernel(const void* __restrict__ src, int sd, float* 
                      : __half2float(reinterpret_cast<const __half*>(src)[i]);
 }
 
+// Split-K reduce (tapgemm ksplit > 1): out[m][n] = epilogue(sum_s part[s][m][n]) with the partials added in index order
+// (deterministic) and the epilogue of the fused path in the same order: * scale, + bias, + frame bias, GELU, + residual,
+// blend.  4 columns per thread (N % 4 == 0).
+template <typename T>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* part, int S, long long M, int N, const float* __restrict__ bias,
+                     const float* __restrict__ fbias, int fbias_ld, int fbias_div, const T* res, long long ldr,
+                     const T* blend, long long ldb, float alpha, float scale, int act, void* out, long long ldc,
+                     int out_fp32) {
+  const int nq = N >> 2;
+  const long long total = M * nq, slab = M * (long long)N;
+  UG_TRIGGER_MISC();
+  pdl_wait();
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / nq;
+    const int n = (int)(i - m * nq) << 2;
+    const float* p = part + m * N + n;
+    float4 acc = ld_act(reinterpret_cast<const float4*>(p));
+    for (int s_ = 1; s_ < S; ++s_) {
+      const float4 v = ld_act(reinterpret_cast<const float4*>(p + (long long)s_ * slab));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    float f[4] = {acc.x * scale, acc.y * scale, acc.z * scale, acc.w * scale};
+    if (bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] += bias[n + j];
+    }
+    if (fbias != nullptr) {
+      const float* fb = fbias + (m / fbias_div) * fbias_ld + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] += fb[j];
+    }
+    if (act == 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = 0.5f * f[j] * (1.0f + erff(f[j] * 0.70710678118654752f));
+    }
+    if (res != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] += Elem<T>::to_f(res[m * ldr + n + j]);
+    }
+    if (blend != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) f[j] = alpha * Elem<T>::to_f(blend[m * ldb + n + j]) + (1.0f - alpha) * f[j];
+    }
+    if (out_fp32) {
+      float* o = reinterpret_cast<float*>(out) + m * ldc + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = f[j];
+    } else {
+      T* o = reinterpret_cast<T*>(out) + m * ldc + n;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) o[j] = Elem<T>::from_f(f[j]);
+    }
+  }
+}
+
 // Whole state dicts in ONE launch (ug_ctx_load_weights): block b serves tensor t with first_block[t] <= b <
 // first_block[t + 1]; matrices go [cout][cin][taps] -> [tap][cout][cin_pad] 16-bit, vectors -> fp32.
 __global__ void __launch_bounds__(256) convert_batch_kernel(const ConvertDesc* __restrict__ d, int n) {
@@ -1315,7 +1393,7 @@ int launch_gn_stats(const void* x1, int C1, const void* x2, int C2, long long ro
   float* mr = stats + sets * g.chunks * G * 2;
   const float inv_cnt = 1.0f / ((float)rows_per_set * (float)(C / G));
   cudaError_t err;
-  UG_DISPATCH_FMT(fmt, (err = launch_pdl(gn_stats_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("gn_stats", gn_stats_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
                                          rows_per_set, g.chunk_rows, G, C / G, stats, mr, counters, inv_cnt, eps)));
   return (int)err;
 }
@@ -1382,7 +1460,7 @@ int launch_gn_fused(const void* x1, int C1, const void* x2, int C2, long long ro
   static std::atomic<int> coop{[] { const char* e = getenv("UG_GN_COOP"); return e ? atoi(e) : 1; }()};
   cudaError_t err = cudaSuccess;
   if (coop.load() != 0) {
-    static const bool no_pdl = getenv("UG_NO_PDL") != nullptr;
+    static const bool no_pdl = pdl_off("gn_fused");
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(g.threads);
@@ -1405,7 +1483,7 @@ int launch_gn_fused(const void* x1, int C1, const void* x2, int C2, long long ro
     cudaGetLastError();
     coop.store(0);
   }
-  UG_DISPATCH_FMT(fmt, (err = launch_pdl(gn_fused_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("gn_fused", gn_fused_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
                                          rows_per_set, chunk_rows, G, C / G, stats, mr, counters, inv_cnt, eps, gamma,
                                          beta, silu, y)));
   return (int)err;
@@ -1433,7 +1511,7 @@ int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long ro
   const float* mr = stats + sets * g.chunks * G * 2;
   (void)eps;
   cudaError_t err;
-  UG_DISPATCH_FMT(fmt, (err = launch_pdl(gn_apply_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("gn_apply", gn_apply_kernel<T>, grid, dim3(g.threads), smem, st, x1, C1 / 8, x2, C2 / 8,
                                          rows_per_set, g.chunk_rows, G, C / G, mr, gamma, beta, silu, y)));
   return (int)err;
 }
@@ -1476,7 +1554,7 @@ int launch_gn_cluster(const void* x1, int C1, const void* x2, int C2, long long 
   cfg.blockDim = dim3((unsigned)threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  static const bool no_pdl = getenv("UG_NO_PDL") != nullptr;
+  static const bool no_pdl = pdl_off("gn_cluster");
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)S;
@@ -1500,7 +1578,7 @@ int launch_ln_t(const void* x, long long rows, int C, const float* gamma, const 
   const long long rows_per_block = (long long)wpb * (32 / LPR);
   const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
   cudaError_t err;
-  UG_DISPATCH_FMT(fmt, (err = launch_pdl(layernorm_kernel<T, LPR, VPL>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, C,
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("layernorm", layernorm_kernel<T, LPR, VPL>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, C,
                                          gamma, beta, eps, add, add_div > 0 ? add_div : 1, y)));
   return (int)err;
 }
@@ -1550,7 +1628,7 @@ int launch_temporal_attention(const void* qkv, void* out, int Tn, long long P, i
   if (Tn <= 32) {
     const size_t smem = (size_t)wpb * 3 * 32 * 128;
     cudaError_t err;
-    UG_DISPATCH_FMT(fmt, (err = launch_pdl(temporal_attn_kernel<T, 32>, dim3(grid), dim3(wpb * 32), smem, st, qkv, out,
+    UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("tattn", temporal_attn_kernel<T, 32>, dim3(grid), dim3(wpb * 32), smem, st, qkv, out,
                                            Tn, P, C, sl)));
     return (int)err;
   } else {
@@ -1562,7 +1640,7 @@ int launch_temporal_attention(const void* qkv, void* out, int Tn, long long P, i
       configured = true;
     }
     cudaError_t err;
-    UG_DISPATCH_FMT(fmt, (err = launch_pdl(temporal_attn_kernel<T, 64>, dim3(grid), dim3(wpb * 32), smem, st, qkv, out,
+    UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("tattn", temporal_attn_kernel<T, 64>, dim3(grid), dim3(wpb * 32), smem, st, qkv, out,
                                            Tn, P, C, sl)));
     return (int)err;
   }
@@ -1579,7 +1657,7 @@ int launch_cross_attention(const void* q, int ldq, const void* kv, void* out, in
   cudaError_t err = cudaErrorInvalidValue;
 #define UG_XATTN(KP)                                                                                             \
   case KP:                                                                                                       \
-    UG_DISPATCH_FMT(fmt, (err = launch_pdl(cross_attn_kernel<T, KP>, grid, dim3(128), smem, st, q, ldq, kv, out, N, C, \
+    UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("cattn", cross_attn_kernel<T, KP>, grid, dim3(128), smem, st, q, ldq, kv, out, N, C, \
                                            Lk, fr, sl)));                                                        \
     break;
   switch (kpad) {
@@ -1617,7 +1695,7 @@ int launch_upsample2x(const void* x, void* y, int N, int H, int W, int C, cudaSt
 int launch_concat(const void* x1, int C1, const void* x2, int C2, long long rows, void* y, cudaStream_t st) {
   if ((C1 & 7) || (C2 & 7)) return (int)cudaErrorInvalidValue;
   const long long total = rows * ((C1 + C2) / 8);
-  return (int)launch_pdl(concat_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, x1, C1 / 8, x2, C2 / 8, rows,
+  return (int)launch_pdl_tag("concat", concat_kernel, dim3(grid_for(total, 256)), dim3(256), 0, st, x1, C1 / 8, x2, C2 / 8, rows,
                          reinterpret_cast<uint4*>(y));
 }
 
@@ -1697,6 +1775,19 @@ int launch_convert_weight(const void* src, int src_dtype, void* dst, int Cout, i
   UG_DISPATCH_FMT(fmt, (convert_weight_kernel<T><<<grid_for(total, 256), 256, 0, st>>>(
                            src, src_dtype, reinterpret_cast<T*>(dst), Cout, Cin, CinPad, taps)));
   return last_err();
+}
+
+int launch_splitk_reduce(const float* part, int S, long long M, int N, const float* bias, const float* fbias, int fbias_ld,
+                         int fbias_div, const void* res, long long ldr, const void* blend, long long ldb, float alpha,
+                         float scale, int act, void* out, long long ldc, int out_fp32, int fmt, cudaStream_t st) {
+  if ((N & 3) || S < 1) return (int)cudaErrorInvalidValue;
+  const long long total = M * (N >> 2);
+  cudaError_t err;
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("splitk", splitk_reduce_kernel<T>, dim3(grid_for(total, 256, 148 * 8)), dim3(256), 0, st, part, S, M,
+                                         N, bias, fbias, fbias_ld, fbias_div > 0 ? fbias_div : 1,
+                                         reinterpret_cast<const T*>(res), ldr, reinterpret_cast<const T*>(blend), ldb, alpha,
+                                         scale, act, out, ldc, out_fp32)));
+  return (int)err;
 }
 
 int launch_convert_batch(const ConvertDesc* dev_descs, int n, long long total_blocks, cudaStream_t st) {

@@ -127,6 +127,11 @@ int launch_frames_out(const void* x, long long pixels, float* y, int fmt, cudaSt
 // weights: src fp32/16-bit [Cout][Cin][taps] -> dst 16-bit [taps][Cout][CinPad] (dst pre-zeroed when padded)
 int launch_convert_weight(const void* src, int src_dtype /*0 f16,1 bf16,2 f32*/, void* dst, int Cout, int Cin,
                           int CinPad, int taps, int fmt, cudaStream_t st);
+// split-K reduce of tapgemm partials [S][M][N] fp32 -> out (16-bit or fp32, row stride ldc) with the fused epilogue's
+// operations in the fused path's order (N % 4 == 0)
+int launch_splitk_reduce(const float* part, int S, long long M, int N, const float* bias, const float* fbias, int fbias_ld,
+                         int fbias_div, const void* res, long long ldr, const void* blend, long long ldb, float alpha,
+                         float scale, int act, void* out, long long ldc, int out_fp32, int fmt, cudaStream_t st);
 // one launch for a whole state dict: descriptors (device memory) sorted by first_block; dst_fmt 0 fp16 / 1 bf16 matrix
 // ([cout][cin][taps] -> [tap][cout][cin_pad]), 2 fp32 vector copy
 struct ConvertDesc {

@@ -150,14 +150,43 @@ inline bool can_tma_res(const Epi& e, int n_out) {
          (reinterpret_cast<uintptr_t>(e.res) % 16) == 0;
 }
 
+// split-K is available to launches whose epilogue the reduce kernel can reproduce (no GEGLU, N % 4 == 0)
+inline bool can_split(const Epi& e, int n_out) { return !e.geglu && (n_out & 3) == 0; }
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline int imin(int a, int b) { return a < b ? a : b; }
 
 // algorithmic work of one tapgemm launch: 2*M*N*K flops over the REAL (unpadded) extents;
 // bytes = A read once + output written once (16-bit), weights ignored (SURVEY.md §8 convention)
 void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmArgs& a, int batch,
-            const char* what, long long k_real, const CUtensorMap* mc = nullptr, const CUtensorMap* mr = nullptr) {
-  const double M = (double)a.W * a.H * a.N * batch;
+            const char* what, long long k_real, const CUtensorMap* mc = nullptr, const CUtensorMap* mr = nullptr);
+
+// Split-K launch: S partial GEMMs into fp32 workspace slabs + one reduce pass carrying the epilogue `e`.
+// `a` holds the geometry (tiling, taps, n_total, bn_tile, ctas); its epilogue fields are overwritten here.
+void launch_split(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, TapGemmArgs a, int S, const Epi& e,
+                  const char* what, long long k_real) {
+  const long long M = (long long)a.W * a.H * a.N;
+  const size_t mk = c.ws.mark();
+  float* part = c.allocf((long long)S * M * a.n_total);
+  Epi pe;
+  pe.out = part; pe.ldc = a.n_total; pe.out_fp32 = 1;
+  fill_epi(a, pe, c.fmt);
+  a.fbias_uniform = 0;
+  a.tma_store = 0;
+  a.res_tma = 0;
+  a.ksplit = S;
+  a.out_z1stride = M * a.n_total;
+  a.out_z0stride = 0;
+  launch(c, ma, mb, a, S, what, k_real);
+  op_check(c, launch_splitk_reduce(part, S, M, a.n_total, e.bias, e.fbias, e.fbias_ld, e.fbias_div, e.res, e.ldr, e.blend,
+                                   e.ldb, e.alpha, e.scale, e.act, e.out, e.ldc, e.out_fp32, c.fmt, c.stream),
+           "splitk_reduce", 0.0, (double)M * a.n_total * (4.0 * S + 2.0));
+  c.ws.release(mk);
+}
+
+void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmArgs& a, int batch,
+            const char* what, long long k_real, const CUtensorMap* mc, const CUtensorMap* mr) {
+  const double M = (double)a.W * a.H * a.N * (a.ksplit > 1 ? 1 : batch);
   const double flops = 2.0 * M * a.n_total * (double)k_real * a.num_taps;
   const double bytes = M * ((double)k_real + (a.geglu ? a.n_total / 2 : a.n_total)) * 2.0;
   const char* name = what;
@@ -165,7 +194,8 @@ void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmA
     const std::string full = std::string(what) + " M" + std::to_string((long long)M) + " N" + std::to_string(a.n_total) +
                              " K" + std::to_string(k_real * a.num_taps) + " bn" + std::to_string(a.bn_tile) + "x" +
                              std::to_string(a.ctas) + (a.res ? " +res" : "") + (a.blend ? " +blend" : "") +
-                             (a.fbias ? " +fbias" : "") + (a.tma_store ? "" : " direct") + (a.res_tma ? " rtma" : "");
+                             (a.fbias ? " +fbias" : "") + (a.tma_store ? "" : " direct") + (a.res_tma ? " rtma" : "") +
+                             (a.ksplit > 1 ? " splitk" + std::to_string(a.ksplit) : "");
     name = c.prof_names.insert(full).first->c_str();
   }
   op_check(c, launch_tapgemm(ma, mb, mc, a, batch, c.stream, mr), name, flops, bytes);
@@ -174,7 +204,6 @@ void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmA
 }  // namespace
 
 void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const void* Wm, int N, const Epi& e) {
-  if (c.dry) return;
   UG_CHECK((K % 8) == 0 && (ldx % 8) == 0, UG_ERR_INVALID, "linear: K and ldx must be multiples of 8");
   TapGemmArgs a;
   base_args(a);
@@ -188,7 +217,12 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   a.fbias_uniform = (e.fbias != nullptr && (a.fbias_div % 128) == 0) ? 1 : 0;   // tiles = 128 consecutive tokens
   a.tma_store = can_tma_store(e);
   a.res_tma = can_tma_res(e, N) ? 1 : 0;
-  a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
+  int ksplit = 1;
+  a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas, can_split(e, N) ? &ksplit : nullptr);
+  if (c.dry) {                                    // size-only pass: the split-K partials are the op's only workspace
+    if (ksplit > 1) { const size_t mk = c.ws.mark(); c.allocf((long long)ksplit * M * N); c.ws.release(mk); }
+    return;
+  }
   const int bn = a.bn_tile / a.ctas;
   CUtensorMap ma, mb, mc, mr;
   unsigned long long dims[5] = {(unsigned long long)K, (unsigned long long)M, 1, 1, 1};
@@ -196,6 +230,10 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
                               (unsigned long long)ldx * 2 * M, (unsigned long long)ldx * 2 * M};
   make_a_map(&ma, x, c.fmt, dims, st, 128, 1, 1, 1);
   make_b_map(&mb, Wm, c.fmt, K, N, (unsigned long long)K * 2, bn);
+  if (ksplit > 1) {
+    launch_split(c, ma, mb, a, ksplit, e, "tapgemm.linear", K);
+    return;
+  }
   if (a.tma_store) {
     const unsigned long long rb = (unsigned long long)e.ldc * 2;
     unsigned long long od[5] = {(unsigned long long)(e.geglu ? N / 2 : N), (unsigned long long)M, 1, 1, 1};
@@ -213,7 +251,6 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
 
 void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* Wm, int Cout, int stride,
                 int asym, const Epi& e) {
-  if (c.dry) return;
   UG_CHECK((C % 8) == 0, UG_ERR_INVALID, "conv3x3: C must be a multiple of 8");
   TapGemmArgs a;
   base_args(a);
@@ -245,10 +282,15 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
   fill_epi(a, e, c.fmt);
   a.tma_store = can_tma_store(e);
   a.res_tma = can_tma_res(e, Cout) ? 1 : 0;
-  a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
+  int ksplit = 1;
+  a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas, can_split(e, Cout) ? &ksplit : nullptr);
+  if (c.dry) {
+    if (ksplit > 1) { const size_t mk = c.ws.mark(); c.allocf((long long)ksplit * Nf * Ho * Wo * Cout); c.ws.release(mk); }
+    return;
+  }
   const int bn = a.bn_tile / a.ctas;
   CUtensorMap ma, mb, mc, mr;
-  if (a.tma_store) {
+  if (a.tma_store && ksplit == 1) {
     const unsigned long long rb = (unsigned long long)e.ldc * 2;
     unsigned long long od[5] = {(unsigned long long)Cout, (unsigned long long)Wo, (unsigned long long)Ho,
                                 (unsigned long long)Nf, 1};
@@ -294,12 +336,15 @@ void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* 
     make_a_map(&ma, x, c.fmt, dims, st, a.bw, 1, a.bh, a.bn);
   }
   make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)9 * Cout, rowb, bn);
+  if (ksplit > 1) {
+    launch_split(c, ma, mb, a, ksplit, e, "tapgemm.conv3x3", C);
+    return;
+  }
   launch(c, ma, mb, a, 1, "tapgemm.conv3x3", C, a.tma_store ? &mc : nullptr, a.res_tma ? &mr : nullptr);
 }
 
 void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm, int Cout, int chunk,
                const Epi& e) {
-  if (c.dry) return;
   UG_CHECK((C % 8) == 0, UG_ERR_INVALID, "tconv3: C must be a multiple of 8");
   const unsigned long long rowb = (unsigned long long)C * 2;
   // chunks are independent zero-padded clips (VAE decode): run one launch per chunk so that
@@ -329,10 +374,15 @@ void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm,
     fill_epi(a, ec, c.fmt);
     a.tma_store = can_tma_store(ec);
     a.res_tma = can_tma_res(ec, Cout) ? 1 : 0;
-    a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas);
+    int ksplit = 1;
+    a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas, can_split(ec, Cout) ? &ksplit : nullptr);
+    if (c.dry) {
+      if (ksplit > 1) { const size_t mk = c.ws.mark(); c.allocf((long long)ksplit * Tc * P * Cout); c.ws.release(mk); }
+      continue;
+    }
     const int bn = a.bn_tile / a.ctas;
     CUtensorMap ma, mb, mc, mr;
-    if (a.tma_store) {
+    if (a.tma_store && ksplit == 1) {
       const unsigned long long rb = (unsigned long long)ec.ldc * 2;
       unsigned long long od[5] = {(unsigned long long)Cout, (unsigned long long)P, (unsigned long long)Tc, 1, 1};
       unsigned long long os[4] = {rb, rb * P, rb * P * Tc, rb * P * Tc};
@@ -347,6 +397,10 @@ void op_tconv3(Ctx& c, const void* x, int T, long long P, int C, const void* Wm,
     unsigned long long st[4] = {rowb, rowb * P, rowb * P * Tc, rowb * P * Tc};
     make_a_map(&ma, reinterpret_cast<const char*>(x) + tok0 * rowb, c.fmt, dims, st, a.bw, a.bh, 1, 1);
     make_b_map(&mb, Wm, c.fmt, C, (unsigned long long)3 * Cout, rowb, bn);
+    if (ksplit > 1) {
+      launch_split(c, ma, mb, a, ksplit, ec, "tapgemm.tconv3", C);
+      continue;
+    }
     launch(c, ma, mb, a, 1, "tapgemm.tconv3", C, a.tma_store ? &mc : nullptr, a.res_tma ? &mr : nullptr);
   }
 }

@@ -126,13 +126,13 @@ __device__ __forceinline__ void finish_cols(float (&f)[NC], const TapGemmArgs& a
     if (full && ((col0 & 3) == 0) && ((a.fbias_ld & 3) == 0)) {
 #pragma unroll
       for (int j = 0; j < NC / 4; ++j) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(fb) + j);
+        const float4 b = ld_act(reinterpret_cast<const float4*>(fb) + j);
         f[4 * j + 0] += b.x; f[4 * j + 1] += b.y; f[4 * j + 2] += b.z; f[4 * j + 3] += b.w;
       }
     } else {
 #pragma unroll
       for (int j = 0; j < NC; ++j)
-        if (full || j < ncols_valid) f[j] += __ldg(fb + j);
+        if (full || j < ncols_valid) f[j] += ld_act(fb + j);
     }
   }
   if (a.act == 1) {
@@ -150,7 +150,7 @@ __device__ __forceinline__ void finish_cols(float (&f)[NC], const TapGemmArgs& a
       const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.res) + off);
 #pragma unroll
       for (int j = 0; j < NC / 8; ++j) {
-        uint4 u = __ldg(p + j);
+        uint4 u = ld_act(p + j);
         float2 t0 = unpack16x2(u.x, fmt), t1 = unpack16x2(u.y, fmt), t2 = unpack16x2(u.z, fmt),
                t3 = unpack16x2(u.w, fmt);
         f[8 * j + 0] += t0.x; f[8 * j + 1] += t0.y; f[8 * j + 2] += t1.x; f[8 * j + 3] += t1.y;
@@ -169,7 +169,7 @@ __device__ __forceinline__ void finish_cols(float (&f)[NC], const TapGemmArgs& a
       const uint4* p = reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.blend) + off);
 #pragma unroll
       for (int j = 0; j < NC / 8; ++j) {
-        uint4 u = __ldg(p + j);
+        uint4 u = ld_act(p + j);
         float2 t0 = unpack16x2(u.x, fmt), t1 = unpack16x2(u.y, fmt), t2 = unpack16x2(u.z, fmt),
                t3 = unpack16x2(u.w, fmt);
         f[8 * j + 0] = al * t0.x + be * f[8 * j + 0]; f[8 * j + 1] = al * t0.y + be * f[8 * j + 1];
@@ -315,6 +315,13 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   };
   const int num_iters = a.num_taps * a.kchunks;
+  // split-K (a.ksplit > 1; batch == ksplit): unit z accumulates the (tap, chunk) iterations [it0, it1) of its tile into
+  // its own fp32 partial (out + z * out_z1stride); a reduce kernel sums the partials in index order afterwards
+  auto k_range = [&](int z, int& it0, int& it1) {
+    if (a.ksplit <= 1) { it0 = 0; it1 = num_iters; return; }
+    it0 = (int)(((long long)num_iters * z) / a.ksplit);
+    it1 = (int)(((long long)num_iters * (z + 1)) / a.ksplit);
+  };
   const int unit0 = blockIdx.x / CTAS, unit_stride = gridDim.x / CTAS;
   // i-th unit of this CTA (pair): round-robin, or the host's balanced list (ragged N tiles cost less than full ones,
   // and a plain round-robin leaves the CTAs that drew one unit more holding the whole tail).  All three roles walk
@@ -390,14 +397,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int bcol0 = a.b_c0 + z0 * a.b_z0_cstep;
         // pair mode: this CTA stages the rank-th half of the tile's (possibly ragged) B rows
         const int brow0 = z1 * a.b_z1_rowstep + (a.b_mn_major ? 0 : n0 + rank * (n_cur(n0) / CTAS));
-        for (int it = 0; it < num_iters; ++it, ++it_g) {
+        int it0, it1;
+        k_range(z, it0, it1);
+        for (int it = it0; it < it1; ++it, ++it_g) {
           const int s = it_g % kSt;
           const uint32_t ph = (uint32_t)(it_g / kSt) & 1u;
           const int tap = it / a.kchunks;
           const int kc = it - tap * a.kchunks;
           mbar_wait(&empty_bar[s], ph ^ 1u);
-          if (it == 0) UG_TRACE(0, ui, 1);
-          if (it == num_iters - 1) UG_TRACE(0, ui, 2);
+          if (it == it0) UG_TRACE(0, ui, 1);
+          if (it == it1 - 1) UG_TRACE(0, ui, 2);
           uint8_t* sa = smem + s * kStB;
           uint8_t* sb = sa + kATileBytes;
           if constexpr (CTAS == 2) {
@@ -435,13 +444,15 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         tc_fence_after();
         if (lane == 0) UG_TRACE(1, tl, 1);
         const uint32_t tmem_d = tmem_base + (uint32_t)buf * 256u;
-        for (int it = 0; it < num_iters; ++it, ++it_g) {
+        int it0, it1;
+        k_range(z_u, it0, it1);
+        for (int it = it0; it < it1; ++it, ++it_g) {
           const int s = it_g % kSt;
           const uint32_t ph = (uint32_t)(it_g / kSt) & 1u;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
-          if (lane == 0 && it == 0) UG_TRACE(1, tl, 2);
-          if (lane == 0 && it == num_iters - 1) UG_TRACE(1, tl, 3);
+          if (lane == 0 && it == it0) UG_TRACE(1, tl, 2);
+          if (lane == 0 && it == it1 - 1) UG_TRACE(1, tl, 3);
           if (elect_one()) {
             const uint32_t sa = smem_u32(smem + s * kStB);
             const uint64_t da = make_desc_kmajor_sw128(sa);
@@ -452,16 +463,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < BK / 16; ++k) {
               if constexpr (CTAS == 2)
-                umma_f16_pair(tmem_d, da + 2 * k, db + bstep * k, idesc, (it | k) != 0 ? 1u : 0u);
+                umma_f16_pair(tmem_d, da + 2 * k, db + bstep * k, idesc, (it != it0 || k != 0) ? 1u : 0u);
               else
-                umma_f16(tmem_d, da + 2 * k, db + bstep * k, idesc, (it | k) != 0 ? 1u : 0u);
+                umma_f16(tmem_d, da + 2 * k, db + bstep * k, idesc, (it != it0 || k != 0) ? 1u : 0u);
             }
             if constexpr (CTAS == 2) {
               umma_commit_pair(&empty_bar[s]);
-              if (it == num_iters - 1) umma_commit_pair(&tmem_full_bar[buf]);
+              if (it == it1 - 1) umma_commit_pair(&tmem_full_bar[buf]);
             } else {
               umma_commit(&empty_bar[s]);
-              if (it == num_iters - 1) umma_commit(&tmem_full_bar[buf]);
+              if (it == it1 - 1) umma_commit(&tmem_full_bar[buf]);
             }
           }
           __syncwarp();
@@ -519,9 +530,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int et = threadIdx.x - 64, col = n0 + et;
         float bsum = 0.f;
         if (col < a.n_total) {
-          if (a.bias != nullptr) bsum = __ldg(a.bias + col);
+          if (a.bias != nullptr) bsum = ld_act(a.bias + col);    // the time-embedding bias is rewritten every step
           if (a.fbias_uniform)
-            bsum += __ldg(a.fbias + (long long)((int)((long long)m_tile_lin * BM) / a.fbias_div) * a.fbias_ld + col);
+            bsum += ld_act(a.fbias + (long long)((int)((long long)m_tile_lin * BM) / a.fbias_div) * a.fbias_ld + col);
         }
         sbt[et] = bsum;
         named_bar_sync(3, kEpiWarps * 32);
@@ -581,7 +592,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                             pix * a.ldb + out_c0 + c);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+              asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
                            : "=r"(bq4[j].x), "=r"(bq4[j].y), "=r"(bq4[j].z), "=r"(bq4[j].w) : "l"(pb + j));
           } else {
 #pragma unroll
@@ -653,7 +664,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                               pix * a.ldr + out_c0 + c);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(rq[which][j].x), "=r"(rq[which][j].y), "=r"(rq[which][j].z), "=r"(rq[which][j].w)
                              : "l"(pr + j));
             }
@@ -662,7 +673,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                                               pix * a.ldb + out_c0 + c);
 #pragma unroll
               for (int j = 0; j < 4; ++j)
-                asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];"
+                asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(bq[which][j].x), "=r"(bq[which][j].y), "=r"(bq[which][j].z), "=r"(bq[which][j].w)
                              : "l"(pb + j));
             }
@@ -930,8 +941,9 @@ int tapgemm_num_sms() {
 // behaviour that shared-memory bandwidth (128 B/clk: TMA fill + UMMA operand reads) binds before the
 // tensor pipe does:   1 CTA: 256 + 2 BN      CTA pair: max(2 BN, 256 + BN)
 // times the number of waves over the SMs (pairs: over SM pairs), plus a fixed per-tile cost.
-int tapgemm_pick_tile(const TapGemmArgs& a, int batch, int* ctas_out) {
+int tapgemm_pick_tile(const TapGemmArgs& a, int batch, int* ctas_out, int* ksplit_out) {
   *ctas_out = 1;
+  if (ksplit_out) *ksplit_out = 1;
   if (a.b_mn_major) return 64;           // MN-major B boxes are [64 K][64 N]
   const long long m_tiles = (long long)a.tiles_x * a.tiles_y * a.tiles_n;
   const int sms = tapgemm_num_sms();
@@ -939,23 +951,41 @@ int tapgemm_pick_tile(const TapGemmArgs& a, int batch, int* ctas_out) {
     const char* e = getenv("UG_TAPGEMM_CTAS");
     return e ? atoi(e) : 0;
   }();
+  static const int max_split = [] {
+    const char* e = getenv("UG_SPLITK");            // 0 / 1 disables split-K, n caps it
+    return e ? atoi(e) : 16;
+  }();
+  // Split-K candidates (only when the caller can take fp32 partials: ksplit_out != nullptr): a launch whose tiles
+  // cannot fill the SMs (M = 64 .. 1200 rows against K = 11520) runs `waves * iters` iterations on a few CTAs; splitting
+  // the (tap, chunk) iterations over S units per tile fills the machine at the price of one reduce pass over S fp32
+  // partials.  Costs in SM clocks: per-iteration shared-memory model as before, epilogue 8 clk per column + 400, reduce
+  // = its bytes at ~3700 B/clk chip-wide + ~3000 clk of launch latency.
+  const long long iters = (long long)a.num_taps * a.kchunks;
+  const double M = (double)a.W * a.H * a.N;
   int best = 16;
-  long long best_cost = -1;
+  double best_cost = -1.0;
   for (int ctas = 1; ctas <= 2; ++ctas) {
     if (force && ctas != force) continue;
     if (ctas == 2 && (m_tiles < 2 || (sms & 1))) continue;
     const int step = a.tma_store ? 64 : 16 * ctas;   // TMA-store slabs are 64 columns wide
     for (int bn = 256; bn >= step; bn -= step) {
       if (a.geglu && bn != 256) continue;      // [128 value | 128 gate] column tiles
-      const long long units = ((m_tiles + ctas - 1) / ctas) * ((a.n_total + bn - 1) / bn) * batch;
+      const long long tiles = ((m_tiles + ctas - 1) / ctas) * ((a.n_total + bn - 1) / bn) * batch;
       const long long slots = sms / ctas;
-      const long long waves = (units + slots - 1) / slots;
       const long long per = ctas == 1 ? 256 + 2 * bn : (2 * bn > 256 + bn ? 2 * bn : 256 + bn);
-      const long long cost = waves * (per + 48);
-      if (best_cost < 0 || cost < best_cost) {
-        best_cost = cost;
-        best = bn;
-        *ctas_out = ctas;
+      const int s_max = (ksplit_out && batch == 1 && !a.geglu && max_split > 1) ? max_split : 1;
+      for (int S = 1; S <= s_max; ++S) {
+        if (S > 1 && (iters / S < 4 || tiles * S > 2 * slots || M * a.n_total * 4.0 * S > 96e6)) break;
+        const long long units = tiles * S;
+        const long long waves = (units + slots - 1) / slots;
+        double cost = (double)waves * ((double)per * (double)((iters + S - 1) / S) + 8.0 * bn + 400.0);
+        if (S > 1) cost += M * a.n_total * (4.0 * S + 4.0) / 3700.0 + 3000.0;
+        if (best_cost < 0 || cost < best_cost) {
+          best_cost = cost;
+          best = bn;
+          *ctas_out = ctas;
+          if (ksplit_out) *ksplit_out = S;
+        }
       }
     }
   }
@@ -964,7 +994,7 @@ int tapgemm_pick_tile(const TapGemmArgs& a, int batch, int* ctas_out) {
 
 int tapgemm_pick_bn(const TapGemmArgs& a, int batch) {
   int ctas;
-  return tapgemm_pick_tile(a, batch, &ctas);
+  return tapgemm_pick_tile(a, batch, &ctas, nullptr);
 }
 
 // Balanced unit lists for launches whose last N tile is ragged (cheaper than a full one) and that run more than one
@@ -1090,6 +1120,10 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   if (ctas == 2 && args.b_mn_major) return (int)cudaErrorInvalidValue;
   if (args.tma_store && (tmC == nullptr || (args.bn_tile & 63) || batch != 1 || args.out_fp32))
     return (int)cudaErrorInvalidValue;
+  if (args.ksplit > 1 && (batch != args.ksplit || !args.out_fp32 || args.tma_store || args.geglu || args.b_mn_major ||
+                          args.bias != nullptr || args.fbias != nullptr || args.res != nullptr || args.blend != nullptr ||
+                          args.act != 0 || args.ksplit > args.num_taps * args.kchunks))
+    return (int)cudaErrorInvalidValue;             // partial sums only: everything else happens in the reduce pass
   if (args.geglu && (args.bn_tile != 256 || (args.n_total & 255))) return (int)cudaErrorInvalidValue;
   if (args.geglu && (args.res != nullptr || args.blend != nullptr || args.fbias != nullptr || args.scale != 1.0f ||
                      args.act != 0))
@@ -1121,7 +1155,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   }
   if (ctas == 1) {
     const int grid = (int)(units < sms ? units : sms);
-    return (int)launch_pdl(tapgemm_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes,
+    return (int)launch_pdl_tag("tapgemm", tapgemm_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes,
                            stream, tmA, tmB, mc, mr, args);
   }
   const long long slots = sms / 2;
@@ -1130,7 +1164,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = kSmemBytes2;
   cfg.stream = stream;
-  static const bool no_pdl = getenv("UG_NO_PDL") != nullptr;
+  static const bool no_pdl = pdl_off("tapgemm");
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;

@@ -49,6 +49,8 @@ struct TapGemmArgs {
                            // needs a 16-bit output, ldc % 8 == 0, batch 1 and the output tensor map
   int res_tma;             // residual tiles arrive by TMA (32-column chunks, in place in the store staging ring):
                            // tmC / tmR are 32-column SWIZZLE_64B maps of the output / residual tensor
+  int ksplit;              // > 1: split-K -- batch == ksplit units per tile, each accumulating its share of the (tap,
+                           // chunk) iterations into an fp32 partial at out + z * out_z1stride (direct stores, no fusions)
   int n_tiles, batch;      // filled by launch_tapgemm
   int n_fastest;           // tile order (filled by launch_tapgemm): N tiles of one M tile run concurrently
 #ifdef UG_TAPGEMM_TRACE
@@ -103,7 +105,8 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
 
 // needs tiles_*, n_total, geglu, b_mn_major filled in; returns bn_tile and the CTA count per tile.
 // The B tensor map's box must have bn_tile / ctas rows.
-int tapgemm_pick_tile(const TapGemmArgs& args, int batch, int* ctas);
+// ksplit (nullable): where non-null the model may also split the K iterations (see TapGemmArgs::ksplit) and returns S.
+int tapgemm_pick_tile(const TapGemmArgs& args, int batch, int* ctas, int* ksplit = nullptr);
 // Balanced per-CTA unit lists for launches with ragged N tiles (pure host code): [slots][len] table, -1 = none;
 // returns len.  max_cost / rr_max_cost (nullable): modelled cost of the heaviest slot, here and under round-robin.
 int tapgemm_build_schedule(int pm_tiles, int n_tiles, int batch, int n_fastest, int n_total, int bn_tile, int ctas,

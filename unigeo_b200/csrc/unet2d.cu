@@ -270,17 +270,21 @@ void unet2d_set_context(Ctx& c, const std::string& prefix, const float* tokens, 
   const Topo2D t = topo2d(g, n.controlnet);
   const size_t mk = c.ws.mark();
   void* tok16 = c.alloc16(rows * D);
-  if (!c.dry) {
-    op_check(c, launch_f32_to_tokens(tokens, D, D, rows, tok16, c.fmt, c.stream), "context tokens");
-    const bool regrow = n.ctx_len * n.ctx_frames < rows;
-    for (size_t i = 0; i < t.transformers.size(); ++i) {
-      const std::string key = n.prefix + t.transformers[i];
-      const int C = t.transformer_c[i];
+  if (!c.dry) op_check(c, launch_f32_to_tokens(tokens, D, D, rows, tok16, c.fmt, c.stream), "context tokens");
+  const bool regrow = n.ctx_len * n.ctx_frames < rows;
+  for (size_t i = 0; i < t.transformers.size(); ++i) {
+    const std::string key = n.prefix + t.transformers[i];
+    const int C = t.transformer_c[i];
+    void* out = tok16;                       // size-only pass: any aligned address (op_linear sizes its split-K partials)
+    if (!c.dry) {
       void*& buf = n.kv[key];
       if (buf == nullptr || regrow) buf = c.dmalloc((size_t)rows * 2 * C * 2);
-      Epi e; e.out = buf; e.ldc = 2 * C;
-      op_linear(c, tok16, rows, D, D, c.M(key + ".transformer_blocks.0.attn2.to_kv.weight"), 2 * C, e);
+      out = buf;
     }
+    Epi e; e.out = out; e.ldc = 2 * C;
+    op_linear(c, tok16, rows, D, D, c.M(key + ".transformer_blocks.0.attn2.to_kv.weight"), 2 * C, e);
+  }
+  if (!c.dry) {
     n.ctx_len = len;
     n.ctx_frames = frames;
   }
