@@ -259,6 +259,11 @@ long long ug_ctx_workspace_bytes(ug_ctx* ctx);
 /* CUDA graphs currently instantiated: ug_denoise_clip / ug_refine_frames_2d run their step loop eagerly on the first
  * call with a given signature, capture it on the second and replay it afterwards (UG_NO_GRAPH=1 keeps them eager). */
 long long ug_ctx_graph_count(ug_ctx* ctx);
+/* Host-only: n / d the way the persistent GEMM kernel's per-tile index decoding computes it (multiply-high by a launch
+ * constant + shift, tapgemm.cuh FastDiv), for 1 <= d, 0 <= n < 2^31; negative ug_status otherwise.  Exists so that the
+ * CPU suite can pin the arithmetic against integer division.  No device needed. */
+long long ug_fastdiv(int d, int n);
+
 /* Per-launch profiling for bench.py's roofline: while enabled, one CUDA event is recorded on the
  * call's stream after every kernel launch; ug_ctx_profile_read synchronises and aggregates by kernel
  * name (returns the number of rows written, or a negative ug_status).  Off by default. */
@@ -283,6 +288,15 @@ int ug_op_groupnorm(int dtype, const void* x1, int C1, const void* x2, int C2, l
                     int silu, void* y, void* stream);
 int ug_op_layernorm(int dtype, const void* x, long long rows, int C, const float* gamma, const float* beta,
                     float eps, const float* add, int add_div, void* y, void* stream);
+/* y[M][N] = LayerNorm(x[M][K]; gamma, beta, eps) W[N][K]^T (+bias) in the FOLDED form the UNet graph uses for every
+ * LayerNorm of a transformer block (replaces [UPSTREAM] diffusers BasicTransformerBlock / TemporalBasicTransformerBlock
+ * norm1 / norm3 / norm_in + to_q|k|v / ff.net.0.proj, reached from /root/reference/model/depthcrafter.py:80-90): the
+ * GEMM reads the raw rows against gamma-scaled weights and its epilogue applies rstd * (acc - mean * colsum) + (bias +
+ * W beta).  x0 == NULL: x is given and one row_stats pass provides (mean, rstd).  x0 != NULL: x = x0[M][K0] W0[K][K0]^T
+ * (+bias0) (+res0) is computed first (and written to x) and the row statistics come out of THAT GEMM's epilogue. */
+int ug_op_ln_linear(int dtype, const void* x0, int K0, const void* W0, const float* bias0, const void* res0, void* x,
+                    long long M, int K, const float* gamma, const float* beta, float eps, const void* W, int N,
+                    const float* bias, int geglu, void* y, void* stream);
 /* qkv [F*N][3C] -> y [F*N][C]; softmax(q k^T / sqrt(dh)) v per frame and head (dh = 64 or C) */
 int ug_op_spatial_attention(int dtype, const void* qkv, int F, int N, int C, int dh, void* y, void* stream);
 /* qkv [T][P][3C] -> y [T][P][C]; attention over T per pixel and 64-wide head */

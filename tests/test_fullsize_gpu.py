@@ -45,6 +45,43 @@ def test_full_architecture_unet_matches_oracle_on_a_small_clip(cuda):
     assert rel_l2(got, ref) <= 1e-2, rel_l2(got, ref)
 
 
+@pytest.mark.parametrize("dtype,tol", [("fp16", 1e-2), ("bf16", 3e-2)])
+def test_full_architecture_unet_with_folded_layernorms_matches_oracle(cuda, monkeypatch, dtype, tol):
+    """The opt-in graph (UG_LN_FOLD=1) in which no LayerNorm output is ever materialised -- gamma folded into the qkv /
+    GEGLU weights, the epilogue applying rstd * (acc - mean * colsum) + (bias + W beta), row statistics left behind by
+    the producing GEMM's epilogue, the frame positional embedding carried in the stored stream and taken out again in
+    the AlphaBlender GEMM -- against the same fp32 oracle and tolerance as the default graph, at SVD-XT widths."""
+    from oracle.pipeline import added_time_ids
+    from oracle.unet_st import unet_forward
+    from unigeo_b200.config import full_config
+    from unigeo_b200.engine import Engine
+    from unigeo_b200.weights import synthetic_state_dict, unet_param_shapes
+    cfg = full_config()
+    sd = synthetic_state_dict(unet_param_shapes(cfg.unet), 77)
+    T, h, w = 3, 16, 32
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(1, T, 8, h, w, generator=g)
+    enc = torch.randn(1, T, 1024, generator=g)
+    ids = added_time_ids(cfg)
+    with torch.no_grad():
+        ref = unet_forward(sd, cfg.unet, x, 0.7, enc, ids)
+    outs = {}
+    for fold in ("1", "0"):
+        monkeypatch.setenv("UG_LN_FOLD", fold)               # read by ug_ctx_finalize
+        e = Engine(cfg, dtype=dtype, device=0)
+        e.load_state_dict("unet", sd)
+        e.prepare(T, h, w)
+        e.set_clip_context(enc[0])
+        outs[fold] = e.unet_forward(x, 0.7, ids[0].tolist())
+        torch.cuda.synchronize()
+        del e
+    assert torch.isfinite(outs["1"]).all()
+    assert rel_l2(outs["1"], ref) <= tol, rel_l2(outs["1"], ref)
+    assert rel_l2(outs["0"], ref) <= tol, rel_l2(outs["0"], ref)
+    assert not torch.equal(outs["1"], outs["0"])             # the two graphs really are different arithmetic
+    assert rel_l2(outs["1"], outs["0"]) <= tol, rel_l2(outs["1"], outs["0"])
+
+
 @pytest.fixture(scope="module")
 def full_engine(cuda):
     from unigeo_b200.clip_embed import ClipEmbedder

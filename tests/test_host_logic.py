@@ -359,3 +359,21 @@ def test_top_level_model_package_is_the_plugin_surface():
     m = importlib.import_module("model")
     from unigeo_b200.model import DepthCrafter, StableNormal
     assert getattr(m, "DepthCrafter") is DepthCrafter and getattr(m, "StableNormal") is StableNormal
+
+
+def test_fastdiv_matches_integer_division():
+    """ug_fastdiv (host-only): the multiply-high division of tapgemm's per-tile index decoding equals n // d for launch
+    constants of every kind (1, powers of two and their neighbours, primes, large) and n up to 2^31 - 1."""
+    import random
+    from unigeo_b200 import _lib
+    lib = _lib.load()
+    rng = random.Random(0)
+    ds = list(range(1, 300)) + [2 ** k for k in range(1, 31)] + [2 ** k + 1 for k in range(1, 30)] + \
+        [2 ** k - 1 for k in range(2, 31)] + [rng.randrange(1, 2 ** 30) for _ in range(300)] + [300, 3000, 74, 148, 3072, 76800]
+    for d in ds:
+        ns = [0, 1, d - 1, d, d + 1, 2 * d - 1, 2 * d, 2 ** 31 - 1, 2 ** 31 - d, max(0, 2 ** 31 - d - 1)] + \
+            [rng.randrange(0, 2 ** 31) for _ in range(40)]
+        for n in ns:
+            if 0 <= n < 2 ** 31:
+                assert lib.ug_fastdiv(d, n) == n // d, (d, n)
+    assert lib.ug_fastdiv(0, 5) < 0 and lib.ug_fastdiv(3, -1) < 0

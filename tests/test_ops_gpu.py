@@ -46,6 +46,89 @@ def test_linear(cuda, dtype, M, K, N):
     check("fp32 out", y32, ref + b, dtype)
 
 
+def _ln_ref(x, gamma, beta, eps):
+    return F.layer_norm(x.float(), (x.shape[1],), gamma, beta, eps)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,K,N", [(256, 64, 192), (300, 320, 960), (1000, 1280, 320), (77, 72, 200), (6144, 320, 960),
+                                   (1200, 1280, 3840)])
+def test_ln_linear_folded(cuda, dtype, M, K, N):
+    """LayerNorm folded into the consuming GEMM (row_stats pass + epilogue correction) against LayerNorm -> linear in
+    fp32; rows with a large common offset check the cancellation acc - mean * colsum."""
+    from unigeo_b200 import ops
+    x = rnd((M, K), dtype, cuda, 1) * 2.0 + rnd((M, 1), dtype, cuda, 5) * 3.0
+    gamma = 1.0 + rnd((K,), torch.float32, cuda, 6, 0.2)
+    beta = rnd((K,), torch.float32, cuda, 7, 0.2)
+    W = rnd((N, K), dtype, cuda, 2, 1 / math.sqrt(K))
+    b = rnd((N,), torch.float32, cuda, 3)
+    ref = _ln_ref(x, gamma, beta, 1e-5) @ W.float().t()
+    check("lnfold", ops.ln_linear(x, gamma, beta, W), ref, dtype, 1.5)
+    check("lnfold+bias", ops.ln_linear(x, gamma, beta, W, bias=b), ref + b, dtype, 1.5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,K,H", [(200, 64, 128), (513, 128, 512), (6144, 320, 1280)])
+def test_ln_linear_folded_geglu(cuda, dtype, M, K, H):
+    from unigeo_b200 import ops
+    x = rnd((M, K), dtype, cuda, 1) * 1.5 + rnd((M, 1), dtype, cuda, 5)
+    gamma = 1.0 + rnd((K,), torch.float32, cuda, 6, 0.2)
+    beta = rnd((K,), torch.float32, cuda, 7, 0.2)
+    W = rnd((2 * H, K), dtype, cuda, 2, 1 / math.sqrt(K))
+    b = rnd((2 * H,), torch.float32, cuda, 3, 0.1)
+    h = _ln_ref(x, gamma, beta, 1e-5) @ W.float().t() + b
+    ref = h[:, :H] * F.gelu(h[:, H:])
+    Wi, bi = ops.geglu_interleave(W, b)
+    check("lnfold geglu", ops.ln_linear(x, gamma, beta, Wi, bias=bi, geglu=True), ref, dtype, 1.5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,K0,K,N,res", [(300, 320, 320, 960, True), (6144, 1280, 320, 2560, True),
+                                          (6144, 320, 320, 960, False), (1000, 256, 640, 1920, True),
+                                          (77, 64, 72, 200, True), (2400, 5120, 1280, 3840, True)])
+def test_ln_linear_folded_producer_stats(cuda, dtype, M, K0, K, N, res):
+    """Row statistics left behind by the epilogue of the GEMM that produces the rows (sum / sum-of-squares partials per
+    N tile and column group) instead of a statistics pass; the consumer is checked against LayerNorm of the rows the
+    producer actually stored."""
+    from unigeo_b200 import ops
+    x0 = rnd((M, K0), dtype, cuda, 11)
+    W0 = rnd((K, K0), dtype, cuda, 12, 1 / math.sqrt(K0))
+    b0 = rnd((K,), torch.float32, cuda, 13)
+    r0 = rnd((M, K), dtype, cuda, 14, 2.0) if res else None
+    gamma = 1.0 + rnd((K,), torch.float32, cuda, 6, 0.2)
+    beta = rnd((K,), torch.float32, cuda, 7, 0.2)
+    W = rnd((N, K), dtype, cuda, 2, 1 / math.sqrt(K))
+    b = rnd((N,), torch.float32, cuda, 3)
+    x = torch.empty((M, K), device=cuda, dtype=dtype)
+    x, y = ops.ln_linear(x, gamma, beta, W, bias=b, producer=(x0, W0, b0, r0))
+    xr = x0.float() @ W0.float().t() + b0 + (r0.float() if res else 0.0)
+    check("producer rows", x, xr, dtype)
+    check("lnfold after producer", y, _ln_ref(x, gamma, beta, 1e-5) @ W.float().t() + b, dtype, 1.5)
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_geglu_gate_function_pointwise(cuda, dtype):
+    """The gate function of the fused GEGLU epilogue against the exact erf GELU, point by point over gate values in
+    [-12, 12] (value = 1, gate = one input channel, so the GEMM part is exact).  The epilogue evaluates x Phi(x) with one
+    MUFU.TANH per element and a fitted quartic (max |error| 2.5e-5 + 2^-12 |x| from the hardware tanh); the bound below
+    is that plus the 16-bit rounding of the output."""
+    from unigeo_b200 import ops
+    M, K, H = 4096, 64, 128
+    x = torch.zeros((M, K), device=cuda, dtype=dtype)
+    x[:, 0] = torch.linspace(-12, 12, M, device=cuda).to(dtype)
+    W = torch.zeros((2 * H, K), device=cuda, dtype=dtype)
+    W[H:, 0] = 1.0                                      # every gate column = x[:, 0]
+    b = torch.zeros(2 * H, device=cuda)
+    b[:H] = 1.0                                         # every value column = 1
+    Wi, bi = ops.geglu_interleave(W, b)
+    y = ops.linear(x, Wi, bias=bi, geglu=True).float()
+    g = x[:, 0].float()
+    ref = F.gelu(g)[:, None].expand(M, H)
+    ulp = 2.0 ** -11 if dtype == torch.float16 else 2.0 ** -8
+    bound = 2.5e-5 + ulp * ref.abs() + 2.0 ** -12 * g.abs()[:, None] + 1e-6
+    assert ((y - ref).abs() <= bound).all(), f"max excess {((y - ref).abs() - bound).max().item():.3e}"
+
+
 @pytest.mark.parametrize("dtype", DTYPES)
 @pytest.mark.parametrize("M,K,H", [(200, 64, 128), (513, 128, 512)])
 def test_linear_geglu(cuda, dtype, M, K, H):

@@ -16,7 +16,11 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-TRACE_LIB = os.path.join(ROOT, "unigeo_b200", "libunigeo_b200_trace.so")
+# split1 / split2 / split3: stamp 1 of the epilogue moves to before the bias staging / after its barrier / just before
+# the accumulator wait (isolates the parts of the tile prologue)
+SPLIT = next((int(a[5:]) for a in sys.argv if a.startswith("split") and a[5:].isdigit()), 0)
+TRACE_LIB = os.path.join(ROOT, "unigeo_b200", f"libunigeo_b200_trace_split{SPLIT}.so" if SPLIT else "libunigeo_b200_trace.so")
+VARIANT = (f"trace_split{SPLIT}", ["UG_TAPGEMM_TRACE", f"UG_TRACE_SPLIT={SPLIT}"]) if SPLIT else ("trace", ["UG_TAPGEMM_TRACE"])
 TILES, ROLES = 16, 4
 
 
@@ -26,11 +30,11 @@ def main():
         return
     if sys.argv[1] == "build":
         from unigeo_b200.build import build_variant
-        print(build_variant("trace", ["UG_TAPGEMM_TRACE"]))
+        print(build_variant(*VARIANT))
         return
     if not os.path.exists(TRACE_LIB):
         from unigeo_b200.build import build_variant
-        build_variant("trace", ["UG_TAPGEMM_TRACE"])
+        build_variant(*VARIANT)
     os.environ["UG_LIB"] = TRACE_LIB
     import ctypes as C
     import math
@@ -92,6 +96,17 @@ def main():
         print(f"epilogue g{grp - 2} accumulator wait {avg((grp, 1), (grp, 0)):9.0f}   ready -> drained "
               f"{avg((grp, 2), (grp, 1)):9.0f}   drained -> stores issued {avg((grp, 3), (grp, 2)):9.0f}")
     print(f"mma(i) issued -> epilogue g0 sees accumulator {avg((2, 1), (1, 3)):9.0f}")
+    if "raw" in sys.argv:            # per-tile timeline of a few CTA pairs, clocks relative to the pair's first stamp
+        for u in (0, n_units // 2):
+            base = t[u][t[u] > 0].min()
+            print(f"-- unit {u}: tile | producer wait0 first last | mma start accfree stage0 last | g0 start acc drained done | g1 ...")
+            for i in range(TILES):
+                if t[u, 2, i, 3] <= 0:
+                    break
+                row = [f"{i:2d} |"]
+                for role, slots in ((0, 3), (1, 4), (2, 4), (3, 4)):
+                    row += [f"{int(t[u, role, i, k] - base):7d}" if t[u, role, i, k] > 0 else "      -" for k in range(slots)] + ["|"]
+                print(" ".join(row))
 
 
 if __name__ == "__main__":

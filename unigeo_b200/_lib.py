@@ -103,6 +103,7 @@ _SIGNATURES = {
                             C.POINTER(C.c_double)], C.c_int),
     "ug_ddim_schedule": ([C.POINTER(UNet2DCfg), _I, _I, C.POINTER(C.c_int), C.POINTER(C.c_double),
                           C.POINTER(C.c_double)], C.c_int),
+    "ug_fastdiv": ([_I, _I], C.c_longlong),
     "ug_tile_schedule": ([_I, _I, _I, _I, _I, _I, _I, _I, C.POINTER(C.c_int), _I, C.POINTER(C.c_longlong),
                           C.POINTER(C.c_longlong)], C.c_int),
     "ug_ctx_launch_count": ([_P, _I], C.c_longlong),
@@ -116,6 +117,7 @@ _SIGNATURES = {
     "ug_op_tconv3": ([_I, _P, _I, _L, _I, _P, _I, _I, _P, _P, _P, _F, _P, _P], C.c_int),
     "ug_op_groupnorm": ([_I, _P, _I, _P, _I, _L, _L, _I, _P, _P, _F, _I, _P, _P], C.c_int),
     "ug_op_layernorm": ([_I, _P, _L, _I, _P, _P, _F, _P, _I, _P, _P], C.c_int),
+    "ug_op_ln_linear": ([_I, _P, _I, _P, _P, _P, _P, _L, _I, _P, _P, _F, _P, _I, _P, _I, _P, _P], C.c_int),
     "ug_op_spatial_attention": ([_I, _P, _I, _I, _I, _I, _P, _P], C.c_int),
     "ug_op_temporal_attention": ([_I, _P, _I, _L, _I, _P, _P], C.c_int),
     "ug_op_cross_attention": ([_I, _P, _P, _I, _I, _I, _I, _I, _P, _P], C.c_int),

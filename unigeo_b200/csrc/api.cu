@@ -564,6 +564,11 @@ extern "C" int ug_debug_tapgemm_trace(unsigned long long* dev_buf) {
 }
 #endif
 
+long long ug_fastdiv(int d, int n) {
+  if (d < 1 || n < 0) return (long long)UG_ERR_INVALID;
+  return (long long)fastdiv_host(make_fastdiv(d), n);
+}
+
 int ug_tile_schedule(int m_units, int n_total, int bn_tile, int batch, int n_fastest, int ctas, int slots, int k_iters,
                      int* units_out, int cap, long long* max_cost, long long* rr_max_cost) {
   int ret = 0;
@@ -954,6 +959,48 @@ int ug_op_layernorm(int dtype, const void* x, long long rows, int C, const float
     ug_ctx* u = scratch_ctx(dtype);
     u->c.stream = reinterpret_cast<cudaStream_t>(stream);
     op_layernorm(u->c, x, rows, C, gamma, beta, eps, add, add_div, y);
+  });
+}
+
+int ug_op_ln_linear(int dtype, const void* x0, int K0, const void* W0, const float* bias0, const void* res0, void* x,
+                    long long M, int K, const float* gamma, const float* beta, float eps, const void* W, int N,
+                    const float* bias, int geglu, void* y, void* stream) {
+  return guard([&] {
+    UG_CHECK(x && gamma && beta && W && y, UG_ERR_INVALID, "null argument");
+    ug_ctx* u = scratch_ctx(dtype);
+    Ctx& cc = u->c;
+    UG_CUDA(cudaSetDevice(cc.device));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    // what ug_ctx_finalize does once per (LayerNorm, linear) pair: gamma into the weights, beta into the bias
+    void* wf = nullptr; float* cs = nullptr; float* bo = nullptr; float2* stat = nullptr;
+    const int cap = 4;
+    UG_CUDA(cudaMalloc(&wf, (size_t)N * K * 2));
+    UG_CUDA(cudaMalloc(&cs, (size_t)N * 4));
+    UG_CUDA(cudaMalloc(&bo, (size_t)N * 4));
+    UG_CUDA(cudaMalloc(&stat, (size_t)M * cap * sizeof(float2)));
+    auto cleanup = [&] { cudaStreamSynchronize(st); cudaFree(wf); cudaFree(cs); cudaFree(bo); cudaFree(stat); };
+    try {
+      UG_CHECK(launch_ln_fold_weights(W, gamma, beta, bias, wf, cs, bo, N, K, cc.fmt, st) == 0, UG_ERR_CUDA, "ln_fold_weights");
+      const int nout = geglu ? N / 2 : N;
+      const std::string sig = "lnlin:" + std::to_string(M) + ":" + std::to_string(K0) + ":" + std::to_string(K) + ":" +
+                              std::to_string(N) + ":" + std::to_string(geglu) + (x0 ? "p" : "") + (res0 ? "r" : "");
+      run_sized(u, sig, stream, [&](Ctx& c) {
+        int parts = 0;
+        if (x0 != nullptr) {              // the rows come out of a GEMM whose epilogue leaves their statistics behind
+          Epi p;
+          p.out = x; p.ldc = K; p.bias = bias0; p.res = res0; p.ldr = K;
+          p.stat_out = stat; p.stat_parts = &parts; p.stat_cap = cap; p.stat_eps = eps;
+          op_linear(c, x0, M, K0, K0, W0, K, p);
+        } else {
+          op_row_stats(c, x, M, K, eps, stat);
+        }
+        Epi e;
+        e.out = y; e.ldc = nout; e.geglu = geglu; e.bias = bo;
+        e.ln_stat = stat; e.ln_parts = parts; e.ln_inv_c = 1.0f / (float)K; e.ln_eps = eps; e.ln_colsum = cs;
+        op_linear(c, x, M, K, K, wf, N, e);
+      });
+    } catch (...) { cleanup(); throw; }
+    cleanup();
   });
 }
 

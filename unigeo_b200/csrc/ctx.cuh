@@ -78,6 +78,17 @@ struct Epi {                     // epilogue description for tapgemm-backed ops
   float scale = 1.f;
   int geglu = 0;
   int act = 0;                   // 1: GELU(acc + bias) before residual
+  // LayerNorm folded into the GEMM (TapGemmArgs::ln_stat): x is the RAW row, Wm = gamma (.) W, bias = bias + W beta
+  const float2* ln_stat = nullptr;
+  int ln_parts = 0;              // 0: (mean, rstd) per row; P: (sum, sum of squares) partials per row
+  float ln_inv_c = 0.f, ln_eps = 0.f;
+  const float* ln_colsum = nullptr;
+  // producer side: per-row (sum, sum of squares) partials of the output for the LayerNorm the next GEMM folds in.
+  // *stat_parts receives the partial count per row (op_linear falls back to one row_stats pass, = 0, for split-K launches)
+  float2* stat_out = nullptr;
+  int* stat_parts = nullptr;
+  int stat_cap = 0;              // partial slots per row the stat_out buffer has room for
+  float stat_eps = 0.f;          // epsilon of that LayerNorm (used by the row_stats fallback, which stores rstd)
 };
 
 struct UNetModel;
@@ -146,6 +157,8 @@ void op_gn(Ctx& c, const void* x1, int C1, const void* x2, int C2, long long row
            const float* gamma, const float* beta, float eps, int silu, void* y);
 void op_layernorm(Ctx& c, const void* x, long long rows, int C, const float* g, const float* b, float eps,
                   const float* add, int add_div, void* y);
+// (mean, rstd) of every row of x [rows][C] -> stat [rows] (the statistics a LayerNorm-folding GEMM consumes)
+void op_row_stats(Ctx& c, const void* x, long long rows, int C, float eps, float2* stat);
 void op_temporal_attention(Ctx& c, const void* qkv, void* out, int T, long long P, int C);
 // q [F*N][ldq] against kv [Fk*Lk][2C] (K | V), head_dim 64 -> out [F*N][C]
 void op_cross_attention(Ctx& c, const void* q, int ldq, const void* kv, void* out, int F, int N, int C, int Lk,

@@ -715,6 +715,55 @@ layernorm_kernel(const void* __restrict__ x, long long rows, int C, const float*
   }
 }
 
+// Row statistics only: what a GEMM with a folded LayerNorm (TapGemmArgs::ln_stat) needs of its A rows when the
+// producing GEMM could not leave them behind.  Same lane mapping and two-pass arithmetic as layernorm_kernel; one
+// read of x, 8 bytes written per row.
+template <typename T, int LPR, int VPL>
+__global__ void __launch_bounds__(256)
+row_stats_kernel(const void* x, long long rows, int C, float eps, float2* __restrict__ stat) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPR;
+  constexpr int RPW = 32 / LPR;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RPW + lane / LPR;
+  const bool rok = row < rows;
+  const int nvec = C >> 3;
+  const uint4* xb = reinterpret_cast<const uint4*>(x) + (rok ? row : 0) * nvec;
+  uint4 raw[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int i = sub + LPR * k;
+    raw[k] = make_uint4(0u, 0u, 0u, 0u);
+    if (rok && i < nvec) raw[k] = ld_act(xb + i);
+  }
+  float2 f[VPL][4];
+  float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    unpack4x2<T>(raw[k], f[k]);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s2 = __fadd2_rn(s2, f[k][j]);      // padding vectors are zero
+  }
+  float s = s2.x + s2.y;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float2 v2 = make_float2(0.f, 0.f);
+  const float2 nm2 = make_float2(-mean, -mean);
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    if (sub + LPR * k < nvec) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 d = __fadd2_rn(f[k][j], nm2); v2 = __ffma2_rn(d, d, v2); }
+    }
+  }
+  float v = v2.x + v2.y;
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (rok && sub == 0) stat[row] = make_float2(mean, rsqrtf(v / (float)C + eps));
+}
+
 // ------------------------------------------------------------------ row softmax (block per row)
 template <typename T, int VPT>
 __global__ void softmax_rows_kernel(void* __restrict__ s, long long rows, int n, int n_valid, float scale_log2e) {
@@ -1581,6 +1630,80 @@ int launch_ln_t(const void* x, long long rows, int C, const float* gamma, const 
   UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("layernorm", layernorm_kernel<T, LPR, VPL>, dim3(grid), dim3(wpb * 32), 0, st, x, rows, C,
                                          gamma, beta, eps, add, add_div > 0 ? add_div : 1, y)));
   return (int)err;
+}
+
+template <typename T>
+__global__ void ln_fold_weights_kernel(const T* __restrict__ W, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ bias,
+                                       T* __restrict__ Wf, float* __restrict__ colsum, float* __restrict__ bias_out,
+                                       int N, int K) {
+  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  float cs = 0.f, bb = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float w = static_cast<float>(W[(size_t)n * K + k]);
+    const T wf = static_cast<T>(gamma[k] * w);
+    Wf[(size_t)n * K + k] = wf;
+    cs += static_cast<float>(wf);            // of the ROUNDED weights: a constant row cancels exactly in the epilogue
+    bb = fmaf(beta[k], w, bb);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    cs += __shfl_xor_sync(0xffffffffu, cs, o);
+    bb += __shfl_xor_sync(0xffffffffu, bb, o);
+  }
+  if (lane == 0) {
+    colsum[n] = cs;
+    bias_out[n] = bb + (bias != nullptr ? bias[n] : 0.f);
+  }
+}
+
+__global__ void scale_f32_kernel(const float* __restrict__ x, float a, float* __restrict__ y, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) y[i] = a * x[i];
+}
+
+template <int LPR, int VPL>
+int launch_rs_t(const void* x, long long rows, int C, float eps, float2* stat, int fmt, cudaStream_t st) {
+  const int wpb = 8;
+  const long long rows_per_block = (long long)wpb * (32 / LPR);
+  const unsigned grid = (unsigned)((rows + rows_per_block - 1) / rows_per_block);
+  cudaError_t err;
+  UG_DISPATCH_FMT(fmt, (err = launch_pdl_tag("layernorm", row_stats_kernel<T, LPR, VPL>, dim3(grid), dim3(wpb * 32), 0, st, x,
+                                         rows, C, eps, stat)));
+  return (int)err;
+}
+
+int launch_ln_fold_weights(const void* W, const float* gamma, const float* beta, const float* bias, void* Wf,
+                           float* colsum, float* bias_out, int N, int K, int fmt, cudaStream_t st) {
+  if (N <= 0 || K <= 0) return (int)cudaErrorInvalidValue;
+  const unsigned grid = (unsigned)((N + 7) / 8);
+  UG_DISPATCH_FMT(fmt, (ln_fold_weights_kernel<T><<<grid, 256, 0, st>>>(reinterpret_cast<const T*>(W), gamma, beta, bias,
+                                                                      reinterpret_cast<T*>(Wf), colsum, bias_out, N, K)));
+  return (int)cudaGetLastError();
+}
+
+int launch_scale_f32(const float* x, float a, float* y, long long n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  scale_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(x, a, y, n);
+  return (int)cudaGetLastError();
+}
+
+int launch_row_stats(const void* x, long long rows, int C, float eps, float2* stat, int fmt, cudaStream_t st) {
+  if ((C & 7) || C > 2048 || C < 8) return (int)cudaErrorInvalidValue;
+  const int nvec = C / 8;
+#define UG_RS(LPR, VPL) return launch_rs_t<LPR, VPL>(x, rows, C, eps, stat, fmt, st)
+  if (nvec <= 8) UG_RS(8, 1);
+  if (nvec <= 16) UG_RS(16, 1);
+  if (nvec <= 32) UG_RS(32, 1);
+  if (nvec <= 40) UG_RS(8, 5);
+  if (nvec <= 64) UG_RS(32, 2);
+  if (nvec <= 80) UG_RS(16, 5);
+  if (nvec <= 128) UG_RS(32, 4);
+  if (nvec <= 160) UG_RS(32, 5);
+  UG_RS(32, 8);
+#undef UG_RS
 }
 
 int launch_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,

@@ -37,6 +37,14 @@ int launch_gn_apply(const void* x1, int C1, const void* x2, int C2, long long ro
                     void* y, int fmt, cudaStream_t st);
 
 // ---- LayerNorm over C, optional per-frame vector added first: LN(x + add[row / add_div]) ----
+// (mean, rstd) of every row of x [rows][C] (two-pass fp32, the LayerNorm kernel's own statistics) -> stat [rows]
+int launch_row_stats(const void* x, long long rows, int C, float eps, float2* stat, int fmt, cudaStream_t st);
+// Finalize-time fold of a LayerNorm's affine into the linear layer behind it (one warp per output row n):
+//   Wf[n][k] = round16(gamma[k] W[n][k]);  colsum[n] = sum_k Wf[n][k];  bias_out[n] = bias[n] (nullable) + sum_k beta[k] W[n][k]
+int launch_ln_fold_weights(const void* W, const float* gamma, const float* beta, const float* bias, void* Wf,
+                           float* colsum, float* bias_out, int N, int K, int fmt, cudaStream_t st);
+// y[i] = a * x[i] (fp32 vectors; shape constants at prepare time)
+int launch_scale_f32(const float* x, float a, float* y, long long n, cudaStream_t st);
 int launch_layernorm(const void* x, long long rows, int C, const float* gamma, const float* beta, float eps,
                      const float* add, int add_div, void* y, int fmt, cudaStream_t st);
 

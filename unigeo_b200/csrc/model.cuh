@@ -15,6 +15,8 @@ struct UNetModel {
   std::unordered_map<std::string, float*> attn2_spatial;   // key -> [T][C]
   std::unordered_map<std::string, float*> attn2_temporal;  // key -> [C]
   std::unordered_map<std::string, float*> time_pos;        // key -> [T][C]  (shape constant)
+  std::unordered_map<std::string, float*> time_pos_blend; // key -> [T][C] = -alpha / (1 - alpha) * time_pos (LayerNorm fold)
+  bool ln_fold = false;                                    // LayerNorms folded into the GEMMs behind them (unet_finalize)
   std::unordered_map<std::string, int> temb_offset;        // resnet key -> offset in temb_out
   int temb_total = 0;
   float* temb_out = nullptr;                                // [temb_total] per-step conv1 biases

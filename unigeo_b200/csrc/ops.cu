@@ -92,6 +92,12 @@ void fill_epi(TapGemmArgs& a, const Epi& e, int fmt) {
   a.scale = e.scale;
   a.geglu = e.geglu;
   a.act = e.act;
+  a.ln_stat = e.ln_stat;
+  a.ln_parts = e.ln_parts;
+  a.ln_inv_c = e.ln_inv_c;
+  a.ln_eps = e.ln_eps;
+  a.ln_colsum = e.ln_colsum;
+  a.stat_out = nullptr;          // set by op_linear once the tile width (= partial count) is known
 }
 
 void base_args(TapGemmArgs& a) {
@@ -195,6 +201,7 @@ void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmA
                              " K" + std::to_string(k_real * a.num_taps) + " bn" + std::to_string(a.bn_tile) + "x" +
                              std::to_string(a.ctas) + (a.res ? " +res" : "") + (a.blend ? " +blend" : "") +
                              (a.fbias ? " +fbias" : "") + (a.tma_store ? "" : " direct") + (a.res_tma ? " rtma" : "") +
+                             (a.ln_stat ? " lnfold" : "") + (a.stat_out ? " +stats" : "") +
                              (a.ksplit > 1 ? " splitk" + std::to_string(a.ksplit) : "");
     name = c.prof_names.insert(full).first->c_str();
   }
@@ -218,11 +225,23 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   a.tma_store = can_tma_store(e);
   a.res_tma = can_tma_res(e, N) ? 1 : 0;
   int ksplit = 1;
-  a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas, can_split(e, N) ? &ksplit : nullptr);
+  // a LayerNorm-folding launch keeps its epilogue (the split-K reduce pass does not know the fold)
+  a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas, (can_split(e, N) && e.ln_stat == nullptr) ? &ksplit : nullptr);
+  // row statistics for the next GEMM's folded LayerNorm: out of this launch's epilogue when its partials fit the
+  // caller's buffer and nothing splits K, else one row_stats pass over the finished output
+  static const bool no_epi_stats = getenv("UG_NO_EPI_STATS") != nullptr;
+  const int parts = 2 * cdiv(N, a.bn_tile);
+  const bool epi_stats = e.stat_out != nullptr && !no_epi_stats && ksplit == 1 && parts <= e.stat_cap && !e.geglu &&
+                         !e.out_fp32;
+  if (e.stat_out != nullptr) {
+    UG_CHECK(e.stat_parts != nullptr && e.stat_cap >= 1 && e.ldc == N, UG_ERR_INVALID, "linear: stat_out needs stat_parts / dense rows");
+    *e.stat_parts = epi_stats ? parts : 0;
+  }
   if (c.dry) {                                    // size-only pass: the split-K partials are the op's only workspace
     if (ksplit > 1) { const size_t mk = c.ws.mark(); c.allocf((long long)ksplit * M * N); c.ws.release(mk); }
     return;
   }
+  if (epi_stats) a.stat_out = e.stat_out;
   const int bn = a.bn_tile / a.ctas;
   CUtensorMap ma, mb, mc, mr;
   unsigned long long dims[5] = {(unsigned long long)K, (unsigned long long)M, 1, 1, 1};
@@ -232,6 +251,7 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   make_b_map(&mb, Wm, c.fmt, K, N, (unsigned long long)K * 2, bn);
   if (ksplit > 1) {
     launch_split(c, ma, mb, a, ksplit, e, "tapgemm.linear", K);
+    if (e.stat_out != nullptr) op_row_stats(c, e.out, M, N, e.stat_eps, e.stat_out);
     return;
   }
   if (a.tma_store) {
@@ -247,6 +267,7 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   }
   launch(c, ma, mb, a, 1, e.geglu ? "tapgemm.linear_geglu" : "tapgemm.linear", K, a.tma_store ? &mc : nullptr,
          a.res_tma ? &mr : nullptr);
+  if (e.stat_out != nullptr && !epi_stats) op_row_stats(c, e.out, M, N, e.stat_eps, e.stat_out);
 }
 
 void op_conv3x3(Ctx& c, const void* x, int Nf, int H, int W, int C, const void* Wm, int Cout, int stride,
@@ -540,6 +561,11 @@ void op_layernorm(Ctx& c, const void* x, long long rows, int C, const float* g, 
   if (c.dry) return;
   op_check(c, launch_layernorm(x, rows, C, g, b, eps, add, add_div, y, c.fmt, c.stream),
            prof_name(c, "layernorm", "rows" + std::to_string(rows) + " C" + std::to_string(C)), 0.0, 4.0 * rows * C);
+}
+void op_row_stats(Ctx& c, const void* x, long long rows, int C, float eps, float2* stat) {
+  if (c.dry) return;
+  op_check(c, launch_row_stats(x, rows, C, eps, stat, c.fmt, c.stream),
+           prof_name(c, "row_stats", "rows" + std::to_string(rows) + " C" + std::to_string(C)), 0.0, 2.0 * rows * C);
 }
 void op_temporal_attention(Ctx& c, const void* qkv, void* out, int T, long long P, int C) {
   if (c.dry) return;

@@ -51,10 +51,50 @@ __device__ __forceinline__ float ld_act(const float* p) {
   asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ float2 ld_act(const float2* p) {
+  float2 v;
+  asm volatile("ld.global.cg.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ float4 ld_act(const float4* p) {
   float4 v;
   asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
   return v;
+}
+
+// Predicated forms for loads issued AHEAD of their use (tapgemm's per-tile vectors, one tile ahead): the value is 0 where
+// `pred` is false, and the asm's output register is the variable itself -- written as `v = 0; if (pred) v = ld(...)` the
+// compiler merges the two definitions with a move that READS the load's destination, and an in-order warp then waits a
+// full L2 round trip at the point of issue (measured: 750 clk per tile).
+__device__ __forceinline__ float ld_act_pred(const float* p, bool pred) {
+  float v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.cg.f32 %0, [%1];\n\t}"
+               : "=f"(v) : "l"(p), "r"((int)pred) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ldg_pred(const float* p, bool pred) {     // read-only data (weights)
+  float v;
+  asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %2, 0;\n\tmov.f32 %0, 0f00000000;\n\t@q ld.global.nc.f32 %0, [%1];\n\t}"
+               : "=f"(v) : "l"(p), "r"((int)pred));
+  return v;
+}
+// Row statistics of a folded LayerNorm (TapGemmArgs::ln_stat) into two float4: parts == 0 -> {mean, rstd, 0, 0}, {0};
+// parts == 2 -> one float4 of partials; parts == 4 -> two.  pred false: zeros, no access.
+__device__ __forceinline__ void ld_stats_pred(const float2* p, int parts, bool pred, float4& s0, float4& s1) {
+  asm volatile(
+      "{\n\t.reg .pred qp, q0, q2, q4;\n\t"
+      "setp.ne.s32 qp, %10, 0;\n\t"
+      "setp.eq.and.s32 q0, %9, 0, qp;\n\t"
+      "setp.ge.and.s32 q2, %9, 2, qp;\n\t"
+      "setp.gt.and.s32 q4, %9, 2, qp;\n\t"
+      "mov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\tmov.f32 %2, 0f00000000;\n\tmov.f32 %3, 0f00000000;\n\t"
+      "mov.f32 %4, 0f00000000;\n\tmov.f32 %5, 0f00000000;\n\tmov.f32 %6, 0f00000000;\n\tmov.f32 %7, 0f00000000;\n\t"
+      "@q0 ld.global.cg.v2.f32 {%0, %1}, [%8];\n\t"
+      "@q2 ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%8];\n\t"
+      "@q4 ld.global.cg.v4.f32 {%4, %5, %6, %7}, [%8+16];\n\t}"
+      : "=f"(s0.x), "=f"(s0.y), "=f"(s0.z), "=f"(s0.w), "=f"(s1.x), "=f"(s1.y), "=f"(s1.z), "=f"(s1.w)
+      : "l"(p), "r"(parts), "r"((int)pred)
+      : "memory");
 }
 
 // Host: launch with the programmatic stream serialization attribute (UG_NO_PDL=1 disables it).
@@ -258,6 +298,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 // MUFU.RCP only: no IEEE fix-up, no slow-path branch (keeps unrolled epilogue math branch-free)
+__device__ __forceinline__ float tanh_approx(float x) {      // MUFU.TANH: max relative error 2^-11
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

@@ -49,6 +49,7 @@ constexpr int kStageBytes2 = kATileBytes + 128 * BK * 2;
 constexpr int kStages2 = 5;
 constexpr int kSmemBytes2 = kStages2 * kStageBytes2 + 4 * kSlabBytes + 256 + 2048;
 
+#ifdef UG_GELU_ERF
 // exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below 16-bit output
 // resolution): 2 MUFU + ~12 FMA-pipe instructions instead of libm erff's ~30
 __device__ __forceinline__ float gelu_erf(float x) {
@@ -88,6 +89,40 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
   return make_float2(fmaf(fabsf(h.x), erf_abs.x, h.x), fmaf(fabsf(h.y), erf_abs.y, h.y));
 }
+#endif
+
+// GELU through ONE MUFU per element:  x Phi(x),  Phi(x) = (1 + tanh(x (c0 + c1 x^2 + c2 x^4))) / 2  with the three
+// coefficients fitted (minimax, here) to the EXACT erf form: max |error| 2.5e-5 over all x -- 19 times tighter than the
+// textbook two-coefficient tanh form, and below what rounding the gate to 16 bit first (as the reference's unfused
+// proj -> gelu does) costs; MUFU.TANH adds <= 2^-12 x relative to Phi.  x^2 is clamped at 36 so that the quartic never
+// turns over (tanh has saturated to 1 - 1e-9 there).  10 instructions per pair (4 FMA-pipe packed, 2 min, 2 MUFU, 2
+// packed) against 16 with 4 MUFU for the erf form: the K = 320 GEGLU epilogue is bound by exactly these (trace: 3700 of a
+// 5700-clock tile period in the gate math, MUFU 32 clk per pair and warp).  -DUG_GELU_ERF restores the erf form.
+__device__ __forceinline__ float2 gelu_tanh2(float2 x) {
+  float2 x2 = __fmul2_rn(x, x);
+  x2.x = fminf(x2.x, 36.0f);
+  x2.y = fminf(x2.y, 36.0f);
+  float2 p = __ffma2_rn(x2, make_float2(-0.0003515167918521911f, -0.0003515167918521911f),
+                        make_float2(0.03700564429163933f, 0.03700564429163933f));
+  p = __ffma2_rn(p, x2, make_float2(0.7975078821182251f, 0.7975078821182251f));
+  const float2 g = __fmul2_rn(p, x);
+  const float2 t = make_float2(tanh_approx(g.x), tanh_approx(g.y));
+  const float2 h = __fmul2_rn(x, make_float2(0.5f, 0.5f));
+  return __ffma2_rn(h, t, h);
+}
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float x2 = fminf(x * x, 36.0f);
+  const float p = fmaf(fmaf(x2, -0.0003515167918521911f, 0.03700564429163933f), x2, 0.7975078821182251f);
+  const float h = 0.5f * x;
+  return fmaf(h, tanh_approx(p * x), h);
+}
+#ifdef UG_GELU_ERF
+__device__ __forceinline__ float2 gelu2(float2 x) { return gelu_erf2(x); }
+__device__ __forceinline__ float gelu1(float x) { return gelu_erf(x); }
+#else
+__device__ __forceinline__ float2 gelu2(float2 x) { return gelu_tanh2(x); }
+__device__ __forceinline__ float gelu1(float x) { return gelu_tanh(x); }
+#endif
 
 __device__ __forceinline__ float2 unpack16x2(uint32_t u, int fmt) {
   return fmt ? Elem<__nv_bfloat16>::unpack2(u) : Elem<__half>::unpack2(u);
@@ -104,17 +139,52 @@ __device__ __forceinline__ void store16(void* base, long long idx, float v, int 
   else reinterpret_cast<__half*>(base)[idx] = __float2half_rn(v);
 }
 
+// (sum, sum of squares) of finished output values, for the LayerNorm the NEXT GEMM folds in (TapGemmArgs::stat_out)
+template <int NC>
+__device__ __forceinline__ void stat_accum(const float (&f)[NC], int ncols_valid, float& s1, float& s2) {
+  if (ncols_valid >= NC) {
+    float2 p1 = make_float2(f[0], f[1]);
+    float2 p2 = __fmul2_rn(p1, p1);
+#pragma unroll
+    for (int j = 2; j < NC; j += 2) {
+      const float2 v = make_float2(f[j], f[j + 1]);
+      p1 = __fadd2_rn(p1, v);
+      p2 = __ffma2_rn(v, v, p2);
+    }
+    s1 += p1.x + p1.y;
+    s2 += p2.x + p2.y;
+  } else {
+#pragma unroll
+    for (int j = 0; j < NC; ++j)
+      if (j < ncols_valid) { s1 += f[j]; s2 = fmaf(f[j], f[j], s2); }
+  }
+}
+
 // Finishes NC (16 or 32) consecutive output columns of one row and stores them.
 //   f[]    accumulator values (already scaled / gated)
 //   col0   first column in OUTPUT column space; ncols_valid = how many of the NC exist
-template <int NC, bool AUX = true>
+//   LNF    the launch folds a LayerNorm in (TapGemmArgs::ln_stat): ln = (rstd, -mean * rstd) of the row,
+//          sb points at the PAIRED per-tile vector {colsum[c], colsum[c+1], bias[c], bias[c+1]} per column pair
+//          (2 floats per column) and the columns become rstd * f + (-mean * rstd) * colsum + bias
+template <int NC, bool AUX = true, bool LNF = false>
 __device__ __forceinline__ void finish_cols(float (&f)[NC], const TapGemmArgs& a, long long pix, long long fb_off,
-                                            int col0, const float* sb, int ncols_valid, bool row_ok) {
+                                            int col0, const float* sb, int ncols_valid, bool row_ok,
+                                            float2 ln = make_float2(1.f, 0.f)) {
   if (!row_ok || ncols_valid <= 0) return;
   const int fmt = a.fmt;
   const bool full = ncols_valid >= NC;
   const bool vec_ok = full && ((col0 & 7) == 0);
-  if (sb != nullptr) {     // per-tile bias (+ frame bias when uniform over the tile), staged in smem
+  if constexpr (LNF) {     // folded LayerNorm: two packed FMAs per column pair (columns past n_total are staged as zeros)
+    const float2 r2 = make_float2(ln.x, ln.x), u2 = make_float2(ln.y, ln.y);
+#pragma unroll
+    for (int j = 0; j < NC / 2; ++j) {
+      const float4 q = reinterpret_cast<const float4*>(sb)[j];
+      const float2 o = __ffma2_rn(make_float2(f[2 * j], f[2 * j + 1]), r2,
+                                  __ffma2_rn(u2, make_float2(q.x, q.y), make_float2(q.z, q.w)));
+      f[2 * j] = o.x;
+      f[2 * j + 1] = o.y;
+    }
+  } else if (sb != nullptr) {     // per-tile bias (+ frame bias when uniform over the tile), staged in smem
 #pragma unroll
     for (int j = 0; j < NC / 4; ++j) {
       const float4 b = reinterpret_cast<const float4*>(sb)[j];
@@ -138,8 +208,8 @@ __device__ __forceinline__ void finish_cols(float (&f)[NC], const TapGemmArgs& a
   if (a.act == 1) {
 #pragma unroll
     for (int j = 0; j < NC; j += 2) {
-      const float2 o = gelu_erf2(make_float2(f[j], f[j + 1]));
-      f[j] = o.x;                     // gelu_erf2 returns 0.5 x (1 + erf(x / sqrt 2)): the GELU itself
+      const float2 o = gelu2(make_float2(f[j], f[j + 1]));
+      f[j] = o.x;
       f[j + 1] = o.y;
     }
   }
@@ -224,11 +294,11 @@ __device__ __forceinline__ void store_cols(const float (&f)[NC], const TapGemmAr
   }
 }
 
-template <int NC>
+template <int NC, bool LNF = false>
 __device__ __forceinline__ void finish_and_store(float (&f)[NC], const TapGemmArgs& a, long long pix,
                                                  long long zoff, long long fb_off, int col0, const float* sb,
-                                                 int ncols_valid, bool row_ok) {
-  finish_cols<NC>(f, a, pix, fb_off, col0, sb, ncols_valid, row_ok);
+                                                 int ncols_valid, bool row_ok, float2 ln = make_float2(1.f, 0.f)) {
+  finish_cols<NC, true, LNF>(f, a, pix, fb_off, col0, sb, ncols_valid, row_ok, ln);
   store_cols<NC>(f, a, pix, zoff, col0, ncols_valid, row_ok);
 }
 
@@ -269,7 +339,10 @@ __device__ __forceinline__ void stage_cols16(const float (&f)[16], uint32_t slab
 // The leader (rank 0) issues every MMA; commits are multicast to both CTAs' barriers; each CTA's TMA
 // counts its bytes on the leader's full barrier; both epilogues release the accumulator by arriving
 // on the leader's tmem_empty barrier.
-template <int CTAS>
+// LN: 0 plain; 1 the epilogue applies a folded LayerNorm (TapGemmArgs::ln_stat); 2 the epilogue leaves row statistics
+// for the next GEMM's folded LayerNorm (TapGemmArgs::stat_out).  Compile-time, so that the unrolled epilogue bodies
+// stay branch-free (a runtime switch inside them cost the GEGLU epilogue 44 branches and half its ILP).
+template <int CTAS, int LN>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
@@ -301,17 +374,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // activation matrix larger than L2 is read from HBM once instead of once per N tile; the N tile is rotated by
   // the M index so that ragged (e.g. 192 + 128) tiles alternate on every CTA.
   auto decode = [&](int t, int& m_lin, int& n_tile, int& z) {
+    // (launch-constant divisors through FastDiv: see tapgemm.cuh)
     if (a.n_fastest) {
-      const int per_z = pm_tiles * n_tiles;
-      z = t / per_z;
-      const int u = t - z * per_z;
-      m_lin = u / n_tiles;
-      n_tile = (u - m_lin * n_tiles + m_lin) % n_tiles;
+      int u;
+      a.fd_perz.divmod(t, z, u);
+      int nrem;
+      a.fd_nt.divmod(u, m_lin, nrem);
+      int nq;
+      a.fd_nt.divmod(nrem + m_lin, nq, n_tile);
     } else {
-      m_lin = t % pm_tiles;
-      const int rest = t / pm_tiles;
-      n_tile = rest % n_tiles;
-      z = rest / n_tiles;
+      int rest;
+      a.fd_pm.divmod(t, rest, m_lin);
+      a.fd_nt.divmod(rest, z, n_tile);
     }
   };
   const int num_iters = a.num_taps * a.kchunks;
@@ -384,10 +458,10 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         decode(t, m_lin, n_tile_p, z);
         int m_tile = m_lin * CTAS + rank;
         const int n0 = n_tile_p * BN;
-        const int z1 = z / a.zdiv, z0 = z - z1 * a.zdiv;
-        const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
-        const int ty = m_tile % a.tiles_y;
-        const int tn = m_tile / a.tiles_y;             // >= tiles_n for the phantom half of an odd pair: OOB -> zeros
+        int z1, z0, tx, ty, tn, mrest;
+        a.fd_zdiv.divmod(z, z1, z0);
+        a.fd_tx.divmod(m_tile, mrest, tx);
+        a.fd_ty.divmod(mrest, tn, ty);                 // tn >= tiles_n for the phantom half of an odd pair: OOB -> zeros
         int base[6] = {0, 0, 0, 0, 0, 0};   // slot 5 swallows unused roles
         base[a.dim_x] += tx * a.bw;
         base[a.dim_y] += ty * a.bh;
@@ -402,8 +476,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int it = it0; it < it1; ++it, ++it_g) {
           const int s = it_g % kSt;
           const uint32_t ph = (uint32_t)(it_g / kSt) & 1u;
-          const int tap = it / a.kchunks;
-          const int kc = it - tap * a.kchunks;
+          int tap, kc;
+          a.fd_kc.divmod(it, tap, kc);
           mbar_wait(&empty_bar[s], ph ^ 1u);
           if (it == it0) UG_TRACE(0, ui, 1);
           if (it == it1 - 1) UG_TRACE(0, ui, 2);
@@ -504,45 +578,112 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int slab_it = 0;
     uint32_t ring_it = 0;                   // chunk ring position of this column group (res_tma path)
     int tl = 0;
-    for (int ui = 0, t; (t = unit_at(ui)) >= 0; ++ui, ++tl) {
+    constexpr bool lnf = LN == 1;
+    constexpr bool stats = LN == 2;
+    // Per-tile vectors ONE TILE AHEAD.  Every tile needs, per thread, its column's bias (+ frame bias) and -- with a folded
+    // LayerNorm -- the column sum and this thread's row statistics.  Requested at the start of the tile that uses them,
+    // each is an exposed L2 round trip (~1000 clk under load) per tile in a loop whose period IS the epilogue's time; here
+    // the loads of tile i + 1 are issued while tile i is processed and their values wait in registers.  (Needs the cheap
+    // index decoding: with ten integer divisions per decode the second decode per tile cost more than the loads.)
+#ifdef UG_NO_TILE_PREFETCH
+    constexpr bool kPrefetch = false;
+#else
+    constexpr bool kPrefetch = true;
+#endif
+    const int et = threadIdx.x - 64;
+    const bool have_sb = a.bias != nullptr || a.fbias_uniform;
+    float pf_b = 0.f, pf_fb = 0.f, pf_c = 0.f;
+    float4 pf_s0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    // (predicated loads whose destination IS the carried variable: nothing here may read a loaded value, or the in-order
+    // warp waits for the L2 round trip at the point of issue)
+    auto prefetch_tile = [&](int tt) {
+      int pm, pn, pz;
+      decode(tt, pm, pn, pz);
+      const int mt = pm * CTAS + rank;
+      const int col = pn * BN + et;
+      const bool col_ok = have_sb && col < a.n_total;
+      pf_b = ld_act_pred(a.bias + col, col_ok && a.bias != nullptr);        // the time-embedding bias is rewritten every step
+      pf_fb = ld_act_pred(a.fbias + (long long)a.fd_fb.div(mt * BM) * a.fbias_ld + col, col_ok && a.fbias_uniform);
+      if constexpr (lnf) {
+        pf_c = ldg_pred(a.ln_colsum + col, col < a.n_total);
+        const long long prow = (long long)mt * BM + r;          // linear ops only: row = pixel
+        ld_stats_pred(a.ln_stat + prow * (a.ln_parts > 0 ? a.ln_parts : 1), a.ln_parts, prow < (long long)a.W, pf_s0, pf_s1);
+      }
+    };
+    int t = unit_at(0), t_next = -1;
+    if (t >= 0) prefetch_tile(t);
+    for (int ui = 0; t >= 0; ++ui, ++tl, t = t_next) {
       trace_tl = tl;
       if (tracer) UG_TRACE(2 + hsel, tl, 0);
+      t_next = unit_at(ui + 1);
+      const float cur_b = pf_b + pf_fb, cur_c = pf_c;
+      const float4 cur_s0 = pf_s0, cur_s1 = pf_s1;
       int m_lin, n_tile, z;
       decode(t, m_lin, n_tile, z);
       int m_tile = m_lin * CTAS + rank;
       const int m_tile_lin = m_tile;
       const int n0 = n_tile * BN;
       const int Ncur = n_cur(n0);
-      const int z1 = z / a.zdiv, z0 = z - z1 * a.zdiv;
-      const int tx = m_tile % a.tiles_x; m_tile /= a.tiles_x;
-      const int ty = m_tile % a.tiles_y;
-      const int tn = m_tile / a.tiles_y;
+      int z1, z0, tx, ty, tn, mrest;
+      a.fd_zdiv.divmod(z, z1, z0);
+      a.fd_tx.divmod(m_tile, mrest, tx);
+      a.fd_ty.divmod(mrest, tn, ty);
       const int x0 = tx * a.bw, y0 = ty * a.bh, nn0 = tn * a.bn;
       const bool row_ok = (ni < a.bn) && (x0 + xi < a.W) && (y0 + yi < a.H) && (nn0 + ni < a.N);
       const long long pix = ((long long)(nn0 + ni) * a.H + (y0 + yi)) * a.W + (x0 + xi);
       const long long zoff = (long long)z1 * a.out_z1stride + (long long)z0 * a.out_z0stride;
-      const long long fb_off = a.fbias ? (long long)((int)pix / a.fbias_div) * a.fbias_ld : 0;
+      const long long fb_off = a.fbias ? (long long)a.fd_fb.div((int)pix) * a.fbias_ld : 0;
       const int buf = tl & 1;
-      // bias (+ frame bias when every row of the tile shares the frame) of this tile's columns -> smem
-      const bool have_sb = a.bias != nullptr || a.fbias_uniform;
-      float* sbt = bias_s + buf * 256;
-      if (have_sb) {
-        const int et = threadIdx.x - 64, col = n0 + et;
-        float bsum = 0.f;
-        if (col < a.n_total) {
-          if (a.bias != nullptr) bsum = ld_act(a.bias + col);    // the time-embedding bias is rewritten every step
-          if (a.fbias_uniform)
-            bsum += ld_act(a.fbias + (long long)((int)((long long)m_tile_lin * BM) / a.fbias_div) * a.fbias_ld + col);
+      // LayerNorm folded into this GEMM: (rstd, -mean * rstd) of this thread's row, requested ahead of the accumulator
+      // wait.  Partial form: the (sum, sum of squares) pieces the producing GEMM's epilogue left, folded in index order.
+      float2 lnv = make_float2(0.f, 0.f);
+      if (lnf && row_ok) {
+        if (a.ln_parts == 0) {
+          lnv = make_float2(cur_s0.y, -cur_s0.x * cur_s0.y);
+        } else {                                                 // 2 or 4 (sum, sum of squares) partials, in index order
+          const float s1 = (cur_s0.x + cur_s0.z) + (cur_s1.x + cur_s1.z);
+          const float s2 = (cur_s0.y + cur_s0.w) + (cur_s1.y + cur_s1.w);
+          const float mean = s1 * a.ln_inv_c;
+          const float rstd = rsqrtf(fmaxf(fmaf(s2, a.ln_inv_c, -mean * mean), 0.f) + a.ln_eps);
+          lnv = make_float2(rstd, -mean * rstd);
         }
-        sbt[et] = bsum;
+      }
+      const float2 ln = lnv;
+      float st1 = 0.f, st2 = 0.f;                                        // producer side (stat_out)
+      // bias (+ frame bias when every row of the tile shares the frame) of this tile's columns -> smem
+      // folded LayerNorm: ONE buffer of paired {colsum, colsum, bias, bias} per column pair (the double buffer has no
+      // room for two vectors), fenced by a second barrier so that no warp still reads the previous tile's vector
+      float* sbt = lnf ? bias_s : bias_s + buf * 256;
+#if defined(UG_TRACE_SPLIT) && UG_TRACE_SPLIT == 1
+      if (tracer) UG_TRACE(2 + hsel, tl, 1);      // (debug variants) where inside the tile prologue the time goes
+#endif
+      if (have_sb) {
+        if (lnf) {
+          named_bar_sync(3, kEpiWarps * 32);
+          sbt[(et >> 1) * 4 + (et & 1)] = cur_c;
+          sbt[(et >> 1) * 4 + 2 + (et & 1)] = cur_b;
+        } else {
+          sbt[et] = cur_b;
+        }
         named_bar_sync(3, kEpiWarps * 32);
       }
+#if defined(UG_TRACE_SPLIT) && UG_TRACE_SPLIT == 2
+      if (tracer) UG_TRACE(2 + hsel, tl, 1);
+#endif
+      if (t_next >= 0) prefetch_tile(t_next);
+      (void)m_tile_lin; (void)kPrefetch;
+      auto sb_at = [&](int c) -> const float* { return lnf ? sbt + 2 * c : (have_sb ? sbt + c : nullptr); };
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 256u;
       const int BNh = BN >> 1;              // GEGLU: [BNh value | BNh gate] accumulator columns
       const bool prefetching = a.res_tma || (a.tma_store && !a.geglu && (a.res != nullptr || a.blend != nullptr));
       if (!prefetching) {                   // (the prefetching path waits after issuing its first loads)
+#if defined(UG_TRACE_SPLIT) && UG_TRACE_SPLIT == 3
+        if (tracer) UG_TRACE(2 + hsel, tl, 1);    // (debug variant) stamp BEFORE the accumulator wait: isolates the tile prologue
+#endif
         mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
+#ifndef UG_TRACE_SPLIT
         if (tracer) UG_TRACE(2 + hsel, tl, 1);
+#endif
         tc_fence_after();
       }
 
@@ -609,7 +750,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 32; ++j) f[j] *= a.scale;
           }
-          finish_cols<32, false>(f, a, pix, fb_off, out_c0 + c, have_sb ? sbt + c : nullptr, a.n_total - (out_c0 + c), row_ok);
+          finish_cols<32, false, lnf>(f, a, pix, fb_off, out_c0 + c, sb_at(c), a.n_total - (out_c0 + c), row_ok, ln);
           mbar_wait(&rbar[b], (it >> 2) & 1u);
           const uint32_t rowaddr = smem_u32(ring + b * 8192) + (uint32_t)r * 64u;
           const uint32_t sw = (uint32_t)((r >> 1) & 3);
@@ -635,6 +776,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t w2 = pack16x2(f[8 * j + 4], f[8 * j + 5], a.fmt), w3 = pack16x2(f[8 * j + 6], f[8 * j + 7], a.fmt);
             asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
           }
+          if constexpr (stats) stat_accum<32>(f, 32, st1, st2);
           fence_proxy_async_smem();
           named_bar_sync(1 + hsel, 128);
           if (issuer) {
@@ -716,11 +858,12 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) f[j] *= a.scale;
           }
           if (out_c0 + c + 32 <= n_out) {
-            finish_cols<32, false>(f, a, pix, fb_off, out_c0 + c, have_sb ? sbt + c : nullptr, n_out - (out_c0 + c), row_ok);
+            finish_cols<32, false, lnf>(f, a, pix, fb_off, out_c0 + c, sb_at(c), n_out - (out_c0 + c), row_ok, ln);
             apply_aux(which, f, c);
           } else {                                               // ragged tail: guarded scalar loads
-            finish_cols<32, true>(f, a, pix, fb_off, out_c0 + c, have_sb ? sbt + c : nullptr, n_out - (out_c0 + c), row_ok);
+            finish_cols<32, true, lnf>(f, a, pix, fb_off, out_c0 + c, sb_at(c), n_out - (out_c0 + c), row_ok, ln);
           }
+          if constexpr (stats) stat_accum<32>(f, n_out - (out_c0 + c), st1, st2);
           stage_cols32(f, slab, r, half, a.fmt);
         };
         prefetch(0, hsel * 64);                                  // overlaps the wait for the accumulator
@@ -778,16 +921,24 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int hq = 0; hq < 2; ++hq) {
                 const float2* bv = reinterpret_cast<const float2*>(sbt + c + 16 * hq);
                 const float2* bg = reinterpret_cast<const float2*>(sbt + BNh + c + 16 * hq);
+                // folded LayerNorm: paired {colsum, colsum, bias, bias} vectors of the value / gate columns
+                const float4* qv4 = reinterpret_cast<const float4*>(sbt + 2 * (c + 16 * hq));
+                const float4* qg4 = reinterpret_cast<const float4*>(sbt + 2 * (BNh + c + 16 * hq));
+                const float2 lr2 = make_float2(lnv.x, lnv.x), lu2 = make_float2(lnv.y, lnv.y);
                 float fq[16];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   float2 val = make_float2(__uint_as_float(v[hq][2 * j]), __uint_as_float(v[hq][2 * j + 1]));
                   float2 gate = make_float2(__uint_as_float(g[hq][2 * j]), __uint_as_float(g[hq][2 * j + 1]));
-                  if (have_sb) {
+                  if constexpr (lnf) {
+                    const float4 qv = qv4[j], qg = qg4[j];
+                    val = __ffma2_rn(val, lr2, __ffma2_rn(lu2, make_float2(qv.x, qv.y), make_float2(qv.z, qv.w)));
+                    gate = __ffma2_rn(gate, lr2, __ffma2_rn(lu2, make_float2(qg.x, qg.y), make_float2(qg.z, qg.w)));
+                  } else if (have_sb) {
                     val = __fadd2_rn(val, bv[j]);
                     gate = __fadd2_rn(gate, bg[j]);
                   }
-                  const float2 o = __fmul2_rn(val, gelu_erf2(gate));
+                  const float2 o = __fmul2_rn(val, gelu2(gate));
                   fq[2 * j] = o.x;
                   fq[2 * j + 1] = o.y;
                 }
@@ -807,7 +958,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] *= a.scale;
               }
-              finish_cols<32>(f, a, pix, fb_off, out_c0 + c, have_sb ? sbt + c : nullptr, n_out - (out_c0 + c), row_ok);
+              finish_cols<32, true, lnf>(f, a, pix, fb_off, out_c0 + c, sb_at(c), n_out - (out_c0 + c), row_ok, ln);
+              if constexpr (stats) stat_accum<32>(f, n_out - (out_c0 + c), st1, st2);
             }
             stage_cols32(f, slab, r, half, a.fmt);
           }
@@ -835,12 +987,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int vc = n0 + c + j, gc = n0 + BNh + c + j;
             float val = __uint_as_float(v[j]);
             float gate = __uint_as_float(g[j]);
-            if (have_sb) {
+            if constexpr (lnf) {
+              const int iv = ((c + j) >> 1) * 4 + ((c + j) & 1), ig = ((BNh + c + j) >> 1) * 4 + ((BNh + c + j) & 1);
+              val = fmaf(val, lnv.x, fmaf(lnv.y, sbt[iv], sbt[iv + 2]));
+              gate = fmaf(gate, lnv.x, fmaf(lnv.y, sbt[ig], sbt[ig + 2]));
+            } else if (have_sb) {
               val += sbt[c + j];
               gate += sbt[BNh + c + j];
             }
             (void)vc; (void)gc;
-            f[j] = val * gelu_erf(gate);
+            f[j] = val * gelu1(gate);
           }
           finish_and_store<32>(f, a, pix, zoff, fb_off, ocol_tile + c, nullptr, a.n_total / 2 - (ocol_tile + c), row_ok);
         }
@@ -861,7 +1017,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int j = 0; j < 32; ++j) f[j] *= a.scale;
             }
-            finish_and_store<32>(f, a, pix, zoff, fb_off, n0 + c, have_sb ? sbt + c : nullptr, a.n_total - (n0 + c), row_ok);
+            finish_and_store<32, lnf>(f, a, pix, zoff, fb_off, n0 + c, sb_at(c), a.n_total - (n0 + c), row_ok, ln);
+            if constexpr (stats) stat_accum<32>(f, a.n_total - (n0 + c), st1, st2);
           } else {
             uint32_t v[16];
             tmem_ld_32x16(trow + c, v);
@@ -870,11 +1027,16 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             float f[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) * a.scale;
-            finish_and_store<16>(f, a, pix, zoff, fb_off, n0 + c, have_sb ? sbt + c : nullptr, a.n_total - (n0 + c), row_ok);
+            finish_and_store<16, lnf>(f, a, pix, zoff, fb_off, n0 + c, sb_at(c), a.n_total - (n0 + c), row_ok, ln);
+            if constexpr (stats) stat_accum<16>(f, a.n_total - (n0 + c), st1, st2);
           }
         }
         if (!released) release(buf);         // this warp had no chunk in this tile (narrow tile)
       }
+      // producer side of a folded LayerNorm: this row's partial over the columns this group finished in this tile
+      // (zeros when the group had none), one slot per (N tile, column group), each written exactly once per launch
+      if (stats && row_ok)
+        a.stat_out[pix * a.stat_parts + n_tile * 2 + hsel] = make_float2(st1, st2);
       if (tracer) UG_TRACE(2 + hsel, tl, 3);
     }
     if (issuer && a.tma_store) bulk_wait_group<0>();            // all tile stores have landed
@@ -1105,9 +1267,12 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
                    const TapGemmArgs& args_in, int batch, cudaStream_t stream, const CUtensorMap* tmR) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(tapgemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(tapgemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes2);
+    cudaError_t e = cudaSuccess;
+#define UG_SMEM_ATTR(K, BYTES) if (e == cudaSuccess) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES)
+    UG_SMEM_ATTR((tapgemm_kernel<1, 0>), kSmemBytes);  UG_SMEM_ATTR((tapgemm_kernel<1, 1>), kSmemBytes);
+    UG_SMEM_ATTR((tapgemm_kernel<1, 2>), kSmemBytes);  UG_SMEM_ATTR((tapgemm_kernel<2, 0>), kSmemBytes2);
+    UG_SMEM_ATTR((tapgemm_kernel<2, 1>), kSmemBytes2); UG_SMEM_ATTR((tapgemm_kernel<2, 2>), kSmemBytes2);
+#undef UG_SMEM_ATTR
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
@@ -1130,10 +1295,31 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     return (int)cudaErrorInvalidValue;             // the GEGLU epilogue is bias + gate only
   if (args.res_tma && (tmR == nullptr || !args.tma_store || args.res == nullptr || args.geglu || (args.n_total & 31)))
     return (int)cudaErrorInvalidValue;
+  const bool rows_flat = args.tiles_y == 1 && args.tiles_n == 1 && args.bh == 1 && args.bn == 1 && batch == 1;
+  if ((args.ln_stat != nullptr || args.stat_out != nullptr) && (!rows_flat || args.ksplit > 1))
+    return (int)cudaErrorInvalidValue;             // LayerNorm fold: linear ops (row = pixel) only
+  if (args.ln_stat != nullptr && (args.ln_colsum == nullptr || args.bias == nullptr || args.ln_parts < 0 ||
+                                  args.ln_parts > 4 || (args.ln_parts & 1) || args.scale != 1.0f))
+    return (int)cudaErrorInvalidValue;
+  if (args.stat_out != nullptr && (args.geglu || args.out_fp32 || args.ln_stat != nullptr))
+    return (int)cudaErrorInvalidValue;             // a launch is a consumer or a producer of row statistics, never both
   const CUtensorMap& mc = tmC ? *tmC : tmA;
   const CUtensorMap& mr = tmR ? *tmR : tmA;
   args.batch = batch;
   args.n_tiles = (args.n_total + args.bn_tile - 1) / args.bn_tile;
+  args.stat_parts = 2 * args.n_tiles;
+  {
+    const long long mt = (long long)args.tiles_x * args.tiles_y * args.tiles_n;
+    const int pm = (int)((mt + ctas - 1) / ctas);
+    args.fd_pm = make_fastdiv(pm);
+    args.fd_nt = make_fastdiv(args.n_tiles);
+    args.fd_perz = make_fastdiv(pm * args.n_tiles);
+    args.fd_tx = make_fastdiv(args.tiles_x);
+    args.fd_ty = make_fastdiv(args.tiles_y);
+    args.fd_zdiv = make_fastdiv(args.zdiv);
+    args.fd_fb = make_fastdiv(args.fbias_div);
+    args.fd_kc = make_fastdiv(args.kchunks);
+  }
   {
     // plain GEMMs whose activation matrix does not survive in L2 (126 MB, shared with the output stream) until the
     // next N pass.  Measured at cfg2: M76800 N320 K1280 100 -> 85 us, M19200 N640 K2560 87 -> 75 us; convolutions
@@ -1153,9 +1339,13 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     args.sched = have ? sv.dev_ptr : nullptr;
     args.sched_len = have ? sv.len : 0;
   }
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TapGemmArgs);
+  static const Kern kern1[3] = {tapgemm_kernel<1, 0>, tapgemm_kernel<1, 1>, tapgemm_kernel<1, 2>};
+  static const Kern kern2[3] = {tapgemm_kernel<2, 0>, tapgemm_kernel<2, 1>, tapgemm_kernel<2, 2>};
+  const int ln_mode = args.ln_stat != nullptr ? 1 : args.stat_out != nullptr ? 2 : 0;
   if (ctas == 1) {
     const int grid = (int)(units < sms ? units : sms);
-    return (int)launch_pdl_tag("tapgemm", tapgemm_kernel<1>, dim3(grid), dim3(kThreads), kSmemBytes,
+    return (int)launch_pdl_tag("tapgemm", kern1[ln_mode], dim3(grid), dim3(kThreads), kSmemBytes,
                            stream, tmA, tmB, mc, mr, args);
   }
   const long long slots = sms / 2;
@@ -1174,7 +1364,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 1 : 2;
-  return (int)cudaLaunchKernelEx(&cfg, tapgemm_kernel<2>, tmA, tmB, mc, mr, args);
+  return (int)cudaLaunchKernelEx(&cfg, kern2[ln_mode], tmA, tmB, mc, mr, args);
 }
 
 }  // namespace ug

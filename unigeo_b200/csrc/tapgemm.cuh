@@ -23,6 +23,35 @@ namespace ug {
 
 constexpr int kMaxTaps = 9;
 
+// Division of a non-negative int (< 2^31) by a launch constant without the ~100-clock integer division sequence: the
+// persistent kernel decodes a unit index into (M tile, N tile, batch, x, y, n, frame) once per tile and role, ten
+// dependent divisions that made up most of a 1650-clock tile prologue in front of an epilogue-bound 6300-clock period
+// (tools/trace_tapgemm.py ... split).  q = (n * m) >> (31 + s), s = ceil(log2 d), m = ceil(2^(31+s) / d): exact for
+// every n < 2^31 (checked on the host against n / d, tests/test_host_logic.py).
+struct FastDiv {
+  unsigned int d, m, sh;     // d <= 1: identity
+#if defined(__CUDACC__)
+  __device__ __forceinline__ int div(int n) const { return d <= 1u ? n : (int)(__umulhi((unsigned int)n, m) >> sh); }
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const { q = div(n); r = n - q * (int)d; }
+#endif
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.d = d < 1 ? 1u : (unsigned int)d;
+  f.m = 0u;
+  f.sh = 0u;
+  if (f.d > 1u) {
+    unsigned int s = 0;
+    while ((1ull << s) < f.d) ++s;
+    f.m = (unsigned int)(((1ull << (31 + s)) + f.d - 1) / f.d);
+    f.sh = s - 1;
+  }
+  return f;
+}
+inline int fastdiv_host(const FastDiv& f, int n) {       // the device arithmetic, for the host-side check
+  return f.d <= 1u ? n : (int)((((unsigned long long)(unsigned int)n * f.m) >> 32) >> f.sh);
+}
+
 struct TapGemmArgs {
   // ---- M tiling over the OUTPUT pixel grid (n, y, x); pixel = (n*H + y)*W + x
   int tiles_x, tiles_y, tiles_n;
@@ -56,6 +85,9 @@ struct TapGemmArgs {
 #ifdef UG_TAPGEMM_TRACE
   unsigned long long* trace;   // debug builds (tools/trace_tapgemm.py): [grid units][4 roles][kTraceTiles][4] clock64 stamps
 #endif
+  // filled by launch_tapgemm: divisors of the per-tile index decoding
+  FastDiv fd_pm, fd_nt, fd_perz;   // M units per N tile (pairs count once), N tiles, their product
+  FastDiv fd_tx, fd_ty, fd_zdiv, fd_fb, fd_kc;   // tiles_x, tiles_y, zdiv, fbias_div, kchunks
   const int* sched;        // filled by launch_tapgemm: [grid units][sched_len] unit indices (-1 = none) when the host
   int sched_len;           // balanced ragged-width tiles over the CTAs (list scheduling); nullptr = round-robin
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
@@ -76,6 +108,18 @@ struct TapGemmArgs {
   long long ldb;
   float alpha;
   float scale;             // value = acc * scale + ...
+  // ---- LayerNorm folded into this GEMM (linear ops; rows = pixels).  The A operand is the RAW row x, the weights are
+  // W' = gamma (.) W, and the epilogue applies   rstd[row] * (acc - mean[row] * colsum[col]) + bias'[col]
+  // with colsum[n] = sum_k W'[n][k] and bias' = bias + W beta: exactly LayerNorm(x) W^T + bias, without a normalised
+  // copy of x ever existing.  ln_stat == nullptr: off.
+  const float2* ln_stat;   // ln_parts == 0: [row] = (mean, rstd).  ln_parts = P > 0: [row * P + p] = (sum, sum of squares)
+  int ln_parts;            //   partials of the row as its producing GEMM's epilogue left them, folded here in index order
+  float ln_inv_c, ln_eps;  //   (1 / row length, epsilon) for the partial form
+  const float* ln_colsum;  // [n_total] (GEGLU: in the interleaved column order of the weights)
+  // ---- producer side of the same fusion: every finished output row leaves its (sum, sum of squares) over the columns
+  // this CTA's column group handled at stat_out[row * stat_parts + n_tile * 2 + group] (fp32, pre-rounding values)
+  float2* stat_out;
+  int stat_parts;          // = 2 * n_tiles (filled by launch_tapgemm)
 };
 
 #ifdef UG_TAPGEMM_TRACE

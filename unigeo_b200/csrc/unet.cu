@@ -112,6 +112,25 @@ void fuse_geglu(Ctx& c, const std::string& k, cudaStream_t st) {
   add_weight(c, k + ".net.0.proj.geglu.bias", bd, true, 1, n, 1);
 }
 
+// LayerNorm `norm` followed by the linear layer `lin` (weight key lin + ".weight", optional lin + ".bias") ->
+// lin + ".lnf.weight" = gamma (.) W, ".lnf.colsum", ".lnf.bias" = bias + W beta: what a tapgemm launch with
+// TapGemmArgs::ln_stat consumes (the GEMM then reads the un-normalised rows)
+void fold_layernorm(Ctx& c, const std::string& norm, const std::string& lin, cudaStream_t st) {
+  if (c.has(lin + ".lnf.weight")) return;
+  const Weight& w = c.W(lin + ".weight");
+  UG_CHECK(w.taps == 1 && !w.is_f32 && w.cin_pad == w.cin, UG_ERR_WEIGHT, "fold_layernorm: plain matrix expected: " + lin);
+  const int N = w.cout, K = w.cin;
+  void* wf = c.dmalloc((size_t)N * K * 2);
+  float* cs = reinterpret_cast<float*>(c.dmalloc((size_t)N * 4));
+  float* bo = reinterpret_cast<float*>(c.dmalloc((size_t)N * 4));
+  const float* bias = c.has(lin + ".bias") ? c.F(lin + ".bias") : nullptr;
+  const int r = launch_ln_fold_weights(w.p, c.F(norm + ".weight"), c.F(norm + ".bias"), bias, wf, cs, bo, N, K, c.fmt, st);
+  UG_CHECK(r == 0, UG_ERR_CUDA, "ln_fold_weights: " + lin);
+  add_weight(c, lin + ".lnf.weight", wf, false, 1, N, K);
+  add_weight(c, lin + ".lnf.colsum", cs, true, 1, N, 1);
+  add_weight(c, lin + ".lnf.bias", bo, true, 1, N, 1);
+}
+
 void unet_finalize(Ctx& c, cudaStream_t st) {
   if (!c.has(U + "conv_in.weight")) return;   // VAE-only context
   if (!c.unet) c.unet = new UNetModel();
@@ -124,6 +143,20 @@ void unet_finalize(Ctx& c, cudaStream_t st) {
     fuse_geglu(c, k + ".temporal_transformer_blocks.0.ff_in", st);
     fuse_geglu(c, k + ".temporal_transformer_blocks.0.ff", st);
   }
+  // LayerNorms folded into the GEMMs that consume them: opt-in (UG_LN_FOLD=1, read at every finalize).  Measured at cfg2
+  // (profiles/r02_ln_fold.txt): 250 fewer launches and 10 fewer activation passes per transformer, but the consumers'
+  // epilogues are instruction-issue bound at K = 320 and the two extra packed FMAs per column pair cost what the
+  // LayerNorm launches did -- 28.4 ms per step either way.
+  { const char* e = getenv("UG_LN_FOLD"); m.ln_fold = e != nullptr && atoi(e) != 0; }
+  if (m.ln_fold)
+    for (const std::string& k : t.transformers) {
+      const std::string sb = k + ".transformer_blocks.0", tb = k + ".temporal_transformer_blocks.0";
+      fold_layernorm(c, sb + ".norm1", sb + ".attn1.to_qkv", st);
+      fold_layernorm(c, sb + ".norm3", sb + ".ff.net.0.proj.geglu", st);
+      fold_layernorm(c, tb + ".norm_in", tb + ".ff_in.net.0.proj.geglu", st);
+      fold_layernorm(c, tb + ".norm1", tb + ".attn1.to_qkv", st);
+      fold_layernorm(c, tb + ".norm3", tb + ".ff.net.0.proj.geglu", st);
+    }
   if (c.has(U + "__temb_all.weight")) return;
   // stack every time_emb_proj (spatial + temporal resnets) into one GEMV; fold conv1.bias in
   const int E = c.cfg.unet_block_out[0] * 4;
@@ -183,6 +216,15 @@ void unet_prepare(Ctx& c, int T, cudaStream_t st) {
     op_gemv(c, c.M(k + ".time_pos_embed.linear_2.weight"), c.F(k + ".time_pos_embed.linear_2.bias"), nullptr,
             hid, tp, T, C, 4 * C, 0, 0);
     m.time_pos[k] = tp;
+    {
+      // LayerNorm fold: the spatial block stores h + emb_t, and the AlphaBlender input alpha * h = alpha * (h + emb_t) -
+      // alpha * emb_t gets the correction as a per-frame bias of the last temporal GEMM: (1 - alpha) * (-alpha / (1 - alpha)) emb_t
+      const float alpha = sigmoidf_host(c.W(k + ".time_mixer.mix_factor").host.at(0));
+      float* tpb = reinterpret_cast<float*>(c.dmalloc((size_t)T * C * 4));
+      const float a = (1.0f - alpha) > 1e-4f ? -alpha / (1.0f - alpha) : 0.0f;
+      op_check(c, launch_scale_f32(tp, a, tpb, (long long)T * C, st), "scale");
+      m.time_pos_blend[k] = tpb;
+    }
     m.attn2_spatial[k] = a2s;
     m.attn2_temporal[k] = a2t;
   }
@@ -306,6 +348,72 @@ Act st_transformer(Ctx& c, const std::string& key, const Act& x, int T, int head
 
   op_gn(c, x.p, C, nullptr, 0, rows, hw, c.F(key + ".norm.weight"), c.F(key + ".norm.bias"),
         c.cfg.eps_transformer_norm, 0, n);
+
+  const float alpha_mix = sigmoidf_host(c.W(key + ".time_mixer.mix_factor").host.at(0));
+  if (m.ln_fold && (1.0f - alpha_mix) > 1e-4f) {
+    // ---- every LayerNorm folded into the GEMM behind it: the GEMM reads the raw rows with gamma-scaled weights and
+    // its epilogue applies rstd * (acc - mean * colsum) + (bias + W beta); the row statistics come out of the epilogue
+    // of the GEMM that PRODUCED the rows (or one row_stats pass where that launch cannot provide them).  No normalised
+    // tensor is ever written: 5 LayerNorm launches and 10 activation passes per transformer disappear.
+    const int cap = 4;     // partials a consumer keeps in registers one tile ahead; wider producers run a row_stats pass
+    float2* stat[2] = {reinterpret_cast<float2*>(c.allocf(rows * cap * 2)), reinterpret_cast<float2*>(c.allocf(rows * cap * 2))};
+    int parts = 0, si = 0;
+    auto produce = [&](Epi& e) {
+      e.stat_out = stat[si]; e.stat_parts = &parts; e.stat_cap = cap; e.stat_eps = ln_eps;
+    };
+    auto consume = [&](Epi& e, const std::string& lin) {
+      e.ln_stat = stat[si]; e.ln_parts = parts; e.ln_inv_c = 1.0f / (float)C; e.ln_eps = ln_eps;
+      e.ln_colsum = c.F(lin + ".lnf.colsum"); e.bias = c.F(lin + ".lnf.bias");
+      si ^= 1;
+    };
+    const float* tp = m.time_pos.at(key);
+    { Epi e; e.out = h; e.ldc = C; e.bias = c.F(key + ".proj_in.bias"); produce(e);
+      op_linear(c, n, rows, C, C, c.M(key + ".proj_in.weight"), C, e); }
+    // spatial block: norm1 -> qkv
+    { Epi e; e.out = big; e.ldc = 3 * C; consume(e, sb + ".attn1.to_qkv");
+      op_linear(c, h, rows, C, C, c.M(sb + ".attn1.to_qkv.lnf.weight"), 3 * C, e); }
+    op_spatial_attention(c, big, T, hw, C, C / heads, ao);
+    { Epi e; e.out = h1; e.ldc = C; e.bias = c.F(sb + ".attn1.to_out.0.bias");
+      e.res = h; e.ldr = C;
+      e.fbias = m.attn2_spatial.at(key); e.fbias_ld = C; e.fbias_div = hw;     // + attn2 (collapsed)
+      produce(e);
+      op_linear(c, ao, rows, C, C, c.M(sb + ".attn1.to_out.0.weight"), C, e); }
+    // norm3 -> GEGLU
+    { Epi e; e.out = big; e.ldc = 4 * C; e.geglu = 1; consume(e, sb + ".ff.net.0.proj.geglu");
+      op_linear(c, h1, rows, C, C, c.M(sb + ".ff.net.0.proj.geglu.lnf.weight"), 8 * C, e); }
+    // hp = spatial block output + emb_t[frame]: the temporal block's input stream
+    { Epi e; e.out = h; e.ldc = C; e.bias = c.F(sb + ".ff.net.2.bias"); e.res = h1; e.ldr = C;
+      e.fbias = tp; e.fbias_ld = C; e.fbias_div = hw;
+      produce(e);
+      op_linear(c, big, rows, 4 * C, 4 * C, c.M(sb + ".ff.net.2.weight"), C, e); }
+    // temporal block: norm_in -> ff_in (GEGLU) -> + hp
+    { Epi e; e.out = big; e.ldc = 4 * C; e.geglu = 1; consume(e, tb + ".ff_in.net.0.proj.geglu");
+      op_linear(c, h, rows, C, C, c.M(tb + ".ff_in.net.0.proj.geglu.lnf.weight"), 8 * C, e); }
+    { Epi e; e.out = h1; e.ldc = C; e.bias = c.F(tb + ".ff_in.net.2.bias"); e.res = h; e.ldr = C;
+      produce(e);
+      op_linear(c, big, rows, 4 * C, 4 * C, c.M(tb + ".ff_in.net.2.weight"), C, e); }
+    // norm1 -> temporal qkv
+    { Epi e; e.out = big; e.ldc = 3 * C; consume(e, tb + ".attn1.to_qkv");
+      op_linear(c, h1, rows, C, C, c.M(tb + ".attn1.to_qkv.lnf.weight"), 3 * C, e); }
+    op_temporal_attention(c, big, ao, T, hw, C);
+    void* h2 = n;   // the GroupNorm output is dead after proj_in
+    { Epi e; e.out = h2; e.ldc = C; e.bias = c.F(tb + ".attn1.to_out.0.bias"); e.res = h1; e.ldr = C;
+      e.fbias = m.attn2_temporal.at(key); e.fbias_ld = C; e.fbias_div = (int)rows;  // + attn2 (one vector)
+      produce(e);
+      op_linear(c, ao, rows, C, C, c.M(tb + ".attn1.to_out.0.weight"), C, e); }
+    // norm3 -> GEGLU -> ff.net.2 + h2, mixed with x_spatial = hp - emb_t
+    { Epi e; e.out = big; e.ldc = 4 * C; e.geglu = 1; consume(e, tb + ".ff.net.0.proj.geglu");
+      op_linear(c, h2, rows, C, C, c.M(tb + ".ff.net.0.proj.geglu.lnf.weight"), 8 * C, e); }
+    { Epi e; e.out = h1; e.ldc = C; e.bias = c.F(tb + ".ff.net.2.bias"); e.res = h2; e.ldr = C;
+      e.blend = h; e.ldb = C; e.alpha = alpha_mix;
+      e.fbias = m.time_pos_blend.at(key); e.fbias_ld = C; e.fbias_div = hw;
+      op_linear(c, big, rows, 4 * C, 4 * C, c.M(tb + ".ff.net.2.weight"), C, e); }
+    { Epi e; e.out = out.p; e.ldc = C; e.bias = c.F(key + ".proj_out.bias"); e.res = x.p; e.ldr = C;
+      op_linear(c, h1, rows, C, C, c.M(key + ".proj_out.weight"), C, e); }
+    c.ws.release(mk);
+    return out;
+  }
+
   { Epi e; e.out = h; e.ldc = C; e.bias = c.F(key + ".proj_in.bias");
     op_linear(c, n, rows, C, C, c.M(key + ".proj_in.weight"), C, e); }
 

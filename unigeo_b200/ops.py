@@ -90,6 +90,28 @@ def layernorm(x, gamma, beta, eps=1e-5, add=None, add_div=1):
     return y
 
 
+def ln_linear(x, gamma, beta, W, bias=None, eps=1e-5, geglu=False, producer=None):
+    """LayerNorm(x) @ W.T (+bias) in the folded form (see ug_op_ln_linear).  x [M,K], W [N,K].
+
+    producer = (x0 [M,K0], W0 [K,K0], bias0 | None, res0 [M,K] | None): x is computed as x0 @ W0.T (+bias0) (+res0)
+    first and its row statistics come out of that GEMM's epilogue; returns (x, y) then."""
+    d = _chk16(x, W)
+    M, K = x.shape
+    N = W.shape[0]
+    y = torch.empty((M, N // 2 if geglu else N), device=x.device, dtype=x.dtype)
+    if producer is None:
+        _lib.check(_lib.load().ug_op_ln_linear(d, None, 0, None, None, None, x.data_ptr(), M, K, gamma.data_ptr(),
+                                               beta.data_ptr(), float(eps), W.data_ptr(), N, _p(bias), int(geglu),
+                                               y.data_ptr(), _s()))
+        return y
+    x0, W0, b0, r0 = producer
+    _chk16(x0, W0, r0)
+    _lib.check(_lib.load().ug_op_ln_linear(d, x0.data_ptr(), x0.shape[1], W0.data_ptr(), _p(b0), _p(r0), x.data_ptr(),
+                                           M, K, gamma.data_ptr(), beta.data_ptr(), float(eps), W.data_ptr(), N,
+                                           _p(bias), int(geglu), y.data_ptr(), _s()))
+    return x, y
+
+
 def spatial_attention(qkv, F, N, C, head_dim=64):
     """qkv [F*N,3C] -> [F*N,C]."""
     d = _chk16(qkv)
