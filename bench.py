@@ -523,13 +523,27 @@ def run_parity(a, eng, cfg, dev):
         m_ref = OM.depth_evaluation(ref_depth, gt["gt_depths"], gt["gt_masks"])
         m_got = OM.depth_evaluation(out["pred_depths"], gt["gt_depths"], gt["gt_masks"])
         keys = ("Abs Rel", "delta < 1.25", "delta < 1.25^2", "delta < 1.25^3")
+        # second label, built from the oracle arm's own prediction: the scene label cannot tell two randomly initialised
+        # arms apart (least-squares alignment -> scale ~ 0 for both), this one can (harness.synthetic.correlated_gt)
+        from harness.synthetic import correlated_gt
+        cg = correlated_gt(ref_depth)
+        s_ref = OM.depth_evaluation(ref_depth, cg["gt_depths"], cg["gt_masks"])
+        s_got = OM.depth_evaluation(out["pred_depths"], cg["gt_depths"], cg["gt_masks"])
+        sens_ok = bool(abs(s_got["Abs Rel"] - s_ref["Abs Rel"]) <= 1e-3 and
+                       all(abs(s_got[k] - s_ref[k]) <= 2e-3 for k in keys[1:]))
+        sens = {"label": "oracle depth x (1 + 0.15 smooth field) + 0.1 (prediction-correlated; alignment scale ~ 1)",
+                "abs_rel": {"b200": s_got["Abs Rel"], "oracle": s_ref["Abs Rel"],
+                            "abs_diff": abs(s_got["Abs Rel"] - s_ref["Abs Rel"])},
+                "delta_abs_diff": {k: abs(s_got[k] - s_ref[k]) for k in keys[1:]}, "pass": sens_ok}
         return {"what": f"DepthCrafter.forward, {steps} steps, {T}x{H}x{W}, {a.dtype} kernels vs fp32 oracle on the same GPU",
                 "abs_rel": {"b200": m_got["Abs Rel"], "oracle": m_ref["Abs Rel"], "abs_diff": abs(m_got["Abs Rel"] - m_ref["Abs Rel"])},
                 "delta_abs_diff": {k: abs(m_got[k] - m_ref[k]) for k in keys[1:]},
                 "valid_pixels_equal": m_got["valid_pixels"] == m_ref["valid_pixels"],
                 "max_abs_depth_diff": float((out["pred_depths"] - ref_depth).abs().max()),
+                "mean_rel_depth_diff": float(((out["pred_depths"] - ref_depth).abs() / ref_depth).mean()),
+                "prediction_correlated_label": sens,
                 "tolerance": {"abs_rel": 1e-3, "delta": 2e-3}, "oracle_seconds": t_oracle,
-                "pass": bool(abs(m_got["Abs Rel"] - m_ref["Abs Rel"]) <= 1e-3 and
+                "pass": bool(sens_ok and abs(m_got["Abs Rel"] - m_ref["Abs Rel"]) <= 1e-3 and
                              all(abs(m_got[k] - m_ref[k]) <= 2e-3 for k in keys[1:]))}
     finally:
         torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32, torch.backends.cudnn.enabled = tf32

@@ -69,3 +69,22 @@ def gt_label(data: dict) -> dict:
         normals.append(torch.from_numpy(data["cam_normal"][i]).permute(1, 2, 0))
         masks.append(torch.from_numpy(data["mask"][i]).bool())
     return {"gt_depths": torch.stack(depths), "gt_normals": torch.stack(normals), "gt_masks": torch.stack(masks)}
+
+
+def correlated_gt(ref_depth, amplitude: float = 0.15, offset: float = 0.1):
+    """A ground truth that DEPENDS on a prediction: depth' = depth * (1 + amplitude * smooth field) + offset.
+
+    Scoring two arms against the synthetic scene says little when the network is randomly initialised -- its output is
+    uncorrelated with the scene, the least-squares alignment (metrics/alignment.py:150-167) then returns scale ~ 0 and
+    both arms collapse onto the same constant, whatever they predicted.  Against THIS label (built from the oracle arm's
+    own prediction) the alignment keeps scale ~ 1, Abs Rel sits near amplitude / 2, and any deviation of the other arm's
+    depths moves its score: the parity number is sensitive to the thing it is meant to compare."""
+    import torch
+    d = torch.as_tensor(ref_depth, dtype=torch.float32)
+    T, H, W = d.shape
+    yy = torch.linspace(0, 1, H)[:, None]
+    xx = torch.linspace(0, 1, W)[None, :]
+    field = torch.sin(6.2831853 * 3 * xx) * torch.cos(6.2831853 * 2 * yy)
+    tt = 1.0 + 0.25 * torch.cos(torch.arange(T, dtype=torch.float32) * 0.7)[:, None, None]
+    gt = d * (1.0 + amplitude * field[None] * tt) + offset
+    return {"gt_depths": gt, "gt_masks": torch.ones_like(gt, dtype=torch.bool)}

@@ -143,6 +143,18 @@ def test_cfg2_plugin_abs_rel_parity(arms, cuda):
         assert abs(m_ref[k] - m_got[k]) <= 2e-3, k
     assert m_ref["valid_pixels"] == m_got["valid_pixels"]
     assert abs(n_ref["normal mean"] - n_got["normal mean"]) <= 0.1
+    # the same two arms against a label that depends on the prediction (harness.synthetic.correlated_gt): with randomly
+    # initialised weights the scene label above aligns both arms to the same constant, this one does not
+    from harness.synthetic import correlated_gt
+    ref_t = torch.from_numpy(np.asarray(ref_depth, dtype=np.float32))
+    cg = correlated_gt(ref_t)
+    s_ref = OM.depth_evaluation(ref_t, cg["gt_depths"], cg["gt_masks"])
+    s_got = OM.depth_evaluation(out["pred_depths"], cg["gt_depths"], cg["gt_masks"])
+    print("cfg2 correlated-label ref", s_ref, "\ncfg2 correlated-label got", s_got)
+    assert 0.01 < s_ref["Abs Rel"] < 0.2, s_ref                 # the label is neither trivial nor unrelated
+    assert abs(s_ref["Abs Rel"] - s_got["Abs Rel"]) <= 1e-3, (s_ref["Abs Rel"], s_got["Abs Rel"])
+    for k in ("delta < 1.25", "delta < 1.25^2", "delta < 1.25^3"):
+        assert abs(s_ref[k] - s_got[k]) <= 2e-3, k
 
 
 def test_vae_encoder_in_bf16_survives_activations_beyond_the_fp16_range(cuda):
