@@ -596,8 +596,8 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     float4 pf_s0 = make_float4(0.f, 0.f, 0.f, 0.f), pf_s1 = make_float4(0.f, 0.f, 0.f, 0.f);
     // (predicated loads whose destination IS the carried variable: nothing here may read a loaded value, or the in-order
     // warp waits for the L2 round trip at the point of issue)
+    int pm = 0, pn = 0, pz = 0;                  // the prefetched tile's decoded index: decoded once, used by both
     auto prefetch_tile = [&](int tt) {
-      int pm, pn, pz;
       decode(tt, pm, pn, pz);
       const int mt = pm * CTAS + rank;
       const int col = pn * BN + et;
@@ -618,8 +618,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       t_next = unit_at(ui + 1);
       const float cur_b = pf_b + pf_fb, cur_c = pf_c;
       const float4 cur_s0 = pf_s0, cur_s1 = pf_s1;
-      int m_lin, n_tile, z;
-      decode(t, m_lin, n_tile, z);
+      const int m_lin = pm, n_tile = pn, z = pz;               // decoded when this tile's vectors were requested
       int m_tile = m_lin * CTAS + rank;
       const int m_tile_lin = m_tile;
       const int n0 = n_tile * BN;
