@@ -2,7 +2,8 @@
     python tools/sass_summary.py > profiles/r02_sass_opcodes.txt
 Counts, per device function of libunigeo_b200.so, the mnemonics that prove the Blackwell-native paths
 (B200_PROFILING.md): UTC*MMA = tcgen05.mma, LDTM / STTM = tcgen05.ld / st, UTMALDG / UTMASTG = TMA tensor loads /
-stores, UTCBAR = tcgen05.commit, SYNCS = mbarrier, HMMA = legacy mma.sync, LDGSTS = cp.async, MUFU.EX2."""
+stores, UTCBAR = tcgen05.commit, SYNCS = mbarrier, HMMA = legacy mma.sync, LDGSTS = cp.async, MUFU.EX2 / MUFU.TANH
+(softmax exponentials / the one-MUFU GELU of the GEMM epilogues), FFMA2 = packed fp32 math."""
 import collections
 import os
 import re
@@ -12,7 +13,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 lib = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "unigeo_b200", "libunigeo_b200.so")
 OPS = ["UTCHMMA", "UTCQMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UTCBAR", "SYNCS", "HMMA", "LDGSTS", "MUFU.EX2",
-       "FFMA2", "UBLKCP"]
+       "MUFU.TANH", "FFMA2", "UBLKCP"]
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
 arch = set(re.findall(r"arch = (sm_\w+)", out))
 fn, counts, size = None, collections.OrderedDict(), {}
