@@ -623,14 +623,18 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m_tile_lin = m_tile;
       const int n0 = n_tile * BN;
       const int Ncur = n_cur(n0);
-      int z1, z0, tx, ty, tn, mrest;
-      a.fd_zdiv.divmod(z, z1, z0);
-      a.fd_tx.divmod(m_tile, mrest, tx);
-      a.fd_ty.divmod(mrest, tn, ty);
+      int z1 = 0, z0 = 0, tx = m_tile, ty = 0, tn = 0, mrest;
+      if (!a.flat) {                        // (plain GEMM rows skip this chain: it sits in front of every tile's epilogue)
+        a.fd_zdiv.divmod(z, z1, z0);
+        a.fd_tx.divmod(m_tile, mrest, tx);
+        a.fd_ty.divmod(mrest, tn, ty);
+      }
       const int x0 = tx * a.bw, y0 = ty * a.bh, nn0 = tn * a.bn;
-      const bool row_ok = (ni < a.bn) && (x0 + xi < a.W) && (y0 + yi < a.H) && (nn0 + ni < a.N);
-      const long long pix = ((long long)(nn0 + ni) * a.H + (y0 + yi)) * a.W + (x0 + xi);
-      const long long zoff = (long long)z1 * a.out_z1stride + (long long)z0 * a.out_z0stride;
+      const bool row_ok = a.flat ? (x0 + r < a.W)
+                                 : (ni < a.bn) && (x0 + xi < a.W) && (y0 + yi < a.H) && (nn0 + ni < a.N);
+      const long long pix = a.flat ? (long long)(x0 + r)
+                                   : ((long long)(nn0 + ni) * a.H + (y0 + yi)) * a.W + (x0 + xi);
+      const long long zoff = a.flat ? 0ll : (long long)z1 * a.out_z1stride + (long long)z0 * a.out_z0stride;
       const long long fb_off = a.fbias ? (long long)a.fd_fb.div((int)pix) * a.fbias_ld : 0;
       const int buf = tl & 1;
       // LayerNorm folded into this GEMM: (rstd, -mean * rstd) of this thread's row, requested ahead of the accumulator
@@ -1318,6 +1322,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     args.fd_zdiv = make_fastdiv(args.zdiv);
     args.fd_fb = make_fastdiv(args.fbias_div);
     args.fd_kc = make_fastdiv(args.kchunks);
+    args.flat = (rows_flat && args.bw == BM && args.zdiv == 1 && args.ksplit <= 1) ? 1 : 0;
   }
   {
     // plain GEMMs whose activation matrix does not survive in L2 (126 MB, shared with the output stream) until the

@@ -88,6 +88,8 @@ struct TapGemmArgs {
   // filled by launch_tapgemm: divisors of the per-tile index decoding
   FastDiv fd_pm, fd_nt, fd_perz;   // M units per N tile (pairs count once), N tiles, their product
   FastDiv fd_tx, fd_ty, fd_zdiv, fd_fb, fd_kc;   // tiles_x, tiles_y, zdiv, fbias_div, kchunks
+  int flat;                // filled by launch_tapgemm: plain GEMM rows (linear ops, batch 1): pixel = M tile * 128 + row,
+                           // the epilogue skips the (x, y, n, z) decoding of a tile
   const int* sched;        // filled by launch_tapgemm: [grid units][sched_len] unit indices (-1 = none) when the host
   int sched_len;           // balanced ragged-width tiles over the CTAs (list scheduling); nullptr = round-robin
   int fmt;                 // 0 = fp16, 1 = bf16 (operands and 16-bit outputs)
