@@ -701,7 +701,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float al = a.alpha, be = 1.0f - a.alpha;
         const bool same_aux = a.blend != nullptr && a.blend == a.res && a.ldr == a.ldb;
         const bool blend_regs = a.blend != nullptr && !same_aux;
-        auto chunk_col = [&](int qq) { return (hsel + 2 * (qq >> 1)) * 64 + (qq & 1) * 32; };
+        // 32-column chunks alternate between the two column groups: a 192-wide tile splits 3 : 3 (64-column slabs
+        // alternating gave 4 : 2 and the heavier group set the tile's time)
+        auto chunk_col = [&](int qq) { return (2 * qq + hsel) * 32; };
         int nch = 0;
         while (nch < 8 && chunk_col(nch) < out_w) ++nch;
         uint8_t* ring = slabs + hsel * 2 * kSlabBytes;
