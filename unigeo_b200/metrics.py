@@ -9,7 +9,9 @@ Same names, argument names, result keys and return shapes as the reference funct
                                                       /root/reference/metrics/eval_normal.py:36-72
 Inputs may live on the host (the plugin's CPU tensors) or already on the GPU (``forward_device`` outputs),
 in which case nothing crosses PCIe but the 19 result scalars.  Only the alignment eval.py uses
-(``align_with_lstsq=True``) is implemented; the other modes of the reference raise.  No CPU path.
+(``align_with_lstsq=True``, passed explicitly at eval.py:49) is implemented.  The DEFAULT stays the reference's
+(``align_with_lstsq=False`` = median scaling, eval_depth.py:13): calling without the flag selects a mode that does not
+exist on the device and raises NotImplementedError rather than silently scoring with another alignment.  No CPU path.
 """
 from __future__ import annotations
 
