@@ -266,7 +266,7 @@ def run_b200(a):
                                      "capture): traffic not reported"}
         except (OSError, ValueError):
             pass
-        roof = {"bound": "tensor", "kernel": "tapgemm_kernel<BN> (tcgen05 implicit GEMM: conv3x3 / temporal conv / linear / attention GEMMs)",
+        roof = {"bound": "tensor", "kernel": "tapgemm_kernel<CTAS, LN> (tcgen05 implicit GEMM: conv3x3 / temporal conv / linear / attention GEMMs)",
                 "achieved": ach, "peak": peak_tf, "unit": "TFLOP/s", "frac": ach / peak_tf,
                 "traffic": traffic.get("tapgemm", {}).get("dram_bytes_per_launch"),
                 "traffic_source": traffic.get("source"),

@@ -13,7 +13,7 @@
 //
 //   Softmax reads S ONCE per block (TMEM read bandwidth, 64 B/clk, and MUFU exp2 are the binding
 //   resources): p = 2^(s*scale - m_ref) against a LAZY reference maximum m_ref.  While no row of the warp
-//   exceeds m_ref by more than 8 (p <= 256, exact in 16 bit) nothing is rescaled; otherwise (and on the
+//   pushes its row sum past 2^14 (every p then is far inside the 16-bit range) nothing is rescaled; otherwise (and on the
 //   first block) the warp takes the exact two-pass route and rescales O in TMEM (tcgen05.ld / st).  O / l is
 //   independent of the reference, so results equal the textbook formulation.
 //   P goes to smem as the 16-bit K-major A operand; V is consumed in place as an MN-major B operand.
@@ -40,13 +40,16 @@ constexpr int kOffBar = kOffP + 8 * kTile;
 constexpr int kSmem = kOffBar + 256;
 constexpr int kThreads = 320;
 constexpr uint32_t kColS = 0, kColO = 256;
+// lazy rescale: a block is taken against the stale reference maximum while its row sums stay below this (every p then
+// is below it too: far inside the 16-bit range of the P operand, 65504 in fp16); beyond it the warp takes the exact route
+constexpr float kPSumMax = 16384.0f;
 constexpr int kPolyDefault = 4;   // measured (L0, 25 x 3072 tokens): 508 us all-MUFU, 462 / 474 / 512 us with every 4th / 3rd / 2nd pair
 
 // 2^x for a pair on the FMA / ALU pipes instead of the MUFU (4 ex2 per clock and SM partition is the kernel's
 // co-binding resource next to the TMEM read port): round-to-nearest split x = r + f by the 1.5 * 2^23 trick, degree-3
 // minimax polynomial of 2^f on [-0.5, 0.5] (max relative error 7.5e-5, below the 16-bit rounding P gets anyway: 4.9e-4 fp16,
 // 3.9e-3 bf16), r added into the exponent field.  x is clamped to [-120, 126]: below, 2^x is 0 in 16 bit anyway;
-// above, the result still exceeds the rescale threshold (256), which sends the block down the exact route.
+// above, the result still exceeds the rescale threshold (kPSumMax), which sends the block down the exact route.
 __device__ __forceinline__ float2 ex2_poly2(float2 x) {
   x.x = fminf(fmaxf(x.x, -120.0f), 126.0f);
   x.y = fminf(fmaxf(x.y, -120.0f), 126.0f);
@@ -234,18 +237,10 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
         pk[i >> 1] = FMT ? Elem<__nv_bfloat16>::pack2(pp.x, pp.y) : Elem<__half>::pack2(pp.x, pp.y);
       }
       rowsum += rs2.x + rs2.y;
-      // threshold test on the packed pairs: one packed max per two elements (p >= 0, inf stays inf)
-      if (FMT) {
-        __nv_bfloat162 mx2 = *reinterpret_cast<__nv_bfloat162*>(&pk[0]);
-#pragma unroll
-        for (int i = 1; i < 16; ++i) mx2 = __hmax2(mx2, *reinterpret_cast<__nv_bfloat162*>(&pk[i]));
-        pmax = fmaxf(pmax, fmaxf(__bfloat162float(mx2.x), __bfloat162float(mx2.y)));
-      } else {
-        __half2 mx2 = *reinterpret_cast<__half2*>(&pk[0]);
-#pragma unroll
-        for (int i = 1; i < 16; ++i) mx2 = __hmax2(mx2, *reinterpret_cast<__half2*>(&pk[i]));
-        pmax = fmaxf(pmax, fmaxf(__half2float(mx2.x), __half2float(mx2.y)));
-      }
+      // The rescale test needs no maximum of its own: every p is >= 0, so the block's row sum bounds each of them
+      // (and inf / nan survive the sum).  The caller compares the sum with kPSumMax; a packed max per pair was half an
+      // instruction per score for the same decision.
+      pmax = rowsum;
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         const int c16 = c * 4 + q4;
@@ -288,7 +283,7 @@ fmha_d64_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ 
       bool exact = (j == 0);
       if (!exact) {
         compute_p(sP, m_ref, valid, rowsum, pmax);
-        exact = __any_sync(0xffffffffu, !(pmax <= 256.0f));   // also catches inf / nan
+        exact = __any_sync(0xffffffffu, !(pmax <= kPSumMax));   // also catches inf / nan
       }
       if (exact) {
         // ---- exact route: row max of this block first, then p against the updated reference
