@@ -1,10 +1,11 @@
 // tapgemm kernel + launcher (see tapgemm.cuh for what it computes and replaces).
 //
-// CTA = 192 threads, one 128 x BN output tile:
+// Persistent CTA = 320 threads walking 128 x BN output tiles (CTA pairs: 256 x BN with cta_group::2):
 //   warp 0      TMA producer   (one elected lane; A box + B box per stage, mbarrier tx-count)
 //   warp 1      TMEM owner + UMMA issuer (one elected lane; tcgen05.mma 128xBNx16, commit -> mbarrier)
-//   warps 2..5  epilogue       (tcgen05.ld 32x32b: thread = output row, registers = columns)
-// smem: STAGES x (A 128x64 + B BNx64) 16-bit tiles in the TMA/UMMA SWIZZLE_128B layout.
+//   warps 2..9  epilogue       (tcgen05.ld 32x32b: thread = output row, registers = columns; 4 TMEM lane quarters x
+//                               2 column groups), accumulator double-buffered in TMEM
+// smem: STAGES x (A 128x64 + B BNx64) 16-bit tiles in the TMA/UMMA SWIZZLE_128B layout + 4 x 16 KB store staging.
 #include "tapgemm.cuh"
 #include "ptx.cuh"
 
@@ -585,11 +586,6 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // each is an exposed L2 round trip (~1000 clk under load) per tile in a loop whose period IS the epilogue's time; here
     // the loads of tile i + 1 are issued while tile i is processed and their values wait in registers.  (Needs the cheap
     // index decoding: with ten integer divisions per decode the second decode per tile cost more than the loads.)
-#ifdef UG_NO_TILE_PREFETCH
-    constexpr bool kPrefetch = false;
-#else
-    constexpr bool kPrefetch = true;
-#endif
     const int et = threadIdx.x - 64;
     const bool have_sb = a.bias != nullptr || a.fbias_uniform;
     float pf_b = 0.f, pf_fb = 0.f, pf_c = 0.f;
@@ -674,7 +670,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (tracer) UG_TRACE(2 + hsel, tl, 1);
 #endif
       if (t_next >= 0) prefetch_tile(t_next);
-      (void)m_tile_lin; (void)kPrefetch;
+      (void)m_tile_lin;
       auto sb_at = [&](int c) -> const float* { return lnf ? sbt + 2 * c : (have_sb ? sbt + c : nullptr); };
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * 256u;
       const int BNh = BN >> 1;              // GEGLU: [BNh value | BNh gate] accumulator columns
