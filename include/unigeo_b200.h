@@ -276,6 +276,11 @@ int ug_ctx_profile_read(ug_ctx* ctx, int cap, char* names /* [cap][64] */, long 
 /* y[M][N] = x[M][K] W[N][K]^T (+bias) (+res) ; geglu: N = 2*Nout, W rows already interleaved by 64 */
 int ug_op_linear(int dtype, const void* x, long long M, int K, const void* W, int N, const float* bias,
                  const void* res, int geglu, int out_fp32, void* y, void* stream);
+/* y = alpha * blend + (1 - alpha) * (x W^T + bias (+res)): the AlphaBlender of a TransformerSpatioTemporalModel fused
+ * into the temporal block's last linear layer ([UPSTREAM] diffusers, reached from model/depthcrafter.py:80-90); blend
+ * [M][N] is a different tensor than res here (both arrive by TMA) */
+int ug_op_linear_blend(int dtype, const void* x, long long M, int K, const void* W, int N, const float* bias,
+                       const void* res, const void* blend, float alpha, void* y, void* stream);
 /* x [Nf][H][W][C], Wt [9][Cout][C] -> y [Nf][H/stride][W/stride][Cout] */
 int ug_op_conv3x3(int dtype, const void* x, int Nf, int H, int W, int C, const void* Wt, int Cout, int stride,
                   int asym_pad, const float* bias, const void* res, void* y, void* stream);

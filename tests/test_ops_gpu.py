@@ -46,6 +46,26 @@ def test_linear(cuda, dtype, M, K, N):
     check("fp32 out", y32, ref + b, dtype)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("M,K,N", [(300, 1280, 320), (6144, 1280, 320), (2500, 2560, 640), (1000, 640, 1280),
+                                   (77, 72, 200), (256, 64, 32), (4096, 256, 96)])
+def test_linear_blend_separate_tensors(cuda, dtype, M, K, N):
+    """AlphaBlender fused into the temporal block's last linear layer with the blend input a DIFFERENT tensor than the
+    residual: both tiles arrive by TMA (the epilogue's chunk ring as two buffer pairs) where the shapes allow, by
+    per-thread loads otherwise (N = 200: rows not 16-byte aligned)."""
+    from unigeo_b200 import ops
+    x = rnd((M, K), dtype, cuda, 1)
+    W = rnd((N, K), dtype, cuda, 2, 1 / math.sqrt(K))
+    b = rnd((N,), torch.float32, cuda, 3)
+    r = rnd((M, N), dtype, cuda, 4)
+    bl = rnd((M, N), dtype, cuda, 5, 2.0)
+    for alpha in (0.3, 0.85):
+        ref = alpha * bl.float() + (1 - alpha) * (x.float() @ W.float().t() + b + r.float())
+        check(f"blend+res a={alpha}", ops.linear_blend(x, W, bl, alpha, bias=b, res=r), ref, dtype)
+    ref = 0.5 * bl.float() + 0.5 * (x.float() @ W.float().t() + b)
+    check("blend only", ops.linear_blend(x, W, bl, 0.5, bias=b), ref, dtype)
+
+
 def _ln_ref(x, gamma, beta, eps):
     return F.layer_norm(x.float(), (x.shape[1],), gamma, beta, eps)
 

@@ -113,6 +113,7 @@ _SIGNATURES = {
     "ug_ctx_profile_read": ([_P, _I, C.c_char_p, C.POINTER(C.c_longlong), C.POINTER(C.c_double),
                              C.POINTER(C.c_double), C.POINTER(C.c_double)], C.c_int),
     "ug_op_linear": ([_I, _P, _L, _I, _P, _I, _P, _P, _I, _I, _P, _P], C.c_int),
+    "ug_op_linear_blend": ([_I, _P, _L, _I, _P, _I, _P, _P, _P, _F, _P, _P], C.c_int),
     "ug_op_conv3x3": ([_I, _P, _I, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P], C.c_int),
     "ug_op_tconv3": ([_I, _P, _I, _L, _I, _P, _I, _I, _P, _P, _P, _F, _P, _P], C.c_int),
     "ug_op_groupnorm": ([_I, _P, _I, _P, _I, _L, _L, _I, _P, _P, _F, _I, _P, _P], C.c_int),

@@ -917,6 +917,18 @@ int ug_op_linear(int dtype, const void* x, long long M, int K, const void* W, in
   });
 }
 
+int ug_op_linear_blend(int dtype, const void* x, long long M, int K, const void* W, int N, const float* bias,
+                       const void* res, const void* blend, float alpha, void* y, void* stream) {
+  return guard([&] {
+    UG_CHECK(x && W && blend && y, UG_ERR_INVALID, "null argument");
+    ug_ctx* u = scratch_ctx(dtype);
+    Epi e;
+    e.out = y; e.ldc = N; e.bias = bias; e.res = res; e.ldr = N; e.blend = blend; e.ldb = N; e.alpha = alpha;
+    const std::string sig = "linb:" + std::to_string(M) + ":" + std::to_string(K) + ":" + std::to_string(N) + (res ? "r" : "");
+    run_sized(u, sig, stream, [&](Ctx& c) { op_linear(c, x, M, K, K, W, N, e); });
+  });
+}
+
 int ug_op_conv3x3(int dtype, const void* x, int Nf, int H, int W, int C, const void* Wt, int Cout, int stride,
                   int asym_pad, const float* bias, const void* res, void* y, void* stream) {
   return guard([&] {

@@ -165,7 +165,8 @@ inline int imin(int a, int b) { return a < b ? a : b; }
 // algorithmic work of one tapgemm launch: 2*M*N*K flops over the REAL (unpadded) extents;
 // bytes = A read once + output written once (16-bit), weights ignored (SURVEY.md §8 convention)
 void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmArgs& a, int batch,
-            const char* what, long long k_real, const CUtensorMap* mc = nullptr, const CUtensorMap* mr = nullptr);
+            const char* what, long long k_real, const CUtensorMap* mc = nullptr, const CUtensorMap* mr = nullptr,
+            const CUtensorMap* mbl = nullptr);
 
 // Split-K launch: S partial GEMMs into fp32 workspace slabs + one reduce pass carrying the epilogue `e`.
 // `a` holds the geometry (tiling, taps, n_total, bn_tile, ctas); its epilogue fields are overwritten here.
@@ -180,6 +181,7 @@ void launch_split(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, TapGemmA
   a.fbias_uniform = 0;
   a.tma_store = 0;
   a.res_tma = 0;
+  a.blend_tma = 0;
   a.ksplit = S;
   a.out_z1stride = M * a.n_total;
   a.out_z0stride = 0;
@@ -191,7 +193,7 @@ void launch_split(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, TapGemmA
 }
 
 void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmArgs& a, int batch,
-            const char* what, long long k_real, const CUtensorMap* mc, const CUtensorMap* mr) {
+            const char* what, long long k_real, const CUtensorMap* mc, const CUtensorMap* mr, const CUtensorMap* mbl) {
   const double M = (double)a.W * a.H * a.N * (a.ksplit > 1 ? 1 : batch);
   const double flops = 2.0 * M * a.n_total * (double)k_real * a.num_taps;
   const double bytes = M * ((double)k_real + (a.geglu ? a.n_total / 2 : a.n_total)) * 2.0;
@@ -200,12 +202,12 @@ void launch(Ctx& c, const CUtensorMap& ma, const CUtensorMap& mb, const TapGemmA
     const std::string full = std::string(what) + " M" + std::to_string((long long)M) + " N" + std::to_string(a.n_total) +
                              " K" + std::to_string(k_real * a.num_taps) + " bn" + std::to_string(a.bn_tile) + "x" +
                              std::to_string(a.ctas) + (a.res ? " +res" : "") + (a.blend ? " +blend" : "") +
-                             (a.fbias ? " +fbias" : "") + (a.tma_store ? "" : " direct") + (a.res_tma ? " rtma" : "") +
+                             (a.fbias ? " +fbias" : "") + (a.tma_store ? "" : " direct") + (a.res_tma ? " rtma" : "") + (a.blend_tma ? " btma" : "") +
                              (a.ln_stat ? " lnfold" : "") + (a.stat_out ? " +stats" : "") +
                              (a.ksplit > 1 ? " splitk" + std::to_string(a.ksplit) : "");
     name = c.prof_names.insert(full).first->c_str();
   }
-  op_check(c, launch_tapgemm(ma, mb, mc, a, batch, c.stream, mr), name, flops, bytes);
+  op_check(c, launch_tapgemm(ma, mb, mc, a, batch, c.stream, mr, mbl), name, flops, bytes);
 }
 
 }  // namespace
@@ -224,6 +226,10 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   a.fbias_uniform = (e.fbias != nullptr && (a.fbias_div % 128) == 0) ? 1 : 0;   // tiles = 128 consecutive tokens
   a.tma_store = can_tma_store(e);
   a.res_tma = can_tma_res(e, N) ? 1 : 0;
+  // the AlphaBlender input by TMA as well when it is a different tensor than the residual (UG_NO_TMA_BLEND: per-thread loads)
+  static const bool no_tma_blend = getenv("UG_NO_TMA_BLEND") != nullptr;
+  a.blend_tma = (a.res_tma && !no_tma_blend && e.blend != nullptr && !(e.blend == e.res && e.ldb == e.ldr) &&
+                 (e.ldb % 8) == 0 && (reinterpret_cast<uintptr_t>(e.blend) % 16) == 0) ? 1 : 0;
   int ksplit = 1;
   // a LayerNorm-folding launch keeps its epilogue (the split-K reduce pass does not know the fold)
   a.bn_tile = tapgemm_pick_tile(a, 1, &a.ctas, (can_split(e, N) && e.ln_stat == nullptr) ? &ksplit : nullptr);
@@ -243,7 +249,7 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
   }
   if (epi_stats) a.stat_out = e.stat_out;
   const int bn = a.bn_tile / a.ctas;
-  CUtensorMap ma, mb, mc, mr;
+  CUtensorMap ma, mb, mc, mr, mbl;
   unsigned long long dims[5] = {(unsigned long long)K, (unsigned long long)M, 1, 1, 1};
   unsigned long long st[4] = {(unsigned long long)ldx * 2, (unsigned long long)ldx * 2 * M,
                               (unsigned long long)ldx * 2 * M, (unsigned long long)ldx * 2 * M};
@@ -263,10 +269,15 @@ void op_linear(Ctx& c, const void* x, long long M, int K, long long ldx, const v
       const unsigned long long rr = (unsigned long long)e.ldr * 2;
       unsigned long long rs[4] = {rr, rr * M, rr * M, rr * M};
       make_a_map(&mr, e.res, c.fmt, od, rs, 128, 1, 1, 1, true);
+      if (a.blend_tma) {
+        const unsigned long long br = (unsigned long long)e.ldb * 2;
+        unsigned long long bs[4] = {br, br * M, br * M, br * M};
+        make_a_map(&mbl, e.blend, c.fmt, od, bs, 128, 1, 1, 1, true);
+      }
     }
   }
   launch(c, ma, mb, a, 1, e.geglu ? "tapgemm.linear_geglu" : "tapgemm.linear", K, a.tma_store ? &mc : nullptr,
-         a.res_tma ? &mr : nullptr);
+         a.res_tma ? &mr : nullptr, a.blend_tma ? &mbl : nullptr);
   if (e.stat_out != nullptr && !epi_stats) op_row_stats(c, e.out, M, N, e.stat_eps, e.stat_out);
 }
 

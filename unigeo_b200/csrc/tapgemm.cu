@@ -347,6 +347,7 @@ template <int CTAS, int LN>
 __global__ void __launch_bounds__(kThreads, 1)
 tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmBl,
                const __grid_constant__ TapGemmArgs a) {
   constexpr int kSt = CTAS == 2 ? kStages2 : kStages;
   constexpr int kStB = CTAS == 2 ? kStageBytes2 : kStageBytes;
@@ -418,6 +419,7 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     if (a.tma_store) tma_prefetch_desc(&tmC);
     if (a.res_tma) tma_prefetch_desc(&tmR);
+    if (a.blend_tma) tma_prefetch_desc(&tmBl);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -696,7 +698,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int out_w = Ncur, out_c0 = n0;
         const float al = a.alpha, be = 1.0f - a.alpha;
         const bool same_aux = a.blend != nullptr && a.blend == a.res && a.ldr == a.ldb;
-        const bool blend_regs = a.blend != nullptr && !same_aux;
+        // A blend tensor that is not the residual: by TMA too where the launcher could build its map (pairm) -- the ring
+        // then works as two (residual, blend) buffer pairs with one chunk of look-ahead -- else by per-thread loads
+        // (4 x LDG.128 per row and chunk touch 32 lines per request: +37 us on the L0 ff.net.2 of the temporal block).
+        const bool pairm = a.blend_tma != 0;
+        const bool blend_regs = a.blend != nullptr && !same_aux && !pairm;
         // 32-column chunks alternate between the two column groups: a 192-wide tile splits 3 : 3 (64-column slabs
         // alternating gave 4 : 2 and the heavier group set the tile's time)
         auto chunk_col = [&](int qq) { return (2 * qq + hsel) * 32; };
@@ -706,14 +712,26 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         uint64_t* rbar = res_bar + hsel * 4;
         const uint32_t chunk_bytes = (uint32_t)(a.bw * a.bh * a.bn) * 64u;
         auto issue_load = [&](int qq) {
+          if (pairm) {                                         // pair (it & 1): residual -> buffer 2p, blend -> 2p + 1
+            const int b = (int)((ring_it + (uint32_t)qq) & 1u) * 2;
+            mbar_arrive_expect_tx(&rbar[b], 2 * chunk_bytes);
+            tma_load_5d(ring + b * 8192, &tmR, &rbar[b], out_c0 + chunk_col(qq), x0, y0, nn0, 0);
+            tma_load_5d(ring + (b + 1) * 8192, &tmBl, &rbar[b], out_c0 + chunk_col(qq), x0, y0, nn0, 0);
+            return;
+          }
           const int b = (int)((ring_it + (uint32_t)qq) & 3u);
           mbar_arrive_expect_tx(&rbar[b], chunk_bytes);
           tma_load_5d(ring + b * 8192, &tmR, &rbar[b], out_c0 + chunk_col(qq), x0, y0, nn0, 0);
         };
         if (issuer && nch > 0) {
-          bulk_wait_group_read<1>();                           // the stores that last read these buffers are done
-          issue_load(0);
-          if (nch > 1) issue_load(1);
+          if (pairm) {
+            bulk_wait_group_read<0>();                         // the pair's residual buffer was the last one stored from
+            issue_load(0);
+          } else {
+            bulk_wait_group_read<1>();                         // the stores that last read these buffers are done
+            issue_load(0);
+            if (nch > 1) issue_load(1);
+          }
         }
         mbar_wait(&tmem_full_bar[buf], (uint32_t)(tl >> 1) & 1u);
         if (tracer) UG_TRACE(2 + hsel, tl, 1);
@@ -722,9 +740,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll 1
         for (int qq = 0; qq < nch; ++qq) {
           const uint32_t it = ring_it + (uint32_t)qq;
-          const int b = (int)(it & 3u);
+          const int b = pairm ? (int)(it & 1u) * 2 : (int)(it & 3u);
           const int c = chunk_col(qq);
-          if (issuer && qq + 2 < nch) {
+          if (!pairm && issuer && qq + 2 < nch) {
             bulk_wait_group_read<1>();                         // buffer (it + 2) & 3 was stored two chunks ago
             issue_load(qq + 2);
           }
@@ -752,7 +770,11 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) f[j] *= a.scale;
           }
           finish_cols<32, false, lnf>(f, a, pix, fb_off, out_c0 + c, sb_at(c), a.n_total - (out_c0 + c), row_ok, ln);
-          mbar_wait(&rbar[b], (it >> 2) & 1u);
+          if (pairm && issuer && qq + 1 < nch) {               // the other pair: its residual buffer left with chunk qq - 1
+            bulk_wait_group_read<0>();
+            issue_load(qq + 1);
+          }
+          mbar_wait(&rbar[b], pairm ? (it >> 1) & 1u : (it >> 2) & 1u);
           const uint32_t rowaddr = smem_u32(ring + b * 8192) + (uint32_t)r * 64u;
           const uint32_t sw = (uint32_t)((r >> 1) & 3);
 #pragma unroll
@@ -765,7 +787,9 @@ tapgemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             f[8 * j + 0] += t0.x; f[8 * j + 1] += t0.y; f[8 * j + 2] += t1.x; f[8 * j + 3] += t1.y;
             f[8 * j + 4] += t2.x; f[8 * j + 5] += t2.y; f[8 * j + 6] += t3.x; f[8 * j + 7] += t3.y;
             if (a.blend != nullptr) {
-              const uint4 bw = same_aux ? u : bq4[j];
+              uint4 bw = same_aux ? u : bq4[j];
+              if (pairm)                                       // the blend chunk sits in the pair's second buffer, same layout
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(bw.x), "=r"(bw.y), "=r"(bw.z), "=r"(bw.w) : "r"(addr + 8192u));
               const float2 s0 = unpack16x2(bw.x, a.fmt), s1 = unpack16x2(bw.y, a.fmt), s2 = unpack16x2(bw.z, a.fmt),
                            s3 = unpack16x2(bw.w, a.fmt);
               f[8 * j + 0] = al * s0.x + be * f[8 * j + 0]; f[8 * j + 1] = al * s0.y + be * f[8 * j + 1];
@@ -1265,7 +1289,8 @@ void tapgemm_set_trace(unsigned long long* dev_buf) { g_trace_buf = dev_buf; }
 #endif
 
 int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC,
-                   const TapGemmArgs& args_in, int batch, cudaStream_t stream, const CUtensorMap* tmR) {
+                   const TapGemmArgs& args_in, int batch, cudaStream_t stream, const CUtensorMap* tmR,
+                   const CUtensorMap* tmBl) {
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaSuccess;
@@ -1306,6 +1331,9 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     return (int)cudaErrorInvalidValue;             // a launch is a consumer or a producer of row statistics, never both
   const CUtensorMap& mc = tmC ? *tmC : tmA;
   const CUtensorMap& mr = tmR ? *tmR : tmA;
+  if (args.blend_tma && (tmBl == nullptr || !args.res_tma || args.blend == nullptr || args.blend == args.res))
+    return (int)cudaErrorInvalidValue;
+  const CUtensorMap& mbl = tmBl ? *tmBl : tmA;
   args.batch = batch;
   args.n_tiles = (args.n_total + args.bn_tile - 1) / args.bn_tile;
   args.stat_parts = 2 * args.n_tiles;
@@ -1341,14 +1369,15 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
     args.sched = have ? sv.dev_ptr : nullptr;
     args.sched_len = have ? sv.len : 0;
   }
-  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const TapGemmArgs);
+  using Kern = void (*)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap,
+                        const TapGemmArgs);
   static const Kern kern1[3] = {tapgemm_kernel<1, 0>, tapgemm_kernel<1, 1>, tapgemm_kernel<1, 2>};
   static const Kern kern2[3] = {tapgemm_kernel<2, 0>, tapgemm_kernel<2, 1>, tapgemm_kernel<2, 2>};
   const int ln_mode = args.ln_stat != nullptr ? 1 : args.stat_out != nullptr ? 2 : 0;
   if (ctas == 1) {
     const int grid = (int)(units < sms ? units : sms);
     return (int)launch_pdl_tag("tapgemm", kern1[ln_mode], dim3(grid), dim3(kThreads), kSmemBytes,
-                           stream, tmA, tmB, mc, mr, args);
+                           stream, tmA, tmB, mc, mr, mbl, args);
   }
   const long long slots = sms / 2;
   cudaLaunchConfig_t cfg = {};
@@ -1366,7 +1395,7 @@ int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = no_pdl ? 1 : 2;
-  return (int)cudaLaunchKernelEx(&cfg, kern2[ln_mode], tmA, tmB, mc, mr, args);
+  return (int)cudaLaunchKernelEx(&cfg, kern2[ln_mode], tmA, tmB, mc, mr, mbl, args);
 }
 
 }  // namespace ug

@@ -78,6 +78,8 @@ struct TapGemmArgs {
                            // needs a 16-bit output, ldc % 8 == 0, batch 1 and the output tensor map
   int res_tma;             // residual tiles arrive by TMA (32-column chunks, in place in the store staging ring):
                            // tmC / tmR are 32-column SWIZZLE_64B maps of the output / residual tensor
+  int blend_tma;           // (res_tma launches whose AlphaBlender input is a different tensor than the residual) the blend
+                           // tile arrives by TMA as well: the ring works as two (residual, blend) buffer pairs, tmBl = its map
   int ksplit;              // > 1: split-K -- batch == ksplit units per tile, each accumulating its share of the (tap,
                            // chunk) iterations into an fp32 partial at out + z * out_z1stride (direct stores, no fusions)
   int n_tiles, batch;      // filled by launch_tapgemm
@@ -147,7 +149,8 @@ int encode_tmap(CUtensorMap* out, const TmapDesc& d);
 // Launch (persistent, one CTA per SM); args.bn_tile must be set (tapgemm_pick_bn) and must equal the
 // row extent of the B tensor map's box.  Returns cudaError_t as int.
 int launch_tapgemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap* tmC,
-                   const TapGemmArgs& args, int batch, cudaStream_t stream, const CUtensorMap* tmR = nullptr);
+                   const TapGemmArgs& args, int batch, cudaStream_t stream, const CUtensorMap* tmR = nullptr,
+                   const CUtensorMap* tmBl = nullptr);
 
 // needs tiles_*, n_total, geglu, b_mn_major filled in; returns bn_tile and the CTA count per tile.
 // The B tensor map's box must have bn_tile / ctas rows.

@@ -38,6 +38,17 @@ def linear(x, W, bias=None, res=None, geglu=False, out_fp32=False):
     return y
 
 
+def linear_blend(x, W, blend, alpha, bias=None, res=None):
+    """alpha * blend + (1 - alpha) * (x @ W.T + bias (+res)); blend [M,N] (see ug_op_linear_blend)."""
+    d = _chk16(x, W, res, blend)
+    M, K = x.shape
+    N = W.shape[0]
+    y = torch.empty((M, N), device=x.device, dtype=x.dtype)
+    _lib.check(_lib.load().ug_op_linear_blend(d, x.data_ptr(), M, K, W.data_ptr(), N, _p(bias), _p(res), blend.data_ptr(),
+                                              float(alpha), y.data_ptr(), _s()))
+    return y
+
+
 def geglu_interleave(W, b):
     """[2H,K] (value rows | gate rows) -> 256-row tiles of [128 value | 128 gate] (what ug_ctx_finalize builds)."""
     H = W.shape[0] // 2
