@@ -377,3 +377,24 @@ def test_fastdiv_matches_integer_division():
             if 0 <= n < 2 ** 31:
                 assert lib.ug_fastdiv(d, n) == n // d, (d, n)
     assert lib.ug_fastdiv(0, 5) < 0 and lib.ug_fastdiv(3, -1) < 0
+
+
+def test_prediction_correlated_label_is_sensitive_where_the_scene_label_is_not():
+    """harness.synthetic.correlated_gt: why the parity block scores both arms against a label built from the oracle
+    arm's prediction.  Two 'arms' that differ by 1 % multiplicative noise: against a label unrelated to them the
+    least-squares alignment (metrics/alignment.py:150-167) collapses both onto nearly the same constant and Abs Rel
+    barely moves; against the correlated label the alignment keeps scale ~ 1 and Abs Rel registers the difference."""
+    from harness.synthetic import correlated_gt
+    from oracle import metrics as OM
+    g = torch.Generator().manual_seed(3)
+    ref = torch.rand(4, 48, 64, generator=g) * 8.0 + 0.9                      # depth in the adapter's range [1/1.1, 10]
+    other = ref * (1.0 + 0.01 * torch.randn(ref.shape, generator=g))
+    unrelated = {"gt_depths": torch.rand(4, 48, 64, generator=g) * 5.0 + 1.0, "gt_masks": torch.ones(4, 48, 64, dtype=torch.bool)}
+    cg = correlated_gt(ref)
+    d_unrel = abs(OM.depth_evaluation(ref, unrelated["gt_depths"], unrelated["gt_masks"])["Abs Rel"] -
+                  OM.depth_evaluation(other, unrelated["gt_depths"], unrelated["gt_masks"])["Abs Rel"])
+    a = OM.depth_evaluation(ref, cg["gt_depths"], cg["gt_masks"])
+    b = OM.depth_evaluation(other, cg["gt_depths"], cg["gt_masks"])
+    assert 0.02 < a["Abs Rel"] < 0.15                                          # neither trivial nor unrelated
+    assert abs(a["Abs Rel"] - b["Abs Rel"]) > 20 * d_unrel                     # the correlated label sees the 1 %
+    assert abs(a["Abs Rel"] - b["Abs Rel"]) > 1e-4
